@@ -1,0 +1,22 @@
+/* common.h -- internal helpers of the host side (not installed). */
+#ifndef EHYB_COMMON_H
+#define EHYB_COMMON_H
+#include <stddef.h>
+#include <stdint.h>
+#include "ehyb.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Records a printf-style message for ehyb_last_error() and returns `code`. */
+int ehyb_fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+/* Prints the last error and aborts: used by the void-returning drop-in wrappers. */
+void ehyb_die(const char *where) __attribute__((noreturn));
+
+static inline int64_t ehyb_round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,367 @@
+/*
+ * layout.c -- the Blackwell-tuned EHYB layout (host-side build, view, de-interleave).
+ *
+ * Logical content is the reference's (convert.c:247-267): an entry of permuted row r in
+ * partition p is an ELL entry iff partStart <= J < partStart+W, stored with the 16-bit
+ * window-local column J-partStart; everything else is remainder, stored with the 32-bit
+ * permuted column.  Per-row entry order is kept in both parts.  What changes is the tiling:
+ *
+ *   slice      64 consecutive rows of one partition (never straddles a partition).  Lane l of
+ *              the warp that processes the slice owns rows l and l+32 ("halves" h=0,1).
+ *   slice blob [ELL values ][ELL columns ][remainder values ][remainder columns]
+ *                w*512 B     ceil4(w)*128 B   wr*512 B          wr*256 B
+ *              ELL values     double  [k][lane][h]         one 128-bit load per lane per k
+ *              ELL columns    uint16  [k/4][lane][h][k%4]  one 128-bit load per lane per 4 k
+ *              rem. values    double  [k][lane][h]
+ *              rem. columns   int32   [k][lane][h]         one 64-bit load per lane per k
+ *              Every region is a multiple of 256 bytes, so slices start 256-byte aligned and
+ *              a slice is addressed by a 32-bit offset in 256-byte units.
+ *   w          max in-window count over the slice's rows (the reference's rule, per 64 rows)
+ *   wr         in-slice remainder width: the ceil(er_fill*64)-th largest spill count of the
+ *              slice (er_fill=0: the largest).  Spill beyond wr, and whole "long" rows (more
+ *              than long_row_threshold in-window entries at a partition head, the
+ *              reference's longVec rule), go to the overflow list.
+ *   overflow   COO (row, col, val), sorted by row, entry order kept; reduced on the device
+ *              by a segmented warp reduction and added to y.
+ *
+ * Unlike the reference layout (W/32 slices per partition, rows beyond the window in a
+ * separate global list) every row of a partition belongs to a slice here: a row beyond the
+ * window simply has no ELL entries.
+ */
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.h"
+#include "convert.h"
+#include "kernel.h"
+
+#define SR EHYB_SLICE_ROWS
+
+struct ehyb_layout {
+    ehyb_layout_view v;
+    ehyb_part_desc *parts;
+    ehyb_slice_desc *slices;
+    unsigned char *blob;
+    int32_t *ovfRow, *ovfCol;
+    double *ovfVal;
+    /* host-only bookkeeping for the de-interleave */
+    int32_t *rowEll;   /* [n] ELL entries of the row */
+    int32_t *rowRemIn; /* [n] remainder entries kept in the slice */
+    int64_t *ovfPtr;   /* [n+1] overflow entries of the row */
+};
+
+int ehyb_convert_reference_layout(const matrixCOO *in, matrixEHYB *out, int *sizeBlockELL, int *sizeER, int quiet);
+
+void ehyb_layout_free(ehyb_layout *L)
+{
+    if (!L) return;
+    free(L->parts); free(L->slices); free(L->blob);
+    free(L->ovfRow); free(L->ovfCol); free(L->ovfVal);
+    free(L->rowEll); free(L->rowRemIn); free(L->ovfPtr);
+    free(L);
+}
+
+int ehyb_layout_get(const ehyb_layout *L, ehyb_layout_view *view)
+{
+    if (!L || !view) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_get: NULL argument");
+    *view = L->v;
+    return EHYB_OK;
+}
+
+/* byte offsets of the four regions inside a slice */
+static inline int64_t reg_ell_col(int w) { return (int64_t)w * 512; }
+static inline int64_t reg_rem_val(int w) { return (int64_t)w * 512 + (int64_t)((w + 3) / 4) * 512; }
+static inline int64_t reg_rem_col(int w, int wr) { return reg_rem_val(w) + (int64_t)wr * 512; }
+static inline int64_t slice_bytes(int w, int wr) { return reg_rem_col(w, wr) + (int64_t)wr * 256; }
+
+static int cmp_int_desc(const void *a, const void *b) { return *(const int *)b - *(const int *)a; }
+
+int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col, const double *val, int nParts,
+                          const int32_t *pb, const ehyb_layout_opts *opts, ehyb_layout **out)
+{
+    if (!rowPtr || !col || !val || !pb || !opts || !out || n64 <= 0 || n64 > INT_MAX || nParts <= 0)
+        return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_build: bad argument");
+    const int n = (int)n64, P = nParts, W = opts->W;
+    const int64_t ncols = opts->ncols > 0 ? opts->ncols : n;
+    const int longThr = opts->long_row_threshold > 0 ? opts->long_row_threshold : EHYB_REF_LONG_ROW;
+    const double fill = opts->er_fill < 0 ? 0.5 : opts->er_fill;
+    int need = (int)ceil(fill * SR);
+    if (need < 1) need = 1;
+    if (need > SR) need = SR;
+    if (W <= 0 || W > 65536) return ehyb_fail(EHYB_ERR_LIMIT, "window %d outside (0, 65536]: column indices are 16-bit", W);
+    if (ncols < n || ncols > INT_MAX) return ehyb_fail(EHYB_ERR_ARG, "ncols %lld must be in [n, 2^31)", (long long)ncols);
+    if (pb[0] != 0 || pb[P] != n) return ehyb_fail(EHYB_ERR_ARG, "partBoundary must run from 0 to n");
+    for (int p = 0; p < P; ++p)
+        if (pb[p] > pb[p + 1]) return ehyb_fail(EHYB_ERR_ARG, "partBoundary not monotone at %d", p);
+
+    ehyb_layout *L = (ehyb_layout *)calloc(1, sizeof *L);
+    if (!L) return ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory");
+    int rc = EHYB_OK;
+    int64_t *sliceOff = NULL;
+    L->parts = (ehyb_part_desc *)calloc((size_t)P, sizeof(ehyb_part_desc));
+    L->rowEll = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+    L->rowRemIn = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+    L->ovfPtr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
+    if (!L->parts || !L->rowEll || !L->rowRemIn || !L->ovfPtr) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
+
+    int nSlices = 0;
+    for (int p = 0; p < P; ++p) {
+        L->parts[p].rowStart = pb[p];
+        L->parts[p].rowEnd = pb[p + 1];
+        L->parts[p].sliceStart = nSlices;
+        nSlices += (pb[p + 1] - pb[p] + SR - 1) / SR;
+        L->parts[p].sliceEnd = nSlices;
+    }
+    L->slices = (ehyb_slice_desc *)calloc((size_t)(nSlices ? nSlices : 1), sizeof(ehyb_slice_desc));
+    sliceOff = (int64_t *)calloc((size_t)nSlices + 1, sizeof(int64_t));
+    if (!L->slices || !sliceOff) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
+
+    /* pass 1: classify rows, choose slice widths */
+    int64_t nnzEll = 0, nnzRemIn = 0, nnzOvf = 0, padEll = 0, padRem = 0, nLong = 0;
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nnzEll, nnzRemIn, nnzOvf, padEll, padRem, nLong) reduction(| : bad)
+    for (int p = 0; p < P; ++p) {
+        const int ps = pb[p], pe = pb[p + 1];
+        const int64_t winEnd = (int64_t)ps + W < n ? (int64_t)ps + W : n;
+        int firstReg = ps, scanning = 1;
+        for (int r = ps; r < pe; ++r) {
+            int ell = 0;
+            for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
+                const int c = col[e];
+                if (c < 0 || c >= ncols) bad = 1;
+                ell += (c >= ps && c < winEnd);
+            }
+            if (scanning && ell > longThr) { /* long rows sit at the head of the partition */
+                firstReg = r + 1;
+                L->rowEll[r] = -1;
+                continue;
+            }
+            scanning = 0;
+            L->rowEll[r] = ell;
+        }
+        nLong += firstReg - ps;
+        for (int s = L->parts[p].sliceStart; s < L->parts[p].sliceEnd; ++s) {
+            const int r0 = ps + (s - L->parts[p].sliceStart) * SR;
+            const int r1 = r0 + SR < pe ? r0 + SR : pe;
+            int w = 0, m = 0, rem[SR];
+            for (int r = r0; r < r1; ++r) {
+                if (L->rowEll[r] < 0) continue;
+                if (L->rowEll[r] > w) w = L->rowEll[r];
+                const int64_t sp = rowPtr[r + 1] - rowPtr[r] - L->rowEll[r];
+                rem[m++] = sp > 65535 ? 65535 : (int)sp;
+            }
+            qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
+            const int wr = m >= need ? rem[need - 1] : 0;
+            if (w > 65535) bad = 1;
+            L->slices[s].w = (uint16_t)w;
+            L->slices[s].wr = (uint16_t)wr;
+            sliceOff[s + 1] = slice_bytes(w, wr);
+            int64_t sumE = 0, sumR = 0;
+            for (int r = r0; r < r1; ++r) {
+                const int64_t len = rowPtr[r + 1] - rowPtr[r];
+                if (L->rowEll[r] < 0) { /* long row: everything overflows */
+                    L->ovfPtr[r + 1] = len;
+                    nnzOvf += len;
+                    continue;
+                }
+                const int64_t sp = len - L->rowEll[r];
+                const int in = sp < wr ? (int)sp : wr;
+                L->rowRemIn[r] = in;
+                L->ovfPtr[r + 1] = sp - in;
+                sumE += L->rowEll[r];
+                sumR += in;
+                nnzOvf += sp - in;
+            }
+            nnzEll += sumE;
+            nnzRemIn += sumR;
+            padEll += (int64_t)SR * w - sumE;
+            padRem += (int64_t)SR * wr - sumR;
+        }
+    }
+    if (bad) { rc = ehyb_fail(EHYB_ERR_ARG, "layout: a column index is outside [0, ncols) or a slice is wider than 65535"); goto fail; }
+
+    for (int s = 0; s < nSlices; ++s) {
+        if (sliceOff[s] / 256 > (int64_t)UINT32_MAX) { rc = ehyb_fail(EHYB_ERR_LIMIT, "layout larger than 1 TiB"); goto fail; }
+        L->slices[s].off256 = (uint32_t)(sliceOff[s] / 256);
+        sliceOff[s + 1] += sliceOff[s];
+    }
+    const int64_t blobBytes = sliceOff[nSlices];
+    for (int r = 0; r < n; ++r) L->ovfPtr[r + 1] += L->ovfPtr[r];
+    const int64_t nOvf = L->ovfPtr[n];
+    if (nOvf > INT_MAX) { rc = ehyb_fail(EHYB_ERR_LIMIT, "overflow list exceeds 2^31 entries"); goto fail; }
+
+    L->blob = (unsigned char *)calloc((size_t)(blobBytes ? blobBytes : 256), 1);
+    L->ovfRow = (int32_t *)malloc((size_t)(nOvf ? nOvf : 1) * sizeof(int32_t));
+    L->ovfCol = (int32_t *)malloc((size_t)(nOvf ? nOvf : 1) * sizeof(int32_t));
+    L->ovfVal = (double *)malloc((size_t)(nOvf ? nOvf : 1) * sizeof(double));
+    if (!L->blob || !L->ovfRow || !L->ovfCol || !L->ovfVal) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory (%lld bytes)", (long long)blobBytes); goto fail; }
+
+    /* pass 2: fill.  Padding stays zero (value 0.0, column 0: a valid window/global index). */
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int p = 0; p < P; ++p) {
+        const int ps = pb[p], pe = pb[p + 1];
+        const int64_t winEnd = (int64_t)ps + W < n ? (int64_t)ps + W : n;
+        for (int s = L->parts[p].sliceStart; s < L->parts[p].sliceEnd; ++s) {
+            const int r0 = ps + (s - L->parts[p].sliceStart) * SR;
+            const int r1 = r0 + SR < pe ? r0 + SR : pe;
+            const int w = L->slices[s].w, wr = L->slices[s].wr;
+            unsigned char *base = L->blob + sliceOff[s];
+            double *ev = (double *)base;
+            uint16_t *ec = (uint16_t *)(base + reg_ell_col(w));
+            double *rv = (double *)(base + reg_rem_val(w));
+            int32_t *rcol = (int32_t *)(base + reg_rem_col(w, wr));
+            for (int r = r0; r < r1; ++r) {
+                const int t = r - r0, lane = t % 32, h = t / 32;
+                const int isLong = L->rowEll[r] < 0;
+                int kE = 0, kR = 0;
+                int64_t o = L->ovfPtr[r];
+                for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
+                    const int c = col[e];
+                    if (!isLong && c >= ps && c < winEnd) {
+                        ev[((int64_t)kE * 32 + lane) * 2 + h] = val[e];
+                        ec[(((int64_t)(kE / 4) * 32 + lane) * 2 + h) * 4 + kE % 4] = (uint16_t)(c - ps);
+                        ++kE;
+                    } else if (!isLong && kR < wr) {
+                        rv[((int64_t)kR * 32 + lane) * 2 + h] = val[e];
+                        rcol[((int64_t)kR * 32 + lane) * 2 + h] = c;
+                        ++kR;
+                    } else {
+                        L->ovfRow[o] = r;
+                        L->ovfCol[o] = c;
+                        L->ovfVal[o] = val[e];
+                        ++o;
+                    }
+                }
+            }
+        }
+    }
+    for (int r = 0; r < n; ++r)
+        if (L->rowEll[r] < 0) L->rowEll[r] = 0; /* long rows own no ELL entries; flagged via rowRemIn = -1 */
+    /* (long rows are recognisable afterwards as rows whose overflow count equals their length
+     *  and exceeds the threshold; the de-interleave recomputes it from the columns) */
+
+    ehyb_layout_view *v = &L->v;
+    v->n = n; v->ncols = ncols; v->nnz = rowPtr[n];
+    v->nParts = P; v->W = W; v->ctasPerPart = opts->ctasPerPart > 0 ? opts->ctasPerPart : 1; v->nSlices = nSlices;
+    v->parts = L->parts; v->slices = L->slices; v->blob = L->blob; v->blobBytes = blobBytes;
+    v->nOverflow = nOvf; v->ovfRow = L->ovfRow; v->ovfCol = L->ovfCol; v->ovfVal = L->ovfVal;
+    v->nnzEll = nnzEll; v->nnzRemInSlice = nnzRemIn; v->nnzOverflow = nnzOvf;
+    v->padEll = padEll; v->padRem = padRem; v->nLongRows = nLong;
+    v->algBytes = 8 * v->nnz + 2 * nnzEll + 4 * (v->nnz - nnzEll) + 8 * ncols + 8 * (int64_t)n;
+    v->formatBytes = blobBytes + (int64_t)nSlices * (int64_t)sizeof(ehyb_slice_desc) +
+                     (int64_t)P * (int64_t)sizeof(ehyb_part_desc) + nOvf * 16;
+    if (nnzEll + nnzRemIn + nnzOvf != v->nnz) { rc = ehyb_fail(EHYB_ERR_ARG, "layout: entry count mismatch"); goto fail; }
+    free(sliceOff);
+    *out = L;
+    return EHYB_OK;
+
+fail:
+    free(sliceOff);
+    ehyb_layout_free(L);
+    return rc;
+}
+
+int ehyb_layout_build(const matrixCOO *m, const ehyb_layout_opts *opts_in, ehyb_layout **out)
+{
+    if (!m || !out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_build: NULL argument");
+    ehyb_layout_opts o;
+    if (opts_in) o = *opts_in;
+    else { memset(&o, 0, sizeof o); o.er_fill = 0.5; }
+    if (o.W <= 0) o.W = m->vectorCacheSize;
+    if (o.ctasPerPart <= 0) o.ctasPerPart = m->kernelPerPart > 0 ? m->kernelPerPart : 1;
+    const int n = m->dimension;
+    if (n <= 0 || !m->rowIdx || !m->partBoundary) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_build: matrix not reordered");
+    int64_t *ptr = (int64_t *)malloc(((size_t)n + 1) * sizeof(int64_t));
+    if (!ptr) return ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory");
+    for (int i = 0; i <= n; ++i) ptr[i] = m->rowIdx[i];
+    int rc = EHYB_OK;
+    for (int64_t e = 0; e + 1 < m->totalNum && rc == EHYB_OK; ++e)
+        if (m->I[e] > m->I[e + 1]) rc = ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_build: entries are not row-sorted");
+    if (rc == EHYB_OK) rc = ehyb_layout_build_csr(n, ptr, m->J, m->V, m->nParts, m->partBoundary, &o, out);
+    free(ptr);
+    return rc;
+}
+
+/* ---------------------------------------------------------------------------------- */
+/* de-interleave: tuned layout -> reference layout                                     */
+/* ---------------------------------------------------------------------------------- */
+
+int ehyb_layout_to_reference(const ehyb_layout *L, matrixEHYB *out, int *sizeBlockELL, int *sizeER)
+{
+    if (!L || !out || !sizeBlockELL || !sizeER) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_to_reference: NULL argument");
+    const ehyb_layout_view *v = &L->v;
+    if (v->nnz > INT_MAX || v->ncols != v->n) return ehyb_fail(EHYB_ERR_LIMIT, "reference layout needs nnz < 2^31 and no halo columns");
+    const int n = (int)v->n, P = v->nParts;
+    const int64_t nnz = v->nnz;
+    matrixCOO c;
+    memset(&c, 0, sizeof c);
+    c.dimension = n; c.totalNum = (int)nnz; c.nParts = P; c.vectorCacheSize = (uint16_t)v->W; c.kernelPerPart = (int16_t)v->ctasPerPart;
+    c.rowIdx = (int *)malloc(((size_t)n + 1) * sizeof(int));
+    c.numInRow = (int *)malloc((size_t)n * sizeof(int));
+    c.numInRow2 = (int *)calloc((size_t)n, sizeof(int));
+    c.I = (int *)malloc((size_t)(nnz ? nnz : 1) * sizeof(int));
+    c.J = (int *)malloc((size_t)(nnz ? nnz : 1) * sizeof(int));
+    c.V = (double *)malloc((size_t)(nnz ? nnz : 1) * sizeof(double));
+    c.partBoundary = (int *)malloc(((size_t)P + 1) * sizeof(int));
+    int rc = EHYB_OK;
+    if (!c.rowIdx || !c.numInRow || !c.numInRow2 || !c.I || !c.J || !c.V || !c.partBoundary) {
+        rc = ehyb_fail(EHYB_ERR_NOMEM, "de-interleave: out of memory");
+        goto done;
+    }
+    for (int p = 0; p < P; ++p) c.partBoundary[p] = v->parts[p].rowStart;
+    c.partBoundary[P] = n;
+    c.rowIdx[0] = 0;
+    for (int r = 0; r < n; ++r) {
+        c.numInRow[r] = L->rowEll[r] + L->rowRemIn[r] + (int)(L->ovfPtr[r + 1] - L->ovfPtr[r]);
+        c.rowIdx[r + 1] = c.rowIdx[r] + c.numInRow[r];
+    }
+    if (c.rowIdx[n] != nnz) { rc = ehyb_fail(EHYB_ERR_ARG, "de-interleave: count mismatch"); goto done; }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int p = 0; p < P; ++p) {
+        const int ps = v->parts[p].rowStart, pe = v->parts[p].rowEnd;
+        for (int s = v->parts[p].sliceStart; s < v->parts[p].sliceEnd; ++s) {
+            const int r0 = ps + (s - v->parts[p].sliceStart) * SR;
+            const int r1 = r0 + SR < pe ? r0 + SR : pe;
+            const int w = v->slices[s].w, wr = v->slices[s].wr;
+            const unsigned char *base = v->blob + (int64_t)v->slices[s].off256 * 256;
+            const double *ev = (const double *)base;
+            const uint16_t *ec = (const uint16_t *)(base + reg_ell_col(w));
+            const double *rv = (const double *)(base + reg_rem_val(w));
+            const int32_t *rcol = (const int32_t *)(base + reg_rem_col(w, wr));
+            for (int r = r0; r < r1; ++r) {
+                const int t = r - r0, lane = t % 32, h = t / 32;
+                int dst = c.rowIdx[r];
+                /* ELL entries first, then the remainder: the reference layout depends on the
+                 * order inside each class only */
+                for (int k = 0; k < L->rowEll[r]; ++k, ++dst) {
+                    c.I[dst] = r;
+                    c.J[dst] = ps + ec[(((int64_t)(k / 4) * 32 + lane) * 2 + h) * 4 + k % 4];
+                    c.V[dst] = ev[((int64_t)k * 32 + lane) * 2 + h];
+                }
+                for (int k = 0; k < L->rowRemIn[r]; ++k, ++dst) {
+                    c.I[dst] = r;
+                    c.J[dst] = rcol[((int64_t)k * 32 + lane) * 2 + h];
+                    c.V[dst] = rv[((int64_t)k * 32 + lane) * 2 + h];
+                }
+                for (int64_t o = L->ovfPtr[r]; o < L->ovfPtr[r + 1]; ++o, ++dst) {
+                    c.I[dst] = v->ovfRow[o];
+                    c.J[dst] = v->ovfCol[o];
+                    c.V[dst] = v->ovfVal[o];
+                }
+                int inw = 0;
+                for (int e = c.rowIdx[r]; e < c.rowIdx[r + 1]; ++e) inw += (c.J[e] >= ps && c.J[e] < ps + v->W);
+                c.numInRow2[r] = inw;
+            }
+        }
+    }
+    rc = ehyb_convert_reference_layout(&c, out, sizeBlockELL, sizeER, 1);
+    if (rc == EHYB_OK) {
+        out->partBoundary = c.partBoundary; /* owned by the caller now */
+        c.partBoundary = NULL;
+    }
+done:
+    free(c.rowIdx); free(c.numInRow); free(c.numInRow2); free(c.I); free(c.J); free(c.V); free(c.partBoundary);
+    return rc;
+}

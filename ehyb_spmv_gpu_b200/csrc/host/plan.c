@@ -1,0 +1,125 @@
+/*
+ * plan.c -- partition-parameter choice.
+ *
+ * The reference picks (nParts, vectorCacheSize, kernelPerPart) in the reader from
+ * compile-time constants of an 82-SM / 93 KB device (solver_test.c:158-182, kernel.h:20-25)
+ * and stores the window in a 16-bit integer, which wraps for n > ~2.6 M (SURVEY.md B-7,
+ * Appendix C).  ehyb_plan() derives the parameters from the queried device instead:
+ *
+ *   - `ctasPerSM` CTAs are meant to be resident per SM, so one CTA may use
+ *     smem_per_sm/ctasPerSM - 1 KB (the per-CTA reservation) of shared memory for its x window;
+ *   - the number of partitions is a multiple of the SM count, so every SM streams the same
+ *     number of partitions (one wave, no tail);
+ *   - the window is sized from the partition size with 2.5 % head-room for the partitioner's
+ *     imbalance (mt-metis: <= 0.1 % on stencils, 3 % on the elasticity graph)
+ *     - rows beyond the window still work, they just have no ELL entries;
+ *   - matrices too small to give every SM `minRows` rows get fewer partitions and several
+ *     CTAs per partition (the reference's "_small" idea).
+ *
+ * Tunables can be overridden through the environment for experiments:
+ * EHYB_PARTS_PER_SM, EHYB_CTAS_PER_SM, EHYB_THREADS, EHYB_CTAS_PER_PART.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.h"
+
+void ehyb_device_info_b200(ehyb_device_info *d)
+{
+    memset(d, 0, sizeof *d);
+    d->device = -1;
+    d->sm_count = 148;
+    d->smem_optin_bytes = 232448;  /* 227 KB */
+    d->smem_per_sm_bytes = 233472; /* 228 KB */
+    d->l2_bytes = 126 * 1024 * 1024;
+    d->max_persist_l2_bytes = 79 * 1024 * 1024;
+    d->cc_major = 10;
+    d->cc_minor = 0;
+    d->hbm_bytes = (size_t)183359 * 1024 * 1024;
+    strcpy(d->name, "NVIDIA B200 (nominal)");
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return s && s[0] ? atoi(s) : dflt;
+}
+
+#define EHYB_SMEM_RESERVE 128 /* mbarrier + scheduler words in front of the window */
+
+int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out)
+{
+    if (n <= 0 || !dev || !out || dev->sm_count <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan: bad argument");
+    const int sms = dev->sm_count;
+    int partsPerSM = env_int("EHYB_PARTS_PER_SM", 2);
+    int ctasPerSM = env_int("EHYB_CTAS_PER_SM", 2);
+    int threads = env_int("EHYB_THREADS", 512);
+    if (partsPerSM < 1) partsPerSM = 1;
+    if (ctasPerSM < 1) ctasPerSM = 1;
+    if (threads < 64 || threads > 1024 || threads % 32) threads = 512;
+    const int minRows = 2048; /* below this a partition's window no longer amortises its load */
+
+    /* largest window one CTA can hold with ctasPerSM CTAs resident */
+    long budget = dev->smem_per_sm_bytes / ctasPerSM - 1024;
+    if (budget > dev->smem_optin_bytes) budget = dev->smem_optin_bytes;
+    int wMax = (int)((budget - EHYB_SMEM_RESERVE) / 8 - 2);
+    wMax -= wMax % 64;
+    if (wMax > 65536) wMax = 65536;
+    if (wMax < 64) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan: no shared memory for a window");
+
+    int P = sms * partsPerSM, kpp = 1;
+    if ((double)n / P < minRows) {
+        /* small matrix: fewer partitions, several CTAs each, still ~ctasPerSM CTAs per SM */
+        P = (n + minRows - 1) / minRows;
+        if (P < 1) P = 1;
+        kpp = (sms * ctasPerSM + P - 1) / P;
+        if (kpp < 1) kpp = 1;
+        if (kpp > 32) kpp = 32;
+    }
+    /* grow P (in multiples of the SM count) until the partitions fit the window */
+    while (ceil((double)n / P * 1.025) > wMax) P += sms;
+    int W = (int)ceil((double)n / P * 1.025);
+    W = (W + 63) / 64 * 64;
+    if (W > wMax) W = wMax;
+    kpp = env_int("EHYB_CTAS_PER_PART", kpp);
+    if (kpp < 1) kpp = 1;
+    out->nParts = P;
+    out->W = W;
+    out->ctasPerPart = kpp;
+    out->threads = threads;
+    out->ctasPerSM = ctasPerSM;
+    return EHYB_OK;
+}
+
+int ehyb_plan_reference(int n, int symmetric, ehyb_plan_t *out)
+{
+    if (n <= 0 || !out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan_reference: bad argument");
+    /* kernel.h:21-25 */
+    const int sm = 82, sm2 = 80, tpb = 1024;
+    const size_t maxShared = 93 * 1024;
+    int factor = 1, kpp = 0;
+    /* the window lives in an int16_t (solver_test.c:55,160): out-of-range doubles wrap */
+#define WRAP16(d) ((int16_t)(int32_t)(d))
+    int16_t w = WRAP16(ceil((double)n / ((double)factor * sm * tpb)) * tpb);
+    if ((size_t)(long)w < maxShared / (2 * sizeof(double))) {
+        static const int ks[4] = {8, 5, 4, 2};
+        int i = 0;
+        do {
+            kpp = ks[i++];
+            w = WRAP16(kpp * ceil((double)n / ((double)sm2 * tpb)) * tpb);
+        } while ((size_t)(long)w * sizeof(double) > maxShared && i < 4);
+        out->nParts = (symmetric ? sm2 : sm) / kpp; /* solver_test.c:173 vs :68 */
+    } else {
+        while ((size_t)(long)w * sizeof(double) > maxShared) {
+            factor += 1;
+            w = WRAP16(ceil((double)n / ((double)factor * sm * tpb)) * tpb);
+        }
+        out->nParts = factor * sm;
+    }
+#undef WRAP16
+    out->W = (int)(uint16_t)w;
+    out->ctasPerPart = kpp;
+    out->threads = tpb;
+    out->ctasPerSM = 1;
+    return EHYB_OK;
+}

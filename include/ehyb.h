@@ -1,0 +1,260 @@
+/*
+ * ehyb.h -- C ABI of the B200-native EHYB SpMV engine (libehyb.so).
+ *
+ * Everything here is new relative to the reference; the reference's own entry points stay
+ * available under their old names (spmv.h, kernel.h, convert.h, reordering.h, mmio.h) and are
+ * thin wrappers over this layer.  Conventions: plain C, plain pointers and sizes; every
+ * function returns EHYB_OK (0) or a negative ehyb_status and never calls exit();
+ * ehyb_last_error() gives the message of the last failure on the calling thread.
+ *
+ * Which reference interface each group replaces:
+ *   device / plan      solver_test.c:158-182, :53-77 (partition-parameter heuristic built on
+ *                      kernel.h:20-25 compile-time constants)
+ *   graph / reorder    reordering.c:41-228, :231-378 (split so that the partition vector can
+ *                      be injected; matrixReorder* are wrappers)
+ *   layout             convert.c:316-369 (COO2EHYB) - emits the Blackwell-tuned layout
+ *   session            spmv.cu:6-60 (cudaMallocTransDataEHYB), spmv.cu:61-133 (spmvGPuEHYB),
+ *                      kernel.cu:324-380, :490-518 (matrixVectorEHYB launchers)
+ *   multi-GPU          none (new layer)
+ */
+#ifndef EHYB_H
+#define EHYB_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "spmv.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum ehyb_status {
+    EHYB_OK = 0,
+    EHYB_ERR_ARG = -1,       /* invalid argument / inconsistent input */
+    EHYB_ERR_NOMEM = -2,     /* host allocation failed */
+    EHYB_ERR_CUDA = -3,      /* a CUDA call failed, or no CUDA device */
+    EHYB_ERR_PARTITION = -4, /* the partitioner failed or is not available */
+    EHYB_ERR_IO = -5,        /* file problem */
+    EHYB_ERR_LIMIT = -6,     /* a format limit was exceeded (e.g. window larger than 65536) */
+    EHYB_ERR_NCCL = -7       /* an NCCL call failed */
+} ehyb_status;
+
+const char *ehyb_last_error(void);
+const char *ehyb_version(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* device query and partition-parameter plan                                              */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct ehyb_device_info {
+    int device;
+    int sm_count;             /* 148 on B200 */
+    int smem_optin_bytes;     /* max dynamic shared memory per CTA (232448 on B200) */
+    int smem_per_sm_bytes;    /* 233472 on B200 */
+    int l2_bytes;
+    int cc_major, cc_minor;
+    int max_persist_l2_bytes; /* cudaDevAttrMaxPersistingL2CacheSize */
+    size_t hbm_bytes;
+    char name[64];
+} ehyb_device_info;
+
+int ehyb_device_count(int *count);
+int ehyb_device_query(int device, ehyb_device_info *out);
+/* Nominal B200 values, so that host-side planning and format build can run without a GPU. */
+void ehyb_device_info_b200(ehyb_device_info *out);
+
+typedef struct ehyb_plan_t {
+    int nParts;      /* P */
+    int W;           /* x window length in elements (vectorCacheSize) */
+    int ctasPerPart; /* kernelPerPart */
+    int threads;     /* threads per CTA */
+    int ctasPerSM;   /* resident CTAs per SM the plan was sized for */
+} ehyb_plan_t;
+
+/* B200 plan from the matrix size and the device (replaces solver_test.c:158-182). */
+int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out);
+/* The reference's own heuristic for an 82/80-SM, 93 KB device, including its int16_t wrap
+ * (SURVEY.md Appendix C).  ctasPerPart = 0 where the reference leaves it uninitialised. */
+int ehyb_plan_reference(int n, int symmetric, ehyb_plan_t *out);
+
+/* ------------------------------------------------------------------------------------ */
+/* graph, partition, reorder                                                              */
+/* ------------------------------------------------------------------------------------ */
+
+/* Graph handed to the partitioner.  symmetric: xadj = rowIdx, adjncy = J (self loops kept),
+ * reordering.c:239-264.  Otherwise the pattern of A + A^T with duplicates kept,
+ * reordering.c:50-89.  *xadj / *adjncy are malloc'd; free with ehyb_free_host. */
+int ehyb_build_graph(const matrixCOO *m, int symmetric, uint32_t **xadj, uint32_t **adjncy);
+
+/* Partitioner hook.  The default runs the pinned mt-metis binary (third_party/mtmetis) out of
+ * process through bin/ehyb_mtmetis (path: $EHYB_MTMETIS_BIN, else next to libehyb.so);
+ * bin/spmv.out installs an in-process call.  ubvec 1.001, ncon 1, no weights, as the
+ * reference (reordering.c:270-293). */
+typedef int (*ehyb_partition_fn)(uint32_t nvtxs, const uint32_t *xadj, const uint32_t *adjncy,
+                                 uint32_t nparts, uint32_t nthreads, float ubvec, uint32_t *where,
+                                 void *user);
+void ehyb_set_partitioner(ehyb_partition_fn fn, void *user);
+int ehyb_partition_graph(uint32_t nvtxs, const uint32_t *xadj, const uint32_t *adjncy,
+                         uint32_t nparts, uint32_t nthreads, uint32_t *where);
+
+/* Everything of matrixReorder after the mt-metis call (reordering.c:299-377), for a given
+ * partition vector partVec[old row] in [0, nParts).  Same in/out contract as matrixReorder. */
+int ehyb_reorder_with_partition(matrixCOO *m, const uint32_t *partVec);
+/* Status-returning matrixReorder / matrixReorder_unsym. */
+int ehyb_reorder(matrixCOO *m, int symmetric);
+/* Contiguous-block partition vector (rows [i*n/P, (i+1)*n/P) -> part i): the structured-grid
+ * alternative used for per-GPU slabs and very large grids where mt-metis is impractical. */
+int ehyb_partition_blocks(uint32_t n, uint32_t nparts, uint32_t *where);
+
+void ehyb_free_host(void *p);
+
+/* ------------------------------------------------------------------------------------ */
+/* Blackwell-tuned device layout (host side)                                              */
+/* ------------------------------------------------------------------------------------ */
+
+#define EHYB_SLICE_ROWS 64 /* rows per slice: lane l owns rows l and l+32 of the slice */
+
+typedef struct ehyb_layout ehyb_layout;
+
+typedef struct ehyb_layout_opts {
+    int W;                  /* x window length; 0 = matrixCOO.vectorCacheSize */
+    int ctasPerPart;        /* 0 = matrixCOO.kernelPerPart (min 1) */
+    double er_fill;         /* in-slice remainder column kept while >= er_fill*64 rows use it;
+                               0 = keep every remainder entry in its slice; default 0.5 */
+    int long_row_threshold; /* rows at a partition head with more in-window entries than this go
+                               whole to the overflow list; 0 = 512 (reference threadLongVec) */
+    int64_t ncols;          /* columns of the local operator (n + halo); 0 = n */
+} ehyb_layout_opts;
+
+typedef struct ehyb_slice_desc {
+    uint32_t off256; /* byte offset of the slice in the blob / 256 */
+    uint16_t w;      /* ELL width (columns), 16-bit window-local indices */
+    uint16_t wr;     /* in-slice remainder width, 32-bit column indices */
+} ehyb_slice_desc;
+
+typedef struct ehyb_part_desc {
+    int32_t rowStart, rowEnd;     /* permuted rows of the partition */
+    int32_t sliceStart, sliceEnd; /* its slices */
+} ehyb_part_desc;
+
+/* Read-only view of a built layout (pointers stay owned by the layout). */
+typedef struct ehyb_layout_view {
+    int64_t n, ncols, nnz;
+    int32_t nParts, W, ctasPerPart, nSlices;
+    const ehyb_part_desc *parts;   /* [nParts] */
+    const ehyb_slice_desc *slices; /* [nSlices] */
+    const unsigned char *blob;     /* [blobBytes] slice data, see DESIGN.md "data layout" */
+    int64_t blobBytes;
+    int64_t nOverflow;             /* overflow (COO, row-sorted, entry order kept) */
+    const int32_t *ovfRow, *ovfCol;
+    const double *ovfVal;
+    /* statistics */
+    int64_t nnzEll, nnzRemInSlice, nnzOverflow, padEll, padRem, nLongRows;
+    int64_t algBytes;              /* 8 nnz + 2 nnzEll + 4 (nnz - nnzEll) + 16 n, BASELINE.md sec. 3 */
+    int64_t formatBytes;           /* blob + descriptors + overflow arrays actually stored */
+} ehyb_layout_view;
+
+/* Build from a reordered matrixCOO (after matrixReorder*, or any row-sorted COO with
+ * partBoundary/nParts set).  Classification of entries is the reference's
+ * (convert.c:247-267): entry -> ELL iff partStart <= J < partStart+W. */
+int ehyb_layout_build(const matrixCOO *m, const ehyb_layout_opts *opts, ehyb_layout **out);
+/* Same from raw CSR arrays with 64-bit row pointers (local blocks of the multi-GPU path). */
+int ehyb_layout_build_csr(int64_t n, const int64_t *rowPtr, const int32_t *col, const double *val,
+                          int nParts, const int32_t *partBoundary, const ehyb_layout_opts *opts,
+                          ehyb_layout **out);
+int ehyb_layout_get(const ehyb_layout *L, ehyb_layout_view *view);
+/* De-interleave the tuned layout back to the reference layout: allocates and
+ * fills `out` like COO2EHYB would for the same matrix (requires W % 32 == 0, W < 32768 and
+ * sizes below 2^31).  Used by the parity tests; the device never sees this form. */
+int ehyb_layout_to_reference(const ehyb_layout *L, matrixEHYB *out, int *sizeBlockELL, int *sizeER);
+void ehyb_layout_free(ehyb_layout *L);
+
+/* ------------------------------------------------------------------------------------ */
+/* device session                                                                         */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct ehyb_handle ehyb_handle;
+
+typedef struct ehyb_session_opts {
+    int device;         /* CUDA device ordinal */
+    int threads;        /* threads per CTA, 0 = default */
+    int use_graph;      /* capture the per-product launches in a CUDA graph (default 1) */
+    int l2_persist_x;   /* L2 access-policy window on x for the remainder gathers (default 1) */
+    int64_t halo_cols;  /* extra x entries after the n local ones (multi-GPU), default 0 */
+} ehyb_session_opts;
+
+void ehyb_session_opts_default(ehyb_session_opts *o);
+
+/* Upload a layout: one allocation + one H2D per array, persistent buffers, own stream. */
+int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, ehyb_handle **out);
+/* y = A x with device vectors (16-byte aligned, x has ncols entries); asynchronous on the
+ * session stream. */
+int ehyb_spmv(ehyb_handle *h, const double *x_d, double *y_d);
+/* Same with HOST vectors: H2D of x, product, D2H of y, synchronous.  This is the call the
+ * reference's spmvGPuEHYB makes around its timed loop (spmv.cu:109-117). */
+int ehyb_spmv_host(ehyb_handle *h, const double *x_h, double *y_h);
+/* Pipelined stream of host products: for i in [0,count): y_h[i] = A x_h[i], with the copies
+ * of product i+1 overlapping the kernels of product i (pinned staging, 2 copy streams). */
+int ehyb_spmv_host_batch(ehyb_handle *h, const double *const *x_h, double *const *y_h, int count);
+/* Device buffers owned by the session (x: ncols doubles, y: n doubles). */
+int ehyb_session_vectors(ehyb_handle *h, double **x_d, double **y_d);
+int ehyb_set_x(ehyb_handle *h, const double *x_h);
+int ehyb_get_y(ehyb_handle *h, double *y_h);
+/* `iters` products of the session's own x into its own y between two CUDA events on the
+ * session stream, after `warmup` untimed ones.  *ms_total = elapsed milliseconds.
+ * If kernel_ms != NULL it receives the summed duration of the main kernel alone, measured
+ * with per-launch events in a second pass of the same length. */
+int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_total, float *kernel_ms);
+/* Number of kernel launches one product issues (1, or 2 when the overflow list is not empty). */
+int ehyb_launches_per_spmv(const ehyb_handle *h);
+int ehyb_sync(ehyb_handle *h);
+void *ehyb_stream(ehyb_handle *h); /* cudaStream_t */
+void ehyb_free(ehyb_handle *h);
+
+/* Device-side description in the reference's struct (for matrixVectorEHYB callers): fills
+ * `d` with dimension/nParts/... and d->b200 = h.  No arrays in the reference layout exist
+ * on the device. */
+int ehyb_describe(ehyb_handle *h, matrixEHYB *d);
+
+/* ------------------------------------------------------------------------------------ */
+/* synthetic matrices (BASELINE.json configs) and Matrix Market I/O    */
+/* ------------------------------------------------------------------------------------ */
+
+typedef enum ehyb_gen_kind {
+    EHYB_GEN_LAPLACE2D = 1, /* 5-point, diag 4, off -1; dims nx, ny */
+    EHYB_GEN_STENCIL27 = 2, /* 27-point, diag 26, off -1; dims nx, ny, nz */
+    EHYB_GEN_ELASTICITY = 3 /* 3 dof/node, 27-point node stencil, dense 3x3 blocks */
+} ehyb_gen_kind;
+
+/* Lower-triangle "file entries" in the column-major order a .mtx of the matrix holds.
+ * Arrays are malloc'd (free with ehyb_free_host).  0-based. */
+int ehyb_gen_lower(ehyb_gen_kind kind, int nx, int ny, int nz, int *n, int64_t *count, int **li,
+                   int **lj, double **lv);
+/* The reader's expansion of a symmetric file into the matrixCOO the pipeline starts from
+ * (solver_test.c:127-265): row-sorted COO with both triangles, rowIdx, numInRow, diag, maxCol,
+ * zeroed numInRow2/partBoundary/reorderList.  y_golden (optional, n, zeroed by the callee) is
+ * accumulated in file order like the reference's check vector; x may be NULL then. */
+int ehyb_coo_from_lower(int n, int64_t count, const int *li, const int *lj, const double *lv,
+                        matrixCOO *out, const double *x, double *y_golden);
+/* General (unsymmetric) entries in file order (solver_test.c:31-126). */
+int ehyb_coo_from_general(int n, int64_t count, const int *fi, const int *fj, const double *fv,
+                          matrixCOO *out, const double *x, double *y_golden);
+/* R-MAT (a,b,c,d)=(0.57,0.19,0.19,0.05), counter-based hash, duplicates summed, values
+ * U(-1,1); general entries sorted by (row, col).  add_diagonal adds 4.0 on the diagonal. */
+int ehyb_gen_rmat(int scale, int edge_factor, uint64_t seed, int add_diagonal, int *n,
+                  int64_t *count, int **fi, int **fj, double **fv);
+/* x of the reference driver: srand(i); x[i] = (rand()%200-100)/1000 (solver_test.c:228-232). */
+void ehyb_x_reference(int n, double *x);
+/* Reads a Matrix Market coordinate file (real|integer|pattern, general|symmetric) with the
+ * reference reader's semantics, but with a buffered parser instead of one fscanf per line.
+ * x_out (optional) receives the driver's x (malloc'd), y_out (optional, needs x_out) the
+ * golden product accumulated in file order. */
+int ehyb_read_mtx(const char *path, matrixCOO *out, int *symmetric, double **x_out, double **y_out);
+int ehyb_write_mtx(const char *path, int n, int64_t count, const int *i, const int *j, const double *v,
+                   int symmetric);
+void ehyb_coo_free(matrixCOO *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,231 @@
+/*
+ * ref_shim.cpp -- builds the UNMODIFIED reference host path into oracle/_ref/libehyb_ref.so.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/ehyb_oracle.c header).  No reference source is
+ * copied: oracle/Makefile compiles convert.c, reordering.c and mmio.c where they lie
+ * (REF=/root/reference) and this file #includes solver_test.c from there so that its
+ * static readers (matrixRead_sym / matrixRead_unsym) can be driven from the tests.
+ *
+ * Two things are intercepted, both at link level, neither by editing the reference:
+ *   - exit(): the reference aborts with exit(0|1) on inconsistent input
+ *     (convert.c:122-125, :136-139, ...).  This file defines its own exit() and the
+ *     library is linked -Bsymbolic-functions, so the reference's calls bind to it; it
+ *     longjmps back into the wrapper, which then returns a non-zero status.
+ *   - MTMETIS_PartGraphKway / mtmetis_init_options: libmtmetis.a is not position
+ *     independent and cannot be linked into a shared object.  The shim forwards the
+ *     call - same arguments, same binary - to bin/ehyb_mtmetis (a 40-line main() around
+ *     the shipped libmtmetis.a), or returns a partition injected by the test.  It also
+ *     records a hash of the graph the reference handed over, so the product's graph
+ *     construction can be compared with it.
+ */
+#include <setjmp.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#define main ref_solver_test_main
+#include "solver_test.c" /* resolved through -I$(REF); brings kernel.h, spmv.h, reordering.h, mmio.h */
+#undef main
+#include "convert.h"
+#include "mtmetis_abi.h" /* third_party/mtmetis: prototypes only */
+
+static jmp_buf g_trap;
+static int g_trap_armed = 0;
+static int g_trap_status = 0;
+
+extern "C" void exit(int status) noexcept
+{
+    g_trap_status = status;
+    if (g_trap_armed) longjmp(g_trap, 1);
+    fflush(stdout);
+    _exit(status ? status : 97);
+}
+
+#define REF_GUARD(stmt)                       \
+    do {                                      \
+        g_trap_armed = 1;                     \
+        if (setjmp(g_trap)) {                 \
+            g_trap_armed = 0;                 \
+            return 1000 + g_trap_status;      \
+        }                                     \
+        stmt;                                 \
+        g_trap_armed = 0;                     \
+    } while (0)
+
+/* ---------------- mt-metis interception ---------------- */
+
+static char g_mtmetis_bin[1024] = "";
+static const uint32_t *g_inject = NULL;
+static uint32_t g_inject_n = 0;
+static uint64_t g_graph_info[8]; /* n, nadj, nparts, nthreads, fnv(xadj), fnv(adjncy), ubvec bits, calls */
+static uint32_t *g_last_where = NULL;
+static uint32_t g_last_where_n = 0;
+
+static uint64_t fnv1a(const void *p, size_t nbytes)
+{
+    const unsigned char *b = (const unsigned char *)p;
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (size_t i = 0; i < nbytes; ++i) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    return h;
+}
+
+extern "C" double *mtmetis_init_options(void)
+{
+    return (double *)calloc(64, sizeof(double));
+}
+
+extern "C" int MTMETIS_PartGraphKway(const uint32_t *nvtxs, const uint32_t *ncon, const uint32_t *xadj,
+                                     const uint32_t *adjncy, const int32_t *vwgt, const uint32_t *vsize,
+                                     const int32_t *adjwgt, const uint32_t *nparts, const float *tpwgts,
+                                     const float *ubvec, const double *options, int32_t *r_edgecut,
+                                     uint32_t *where)
+{
+    (void)ncon; (void)vwgt; (void)vsize; (void)adjwgt; (void)tpwgts;
+    uint32_t n = *nvtxs;
+    uint32_t nthreads = (uint32_t)options[EHYB_MTMETIS_OPTION_NTHREADS];
+    g_graph_info[0] = n;
+    g_graph_info[1] = xadj[n];
+    g_graph_info[2] = *nparts;
+    g_graph_info[3] = nthreads;
+    g_graph_info[4] = fnv1a(xadj, ((size_t)n + 1) * 4);
+    g_graph_info[5] = fnv1a(adjncy, (size_t)xadj[n] * 4);
+    uint32_t ub_bits;
+    memcpy(&ub_bits, ubvec, 4);
+    g_graph_info[6] = ub_bits;
+    g_graph_info[7] += 1;
+    if (g_inject) {
+        if (g_inject_n != n) return 0;
+        memcpy(where, g_inject, (size_t)n * 4);
+        if (r_edgecut) *r_edgecut = -1;
+    } else {
+        if (!g_mtmetis_bin[0]) {
+            fprintf(stderr, "ref_shim: no partition injected and no mt-metis helper set\n");
+            return 0;
+        }
+        char gpath[] = "/tmp/ehyb_ref_graph_XXXXXX";
+        char wpath[] = "/tmp/ehyb_ref_where_XXXXXX";
+        int gfd = mkstemp(gpath), wfd = mkstemp(wpath);
+        if (gfd < 0 || wfd < 0) return 0;
+        close(wfd);
+        FILE *f = fdopen(gfd, "wb");
+        uint32_t hdr[4] = {0x47594845u, n, *nparts, nthreads};
+        fwrite(hdr, sizeof hdr, 1, f);
+        fwrite(ubvec, 4, 1, f);
+        fwrite(xadj, 4, (size_t)n + 1, f);
+        fwrite(adjncy, 4, xadj[n], f);
+        fclose(f);
+        char cmd[4096];
+        snprintf(cmd, sizeof cmd, "'%s' '%s' '%s'", g_mtmetis_bin, gpath, wpath);
+        int rc = system(cmd);
+        int ok = 0;
+        if (rc == 0) {
+            f = fopen(wpath, "rb");
+            int32_t cut;
+            if (f && fread(&cut, 4, 1, f) == 1 && fread(where, 4, n, f) == n) {
+                ok = 1;
+                if (r_edgecut) *r_edgecut = cut;
+            }
+            if (f) fclose(f);
+        }
+        unlink(gpath);
+        unlink(wpath);
+        if (!ok) return 0;
+    }
+    free(g_last_where);
+    g_last_where = (uint32_t *)malloc((size_t)n * 4 + 4);
+    memcpy(g_last_where, where, (size_t)n * 4);
+    g_last_where_n = n;
+    return 1; /* MTMETIS_SUCCESS */
+}
+
+/* solver_test.c's main (renamed above, never called) references the device entry point. */
+extern "C" void spmvGPuEHYB(matrixCOO *, const double *, double *, const int, int *) {}
+
+/* ---------------- exported wrappers ---------------- */
+
+extern "C" {
+
+void ref_set_mtmetis_bin(const char *path) { snprintf(g_mtmetis_bin, sizeof g_mtmetis_bin, "%s", path); }
+void ref_set_partition(const uint32_t *where, uint32_t n) { g_inject = where; g_inject_n = n; }
+void ref_graph_info(uint64_t *out) { memcpy(out, g_graph_info, sizeof g_graph_info); }
+uint32_t ref_last_partition(uint32_t *out, uint32_t cap)
+{
+    if (out && cap >= g_last_where_n) memcpy(out, g_last_where, (size_t)g_last_where_n * 4);
+    return g_last_where_n;
+}
+
+size_t ref_sizeof_matrixCOO(void) { return sizeof(matrixCOO); }
+size_t ref_sizeof_matrixEHYB(void) { return sizeof(matrixEHYB); }
+
+/* The reference's own reader on a .mtx file: solver_test.c:328-355 + :127-265 / :31-126.
+ * y is the golden product accumulated while reading; it is calloc'd here instead of the
+ * reference's malloc (B-10).  Returns 0, or 1000+status when the reference called exit. */
+int ref_read_mtx(const char *path, matrixCOO *coo, double **x, double **y, int *symmetric)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return 1;
+    MM_typecode matcode;
+    if (mm_read_banner(f, &matcode) != 0) { fclose(f); return 2; }
+    *symmetric = mm_is_symmetric(matcode) ? 1 : 0;
+    memset(coo, 0, sizeof *coo);
+    REF_GUARD({
+        if (*symmetric) matrixRead_sym(coo, x, y, f);
+        else matrixRead_unsym(coo, x, y, f);
+    });
+    fclose(f);
+    return 0;
+}
+
+/* A matrixCOO owned by malloc (the reference frees I/J/V inside matrixReorder,
+ * reordering.c:363-366), filled from caller arrays: the state right after the reader. */
+int ref_coo_from_arrays(matrixCOO *coo, int n, int totalNum, const int *I, const int *J, const double *V,
+                        const int *rowIdx, const int *numInRow, int maxCol, int nParts, int W, int kpp)
+{
+    memset(coo, 0, sizeof *coo);
+    coo->dimension = n;
+    coo->totalNum = totalNum;
+    coo->maxCol = maxCol;
+    coo->nParts = nParts;
+    coo->vectorCacheSize = (uint16_t)W;
+    coo->kernelPerPart = (int16_t)kpp;
+    coo->partBoundary = (int *)calloc(n, sizeof(int));
+    coo->reorderList = (int *)calloc(n, sizeof(int));
+    coo->numInRow = (int *)calloc(n, sizeof(int));
+    coo->numInRow2 = (int *)calloc(n, sizeof(int));
+    coo->I = (int *)malloc((size_t)totalNum * sizeof(int));
+    coo->J = (int *)malloc((size_t)totalNum * sizeof(int));
+    coo->V = (double *)malloc((size_t)totalNum * sizeof(double));
+    coo->diag = (double *)calloc(n, sizeof(double));
+    coo->rowIdx = (int *)malloc(((size_t)n + 1) * sizeof(int));
+    memcpy(coo->I, I, (size_t)totalNum * sizeof(int));
+    memcpy(coo->J, J, (size_t)totalNum * sizeof(int));
+    memcpy(coo->V, V, (size_t)totalNum * sizeof(double));
+    memcpy(coo->rowIdx, rowIdx, ((size_t)n + 1) * sizeof(int));
+    memcpy(coo->numInRow, numInRow, (size_t)n * sizeof(int));
+    return 0;
+}
+
+int ref_matrixReorder(matrixCOO *coo, int symmetric)
+{
+    REF_GUARD({
+        if (symmetric) matrixReorder(coo);
+        else matrixReorder_unsym(coo);
+    });
+    return 0;
+}
+
+int ref_COO2EHYB(matrixCOO *coo, matrixEHYB *out, int *sizeBlockELL, int *sizeER)
+{
+    memset(out, 0, sizeof *out);
+    REF_GUARD(COO2EHYB(coo, out, sizeBlockELL, sizeER));
+    return 0;
+}
+
+void ref_vectorReorder(int n, const double *v, double *vr, const int *list) { vectorReorder(n, v, vr, list); }
+void ref_vectorRecover(int n, const double *vr, double *v, const int *list) { vectorRecover(n, vr, v, list); }
+
+void ref_free(void *p) { free(p); }
+
+} /* extern "C" */
