@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- fp64 EHYB SpMV throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A step is one y = A x product.  Workload at every N: BASELINE.json configs[1], the 3-D
+27-point stencil 128^3 (n 2 097 152, nnz 55 742 968, fp64) PER GPU: at N > 1 the global grid
+is 128 x 128 x 128N, rank r owns z-slab r (weak scaling) and exchanges its x halo planes with
+its neighbours every product (NCCL send/recv inside libehyb.so).  Inputs are resident in HBM
+when the timed region starts; the matrix data (~600 MB) is larger than L2 (126 MB).
+
+The JSON line carries: value (GFLOP/s = 2 nnz / t, all ranks), roofline (algorithmic bytes of
+the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json), e2e (the same
+metric through the host-buffer entry point, H2D of x and D2H of y inside the timed region),
+cpu_baseline (the oracle's CSR product on the host cores; rank 0, N=1 only), clocks.
+`--impl reference` times the reference's CPU path (CSR over its own arrays, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("EHYB_MTMETIS_BIN", str(ROOT / "bin" / "ehyb_mtmetis"))
+
+GRID = (128, 128, 128)  # BASELINE.json configs[1]
+WORKLOAD = "3D 27-point stencil 128^3 (n 2097152, nnz 55742968) fp64, EHYB, per GPU"
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = get_reasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def build_matrix(grid, x=None):
+    """generate -> matrixCOO -> plan -> mt-metis -> reorder -> tuned layout (all product code)."""
+    from ehyb_spmv_gpu_b200 import api
+    t0 = time.time()
+    n, li, lj, lv = api.gen_lower(api.GEN_STENCIL27, *grid)
+    if x is None:
+        x = api.x_reference(n)
+    m = api.CooMatrix.from_lower(n, li, lj, lv, x)
+    del li, lj, lv
+    try:
+        dev = api.device_query(int(os.environ.get("LOCAL_RANK", "0")))
+    except Exception:
+        dev = api.device_info_b200()
+    pl = api.plan(n, dev)
+    m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
+    m.reorder()
+    arr_pb = m.arrays()["partBoundary"] if False else None
+    lay = api.Layout(m, er_fill=float(os.environ.get("EHYB_ER_FILL", "-1")))
+    return m, lay, x, pl, time.time() - t0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ehyb_spmv_gpu_b200 import _lib, api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N > 1 must be launched with torchrun (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+
+    if world > 1:
+        from ehyb_spmv_gpu_b200 import multigpu
+        return multigpu.bench(args, rank, world, local, GRID, WORKLOAD)
+
+    m, lay, x, pl, t_prep = build_matrix(GRID)
+    st = lay.stats()
+    s = api.Session(lay, device=local)
+    xr = m.vector_reorder(x)
+    s.set_x(xr)
+    launches = s.launches_per_spmv()
+
+    # ---- device-resident timed region: CUDA events on the session stream inside libehyb ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    ms, kms = s.time_spmv(args.warmup, args.steps, kernel_only=True)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    gflops = 2.0 * st["nnz"] / (ms_per_step * 1e6)
+    kernel_us = kms / args.steps * 1e3
+
+    # quick parity check of what was timed (not in the timed region)
+    y = m.vector_recover(s.get_y())
+    err = float(np.abs(y - m.y_golden).max())
+
+    # ---- end to end: host buffers, H2D of x and D2H of y every step, through the C ABI ----
+    n = m.n
+    pin = []
+    def pinned(count):
+        p = C.c_void_p()
+        _lib.check(lib, lib.ehyb_host_alloc_pinned(C.c_size_t(count * 8), C.byref(p)), "ehyb_host_alloc_pinned")
+        pin.append(p)
+        return np.ctypeslib.as_array((C.c_double * count).from_address(p.value))
+    nbuf = 4
+    xs = [pinned(n) for _ in range(nbuf)]
+    ys = [pinned(n) for _ in range(nbuf)]
+    for b in xs:
+        b[:] = xr
+    s.spmv_host_batch([xs[i % nbuf] for i in range(max(args.warmup, 3))], [ys[i % nbuf] for i in range(max(args.warmup, 3))])
+    t0 = time.perf_counter()
+    s.spmv_host_batch([xs[i % nbuf] for i in range(args.steps)], [ys[i % nbuf] for i in range(args.steps)])
+    t_e2e = time.perf_counter() - t0
+    e2e_gflops = 2.0 * st["nnz"] * args.steps / t_e2e / 1e9
+    assert np.array_equal(np.asarray(ys[0]), s.spmv_host(np.asarray(xs[0])))
+
+    # ---- CPU baseline: the oracle's CSR product on the host cores (bounded sample) ----
+    from oracle import oracle as O
+    orc = O.Oracle()
+    a = m.arrays()
+    cpu_iters = 20
+    sec, y_cpu = orc.csr_spmv_timed(a["rowIdx"], a["J"], a["V"], xr, 2, cpu_iters)
+    cpu_gflops = 2.0 * st["nnz"] * cpu_iters / sec / 1e9
+    absAx = orc.csr_abs_spmv(a["rowIdx"], a["J"], a["V"], xr)
+    gate_fail = int(np.count_nonzero(~(np.abs(s.get_y() - y_cpu) <= 1e-12 * absAx)))
+
+    peaks, peak_src = measured_peaks()
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = st["algBytes"] / (kernel_us * 1e3)  # bytes / ns = GB/s
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    out = {
+        "metric": "fp64 SpMV GFLOP/s (2*nnz/t), EHYB format", "value": round(gflops, 2), "unit": "GFLOP/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 6),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "grid": list(GRID), "n": n, "nnz": st["nnz"],
+                   "partitions": st["nParts"], "window": st["W"], "ctas_per_partition": st["ctasPerPart"],
+                   "slices": st["nSlices"], "nnz_ell": st["nnzEll"], "nnz_remainder_in_slice": st["nnzRemInSlice"],
+                   "nnz_overflow": st["nnzOverflow"], "format_bytes": st["formatBytes"],
+                   "l2": "matrix data (%.0f MB) larger than L2 (126 MB), no flush" % (st["formatBytes"] / 1e6),
+                   "host_prep_s": round(t_prep, 1)},
+        "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "ehyb_staged_kernel", "kernel_us": round(kernel_us, 3),
+                     "algorithmic_bytes_per_launch": st["algBytes"],
+                     "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
+                     "whole_step_GBs": round(st["algBytes"] / (ms_per_step * 1e6), 1)},
+        "e2e": {"value": round(e2e_gflops, 2), "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * n,
+                "d2h_bytes_per_step": 8 * n, "api": "ehyb_spmv_host_batch (pinned host x/y, copies pipelined)"},
+        "cpu_baseline": {"value": round(cpu_gflops, 2), "unit": "GFLOP/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": "%d CSR products of the same permuted matrix (oracle orc_csr_spmv, OpenMP)" % cpu_iters},
+        "gpu_launches": launches * args.steps,
+        "clocks": clocks,
+        "parity": {"max_abs_err_vs_golden": err, "rows_outside_1e-12_gate": gate_fail},
+    }
+    for p in pin:
+        lib.ehyb_host_free_pinned(p)
+    s.free(); lay.free(); m.free()
+    print(json.dumps(out), flush=True)
+
+
+def run_reference(args):
+    """The reference has no CPU SpMV routine of its own: its CPU path is the CSR
+    product over its own arrays (rowIdx/J/V after matrixReorder).  Built here with the oracle's
+    restatement of the reader + reorder (the pinned mt-metis binary provides the partition) and
+    timed with every host thread.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import oracle as O
+    orc = O.Oracle()
+    n, li, lj, lv = O.gen_stencil27_lower(*GRID)
+    x = orc.x_reference(n)
+    m = orc.read_sym(n, li, lj, lv)
+    P, W, _ = orc.heuristic_ref(n, True)
+    xadj, adj = orc.graph(m)
+    part = O.mtmetis_partition(xadj, adj, P, nthreads=1)
+    r = orc.reorder(m, P, W, part)
+    xr = orc.vector_reorder(x, r["reorderList"])
+    sec_w, _ = orc.csr_spmv_timed(r["rowIdx"], r["J"], r["V"], xr, args.warmup, 1)
+    sec, _ = orc.csr_spmv_timed(r["rowIdx"], r["J"], r["V"], xr, 0, args.steps)
+    gflops = 2.0 * m["nnz"] * args.steps / sec / 1e9
+    out = {
+        "impl": "reference", "metric": "fp64 SpMV GFLOP/s (2*nnz/t), EHYB format", "value": round(gflops, 3),
+        "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(sec / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "grid": list(GRID), "n": n, "nnz": m["nnz"],
+                   "partitions": P, "window": W, "note": "reference partition parameters (82-SM heuristic)"},
+        "cpu_baseline": {"value": round(gflops, 3), "unit": "GFLOP/s", "cores": orc.num_threads(), "kind": "port",
+                         "sample": "%d CSR products of the whole matrix per run" % args.steps},
+        "e2e": {"value": round(gflops, 3), "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

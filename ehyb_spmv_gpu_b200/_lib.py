@@ -89,7 +89,7 @@ class LayoutView(C.Structure):
 
 class SessionOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("threads", C.c_int), ("use_graph", C.c_int),
-                ("l2_persist_x", C.c_int), ("halo_cols", C.c_int64)]
+                ("l2_persist_x", C.c_int), ("halo_cols", C.c_int64), ("kernel", C.c_int)]
 
 
 # every symbol the headers declare; checked at load time (tests/test_abi.py re-checks against

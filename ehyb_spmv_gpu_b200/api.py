@@ -15,6 +15,7 @@ from ._lib import (DeviceInfo, EhybError, LayoutOpts, LayoutView, MatrixCOO, Mat
                    SessionOpts, check)
 
 GEN_LAPLACE2D, GEN_STENCIL27, GEN_ELASTICITY = 1, 2, 3
+KERNEL_DIRECT, KERNEL_STAGED = 1, 2
 
 
 def _np(ptr, count, dtype):
@@ -248,7 +249,7 @@ def ehyb_struct_to_dict(e: MatrixEHYB, sizeELL: int, sizeER: int, n: int):
 class Layout:
     """ehyb_layout: the Blackwell-tuned layout on the host."""
 
-    def __init__(self, m: CooMatrix, W: int = 0, ctasPerPart: int = 0, er_fill: float = 0.5,
+    def __init__(self, m: CooMatrix, W: int = 0, ctasPerPart: int = 0, er_fill: float = -1.0,
                  long_row_threshold: int = 0, ncols: int = 0):
         self.lib = L.load()
         self.h = C.c_void_p()
@@ -299,7 +300,7 @@ class Session:
     """ehyb_handle: a layout resident on one GPU."""
 
     def __init__(self, layout: Layout, device: int = 0, threads: int = 0, use_graph: bool = True,
-                 l2_persist_x: bool = True, halo_cols: int = 0):
+                 l2_persist_x: bool = True, halo_cols: int = 0, kernel: int = 0):
         self.lib = L.load()
         self.h = C.c_void_p()
         self.n = int(layout.v.n)
@@ -307,6 +308,7 @@ class Session:
         o = SessionOpts()
         self.lib.ehyb_session_opts_default(C.byref(o))
         o.device, o.threads, o.use_graph, o.l2_persist_x, o.halo_cols = device, threads, int(use_graph), int(l2_persist_x), halo_cols
+        o.kernel = kernel
         check(self.lib, self.lib.ehyb_upload(layout.h, C.byref(o), C.byref(self.h)), "ehyb_upload")
 
     def spmv_host(self, x: np.ndarray) -> np.ndarray:

@@ -1,0 +1,503 @@
+/*
+ * ehyb_device.cu -- device management behind the C ABI (include/ehyb.h, "device session").
+ *
+ * Replaces the reference's cudaMallocTransDataEHYB (spmv.cu:6-60: 12 cudaMalloc + 11 blocking
+ * copies per session, sizes computed with the wrong element type, B-5) and the per-call
+ * launcher matrixVectorBlockELL (kernel.cu:324-380: cudaFuncSetAttribute on every product,
+ * three launches, legacy default stream) with:
+ *   - one upload per array into persistent buffers, on the session's own stream;
+ *   - shared-memory opt-in set once; the product is one launch (two when the overflow list
+ *     is not empty), optionally replayed from a CUDA graph;
+ *   - an L2 access-policy window (persisting) on x, so that the remainder gathers keep
+ *     hitting L2 while the matrix streams through with evict-first loads;
+ *   - CUDA-event timing on the session stream;
+ *   - int status codes, no exit().
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../host/common.h"
+#include "ehyb_kernels.cuh"
+
+using namespace ehyb;
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return ehyb_fail(EHYB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+struct ehyb_handle {
+    int device;
+    cudaStream_t stream, h2d, d2h;
+    int64_t n, ncols, nnz, nOvf, blobBytes, algBytes;
+    int nParts, W, kpp, nSlices, threads, ctasPerSM, kernel, kcEll, kcRem;
+    size_t smemBytes;
+    ehyb_part_desc *parts;
+    ehyb_slice_desc *slices;
+    unsigned char *blob;
+    int32_t *ovfRow, *ovfCol;
+    double *ovfVal;
+    double *x, *y;       /* session vectors */
+    double *xb[2], *yb[2]; /* double buffers of the pipelined host path (lazy) */
+    cudaEvent_t evX[2], evK[2], evY[2], ev0, ev1;
+    int use_graph, l2_persist, pdl;
+    cudaGraphExec_t gexec;
+    const double *gx;
+    double *gy;
+};
+
+extern "C" int ehyb_device_count(int *count)
+{
+    if (!count) return ehyb_fail(EHYB_ERR_ARG, "ehyb_device_count: NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return ehyb_fail(EHYB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_device_query(int device, ehyb_device_info *out)
+{
+    if (!out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_device_query: NULL");
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    memset(out, 0, sizeof *out);
+    out->device = device;
+    out->sm_count = p.multiProcessorCount;
+    out->smem_optin_bytes = (int)p.sharedMemPerBlockOptin;
+    out->smem_per_sm_bytes = (int)p.sharedMemPerMultiprocessor;
+    out->l2_bytes = p.l2CacheSize;
+    out->cc_major = p.major;
+    out->cc_minor = p.minor;
+    out->max_persist_l2_bytes = p.persistingL2CacheMaxSize;
+    out->hbm_bytes = p.totalGlobalMem;
+    snprintf(out->name, sizeof out->name, "%.63s", p.name);
+    return EHYB_OK;
+}
+
+extern "C" void ehyb_session_opts_default(ehyb_session_opts *o)
+{
+    memset(o, 0, sizeof *o);
+    o->device = 0;
+    o->threads = 0;
+    o->use_graph = 1;
+    o->l2_persist_x = 1;
+    o->halo_cols = 0;
+    o->kernel = 0;
+}
+
+/* kernel variants: register budget follows the number of resident threads per SM */
+typedef void (*main_kernel_t)(const MainArgs);
+static main_kernel_t pick_kernel(int kernel, int threads, int ctasPerSM)
+{
+    if (kernel == EHYB_KERNEL_STAGED) return threads <= 512 ? ehyb_staged_kernel<512> : ehyb_staged_kernel<768>;
+    /* 64 K registers per SM: <= 64 per thread at 1024 resident threads, <= 32 at 2048 */
+    if (threads * ctasPerSM > 1024) return ehyb_main_kernel<1024, 2>;
+    return ehyb_main_kernel<1024, 1>;
+}
+
+static int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return s && s[0] ? atoi(s) : dflt;
+}
+
+extern "C" void ehyb_free(ehyb_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    cudaFree(h->parts); cudaFree(h->slices); cudaFree(h->blob);
+    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal);
+    cudaFree(h->x); cudaFree(h->y);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->xb[i]); cudaFree(h->yb[i]);
+        if (h->evX[i]) cudaEventDestroy(h->evX[i]);
+        if (h->evK[i]) cudaEventDestroy(h->evK[i]);
+        if (h->evY[i]) cudaEventDestroy(h->evY[i]);
+    }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->l2_persist) cudaCtxResetPersistingL2Cache();
+    if (h->h2d) cudaStreamDestroy(h->h2d);
+    if (h->d2h) cudaStreamDestroy(h->d2h);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    free(h);
+}
+
+static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, ehyb_handle *h)
+{
+    CU(cudaSetDevice(o->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, o->device));
+    if (prop.major < 9)
+        return ehyb_fail(EHYB_ERR_CUDA, "device %d (%s, sm_%d%d) has no TMA bulk copies; this engine targets sm_100a", o->device,
+                         prop.name, prop.major, prop.minor);
+    h->device = o->device;
+    h->n = v->n; h->ncols = v->ncols + (o->halo_cols > 0 && v->ncols == v->n ? o->halo_cols : 0);
+    h->nnz = v->nnz; h->nOvf = v->nOverflow; h->blobBytes = v->blobBytes; h->algBytes = v->algBytes;
+    h->nParts = v->nParts; h->W = v->W; h->kpp = v->ctasPerPart > 0 ? v->ctasPerPart : 1; h->nSlices = v->nSlices;
+    int kernel = o->kernel > 0 ? o->kernel : env_int("EHYB_KERNEL", EHYB_KERNEL_STAGED);
+    int threads = o->threads > 0 ? o->threads : env_int("EHYB_THREADS", 0);
+    const size_t winBytes = (((size_t)v->W + 2) * sizeof(double) + 127) & ~(size_t)127;
+    if (kernel == EHYB_KERNEL_STAGED) {
+        /* warps = staging capacity: 2 slots each, as many as fit next to the window */
+        int kc = env_int("EHYB_CHUNK", 8);
+        if (kc < 4) kc = 4;
+        kc = kc / 4 * 4;
+        if (kc > 32) kc = 32;
+        int kr = env_int("EHYB_CHUNK_REM", 4);
+        kr = kr < 4 ? 4 : (kr > 32 ? 32 : kr / 4 * 4);
+        h->kcEll = kc;
+        h->kcRem = kr;
+        const size_t fixed = (size_t)kStageHeader + winBytes;
+        const size_t perWarp = (size_t)kSlotsPerWarp * slot_bytes(kc, kr);
+        int nw = fixed + perWarp <= prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - fixed) / perWarp) : 0;
+        if (nw > kMaxStageWarps) nw = kMaxStageWarps;
+        if (threads > 0 && threads / 32 < nw) nw = threads / 32 > 0 ? threads / 32 : 1;
+        if (nw < 1) kernel = EHYB_KERNEL_DIRECT; /* window too large to stage next to it */
+        else {
+            h->threads = nw * 32;
+            h->smemBytes = fixed + (size_t)nw * perWarp;
+            h->ctasPerSM = (int)(prop.sharedMemPerMultiprocessor / (h->smemBytes + 1024));
+            if (h->ctasPerSM < 1) h->ctasPerSM = 1;
+        }
+    }
+    if (kernel != EHYB_KERNEL_STAGED) {
+        kernel = EHYB_KERNEL_DIRECT;
+        h->smemBytes = (size_t)kSmemHeader + ((size_t)v->W + 2) * sizeof(double);
+        if (h->smemBytes > prop.sharedMemPerBlockOptin)
+            return ehyb_fail(EHYB_ERR_LIMIT, "window of %d doubles needs %zu bytes of shared memory, device allows %zu", v->W,
+                             h->smemBytes, (size_t)prop.sharedMemPerBlockOptin);
+        /* resident CTAs per SM by shared memory (1 KB reserved per CTA) */
+        int bySmem = (int)(prop.sharedMemPerMultiprocessor / (h->smemBytes + 1024));
+        if (bySmem < 1) bySmem = 1;
+        if (threads <= 0) threads = bySmem >= 2 ? 512 : 1024;
+        threads = (threads + 31) / 32 * 32;
+        if (threads > 1024) threads = 1024;
+        h->threads = threads;
+        h->ctasPerSM = bySmem;
+        while (h->ctasPerSM > 1 && h->ctasPerSM * threads > 1024) h->ctasPerSM--;
+    }
+    h->kernel = kernel;
+
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    CU(cudaMalloc(&h->parts, sizeof(ehyb_part_desc) * (size_t)h->nParts));
+    CU(cudaMalloc(&h->slices, sizeof(ehyb_slice_desc) * (size_t)(h->nSlices ? h->nSlices : 1)));
+    CU(cudaMalloc(&h->blob, (size_t)(h->blobBytes ? h->blobBytes : 256)));
+    CU(cudaMemcpyAsync(h->parts, v->parts, sizeof(ehyb_part_desc) * (size_t)h->nParts, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->slices, v->slices, sizeof(ehyb_slice_desc) * (size_t)h->nSlices, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->blob, v->blob, (size_t)h->blobBytes, cudaMemcpyHostToDevice, h->stream));
+    if (h->nOvf > 0) {
+        CU(cudaMalloc(&h->ovfRow, sizeof(int32_t) * (size_t)h->nOvf));
+        CU(cudaMalloc(&h->ovfCol, sizeof(int32_t) * (size_t)h->nOvf));
+        CU(cudaMalloc(&h->ovfVal, sizeof(double) * (size_t)h->nOvf));
+        CU(cudaMemcpyAsync(h->ovfRow, v->ovfRow, sizeof(int32_t) * (size_t)h->nOvf, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->ovfCol, v->ovfCol, sizeof(int32_t) * (size_t)h->nOvf, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(h->ovfVal, v->ovfVal, sizeof(double) * (size_t)h->nOvf, cudaMemcpyHostToDevice, h->stream));
+    }
+    CU(cudaMalloc(&h->x, sizeof(double) * (size_t)(h->ncols + 2)));
+    CU(cudaMalloc(&h->y, sizeof(double) * (size_t)(h->n + 2)));
+    CU(cudaMemsetAsync(h->x, 0, sizeof(double) * (size_t)(h->ncols + 2), h->stream));
+    CU(cudaMemsetAsync(h->y, 0, sizeof(double) * (size_t)(h->n + 2), h->stream));
+
+    /* shared-memory opt-in: once per session, not once per product (kernel.cu:351) */
+    CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ehyb_staged_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU(cudaFuncSetAttribute(ehyb_staged_kernel<768>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(ehyb_staged_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CU(cudaFuncSetAttribute(ehyb_staged_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+
+    h->use_graph = o->use_graph;
+    h->pdl = env_int("EHYB_PDL", 1);
+    h->l2_persist = 0;
+    if (o->l2_persist_x && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        size_t want = sizeof(double) * (size_t)h->ncols;
+        size_t carve = want < (size_t)prop.persistingL2CacheMaxSize ? want : (size_t)prop.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof attr);
+            size_t win = want < (size_t)prop.accessPolicyMaxWindowSize ? want : (size_t)prop.accessPolicyMaxWindowSize;
+            attr.accessPolicyWindow.base_ptr = h->x;
+            attr.accessPolicyWindow.num_bytes = win;
+            attr.accessPolicyWindow.hitRatio = win <= carve ? 1.0f : (float)carve / (float)win;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) h->l2_persist = 1;
+        }
+        cudaGetLastError();
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, ehyb_handle **out)
+{
+    if (!L || !out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_upload: NULL argument");
+    ehyb_session_opts o;
+    if (opts) o = *opts;
+    else ehyb_session_opts_default(&o);
+    ehyb_layout_view v;
+    int rc = ehyb_layout_get(L, &v);
+    if (rc) return rc;
+    ehyb_handle *h = (ehyb_handle *)calloc(1, sizeof *h);
+    if (!h) return ehyb_fail(EHYB_ERR_NOMEM, "ehyb_upload: out of memory");
+    rc = upload_impl(&v, &o, h);
+    if (rc) {
+        char msg[512];
+        snprintf(msg, sizeof msg, "%s", ehyb_last_error());
+        ehyb_free(h);
+        return ehyb_fail(rc, "%s", msg);
+    }
+    *out = h;
+    return EHYB_OK;
+}
+
+/* the launches of one product, on `s` */
+static int launch_product(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
+{
+    MainArgs a;
+    a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
+    a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.kcEll = h->kcEll; a.kcRem = h->kcRem; a.dbg = env_int("EHYB_DEBUG_SKIP", 0);
+    main_kernel_t k = pick_kernel(h->kernel, h->threads, h->ctasPerSM);
+    if (h->kernel == EHYB_KERNEL_STAGED && h->pdl) {
+        /* programmatic dependent launch: this grid may start while the previous kernel of the
+         * stream drains; it orders itself with griddepcontrol.wait before touching x or y */
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(h->nParts * h->kpp));
+        cfg.blockDim = dim3((unsigned)h->threads);
+        cfg.dynamicSmemBytes = h->smemBytes;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, k, a));
+    } else {
+        k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, s>>>(a);
+        CU(cudaGetLastError());
+    }
+    if (h->nOvf > 0) {
+        OverflowArgs o;
+        o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = x_d; o.y = y_d;
+        const int64_t warps = (h->nOvf + kOvfPerWarp - 1) / kOvfPerWarp;
+        const unsigned blocks = (unsigned)((warps + 7) / 8);
+        ehyb_overflow_kernel<<<blocks, 256, 0, s>>>(o);
+        CU(cudaGetLastError());
+    }
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h) { return h ? (h->nOvf > 0 ? 2 : 1) : 0; }
+
+extern "C" int ehyb_spmv(ehyb_handle *h, const double *x_d, double *y_d)
+{
+    if (!h || !x_d || !y_d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_spmv: NULL argument");
+    CU(cudaSetDevice(h->device));
+    if (!h->use_graph || h->nOvf == 0) return launch_product(h, x_d, y_d, h->stream); /* one launch: nothing to fuse */
+    if (!h->gexec || h->gx != x_d || h->gy != y_d) {
+        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = NULL; }
+        cudaGraph_t g;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = launch_product(h, x_d, y_d, h->stream);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+        if (rc) return rc;
+        if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&h->gexec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        h->gx = x_d; h->gy = y_d;
+    }
+    CU(cudaGraphLaunch(h->gexec, h->stream));
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_sync(ehyb_handle *h)
+{
+    if (!h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_sync: NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return EHYB_OK;
+}
+
+extern "C" void *ehyb_stream(ehyb_handle *h) { return h ? (void *)h->stream : NULL; }
+
+extern "C" int ehyb_session_vectors(ehyb_handle *h, double **x_d, double **y_d)
+{
+    if (!h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_session_vectors: NULL");
+    if (x_d) *x_d = h->x;
+    if (y_d) *y_d = h->y;
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_set_x(ehyb_handle *h, const double *x_h)
+{
+    if (!h || !x_h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_set_x: NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->x, x_h, sizeof(double) * (size_t)h->ncols, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_get_y(ehyb_handle *h, double *y_h)
+{
+    if (!h || !y_h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_get_y: NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(y_h, h->y, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_spmv_host(ehyb_handle *h, const double *x_h, double *y_h)
+{
+    if (!h || !x_h || !y_h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_spmv_host: NULL argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->x, x_h, sizeof(double) * (size_t)h->ncols, cudaMemcpyHostToDevice, h->stream));
+    int rc = ehyb_spmv(h, h->x, h->y);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(y_h, h->y, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return EHYB_OK;
+}
+
+static int ensure_pipeline(ehyb_handle *h)
+{
+    if (h->h2d) return EHYB_OK;
+    CU(cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaMalloc(&h->xb[i], sizeof(double) * (size_t)(h->ncols + 2)));
+        CU(cudaMalloc(&h->yb[i], sizeof(double) * (size_t)(h->n + 2)));
+        CU(cudaEventCreateWithFlags(&h->evX[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->evK[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->evY[i], cudaEventDisableTiming));
+    }
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_spmv_host_batch(ehyb_handle *h, const double *const *x_h, double *const *y_h, int count)
+{
+    if (!h || !x_h || !y_h || count < 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_spmv_host_batch: bad argument");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_pipeline(h);
+    if (rc) return rc;
+    /* product i uses buffer pair i%2: its H2D waits for kernel i-2, its kernel for D2H i-2 */
+    for (int i = 0; i < count; ++i) {
+        const int b = i & 1;
+        if (i >= 2) CU(cudaStreamWaitEvent(h->h2d, h->evK[b], 0));
+        CU(cudaMemcpyAsync(h->xb[b], x_h[i], sizeof(double) * (size_t)h->ncols, cudaMemcpyHostToDevice, h->h2d));
+        CU(cudaEventRecord(h->evX[b], h->h2d));
+        CU(cudaStreamWaitEvent(h->stream, h->evX[b], 0));
+        if (i >= 2) CU(cudaStreamWaitEvent(h->stream, h->evY[b], 0));
+        rc = launch_product(h, h->xb[b], h->yb[b], h->stream);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->evK[b], h->stream));
+        CU(cudaStreamWaitEvent(h->d2h, h->evK[b], 0));
+        CU(cudaMemcpyAsync(y_h[i], h->yb[b], sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->d2h));
+        CU(cudaEventRecord(h->evY[b], h->d2h));
+    }
+    CU(cudaStreamSynchronize(h->h2d));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->d2h));
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_total, float *kernel_ms)
+{
+    if (!h || !ms_total || iters <= 0 || warmup < 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_time_spmv: bad argument");
+    CU(cudaSetDevice(h->device));
+    for (int i = 0; i < warmup; ++i) {
+        int rc = ehyb_spmv(h, h->x, h->y);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < iters; ++i) {
+        int rc = ehyb_spmv(h, h->x, h->y);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
+    if (kernel_ms) {
+        /* main kernel alone: one event pair per launch, summed */
+        MainArgs a;
+        a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
+        a.x = h->x; a.y = h->y; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.kcEll = h->kcEll; a.kcRem = h->kcRem; a.dbg = env_int("EHYB_DEBUG_SKIP", 0);
+        main_kernel_t k = pick_kernel(h->kernel, h->threads, h->ctasPerSM);
+        cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)iters * 2, sizeof(cudaEvent_t));
+        if (!ev) return ehyb_fail(EHYB_ERR_NOMEM, "ehyb_time_spmv: out of memory");
+        for (int i = 0; i < 2 * iters; ++i) cudaEventCreate(&ev[i]);
+        for (int i = 0; i < iters; ++i) {
+            cudaEventRecord(ev[2 * i], h->stream);
+            k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, h->stream>>>(a);
+            cudaEventRecord(ev[2 * i + 1], h->stream);
+            if (h->nOvf > 0) {
+                OverflowArgs o;
+                o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = h->x; o.y = h->y;
+                const int64_t warps = (h->nOvf + kOvfPerWarp - 1) / kOvfPerWarp;
+                ehyb_overflow_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, h->stream>>>(o);
+            }
+        }
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        float sum = 0.f;
+        for (int i = 0; i < iters && e == cudaSuccess; ++i) {
+            float t = 0.f;
+            e = cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+            sum += t;
+        }
+        for (int i = 0; i < 2 * iters; ++i) cudaEventDestroy(ev[i]);
+        free(ev);
+        if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "kernel timing: %s", cudaGetErrorString(e));
+        *kernel_ms = sum;
+    }
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_describe(ehyb_handle *h, matrixEHYB *d)
+{
+    if (!h || !d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_describe: NULL");
+    memset(d, 0, sizeof *d);
+    d->dimension = (int)h->n;
+    d->nParts = h->nParts;
+    d->vectorCacheSize = (int16_t)h->W;
+    d->kernelPerPart = h->kpp;
+    d->b200 = h;
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_session_info(const ehyb_handle *h, int *threads, int *ctasPerSM, int *grid, int64_t *smemBytes, int *l2_persist)
+{
+    if (!h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_session_info: NULL");
+    if (threads) *threads = h->threads;
+    if (ctasPerSM) *ctasPerSM = h->ctasPerSM;
+    if (grid) *grid = h->nParts * h->kpp;
+    if (smemBytes) *smemBytes = (int64_t)h->smemBytes;
+    if (l2_persist) *l2_persist = h->l2_persist;
+    return EHYB_OK;
+}
+
+/* pinned host memory for callers that want true asynchronous copies */
+extern "C" int ehyb_host_alloc_pinned(size_t bytes, void **out)
+{
+    if (!out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_host_alloc_pinned: NULL");
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_host_free_pinned(void *p)
+{
+    CU(cudaFreeHost(p));
+    return EHYB_OK;
+}

@@ -1,0 +1,702 @@
+/*
+ * ehyb_kernels.cuh -- device code of the EHYB SpMV engine for sm_100a (B200).
+ *
+ * Replaces the reference's kernelCachedBlockedELL / _small, vecReorderER and longRowKernel
+ * (reference kernel.cu:110-195, :197-284, :69-77, :43-67).  Semantics are the reference's
+ * (SURVEY.md A.4): y = A_ell * x(window) + A_rem * x(global); the design is not:
+ *
+ *   - the x window of a partition is staged into shared memory by TMA bulk copies
+ *     (cp.async.bulk.shared::cluster.global + mbarrier complete_tx; SASS: UBLKCP), issued by
+ *     one thread, instead of a strided copy loop by all threads;
+ *   - values and 16-bit window-local columns stream from HBM with 128-bit loads
+ *     (one LDG.128 = two rows of one ELL column; one LDG.128 = two rows of four columns),
+ *     bypassing L1 and marked evict-first in L2 so that x stays cached;
+ *   - a warp owns a 64-row slice, lane l the rows l and l+32: two independent fp64
+ *     accumulator chains per thread, and y is written ONCE, with fully coalesced 256-byte
+ *     stores - the in-slice remainder is accumulated by the same lane (no yER round trip, no
+ *     scatter-add kernel, no global work counter to reset: SURVEY.md B-1, B-2);
+ *   - irregular spill and long rows go through a COO list reduced with warp-shuffle
+ *     segmented sums (ehyb_overflow_kernel), one atomic per row segment.
+ *
+ * No tensor cores: SpMV is not a dense contraction (arithmetic intensity ~0.19 flop/B).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ehyb.h"
+
+namespace ehyb {
+
+constexpr int kSmemHeader = 128; /* mbarrier + slice counter in front of the window */
+
+struct MainArgs {
+    const ehyb_part_desc *parts;
+    const ehyb_slice_desc *slices;
+    const unsigned char *blob;
+    const double *x;
+    double *y;
+    int n;    /* local rows == end of the windowable x range */
+    int W;    /* window length in elements */
+    int kpp;  /* CTAs per partition */
+    int kcEll; /* staged kernel: ELL columns per chunk (multiple of 4) */
+    int kcRem; /* staged kernel: remainder columns per chunk (multiple of 4) */
+    int dbg;   /* development only (EHYB_DEBUG_SKIP): 1 = skip remainder math, 2 = skip ELL math */
+};
+
+struct OverflowArgs {
+    const int32_t *row, *col;
+    const double *val;
+    int64_t count;
+    const double *x;
+    double *y;
+};
+
+/* ---------------------------------------------------------------- PTX helpers ----- */
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+/* TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar` */
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+/* streaming 128-bit loads: read-only path, no L1 allocation, evict-first in L2 */
+__device__ __forceinline__ uint64_t make_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2 *p, uint64_t pol)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ uint4 ld_stream_u32x4(const uint4 *p, uint64_t pol)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ int2 ld_stream_s32x2(const int2 *p, uint64_t pol)
+{
+    int2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;"
+                 : "=r"(v.x), "=r"(v.y)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+
+/* x gather of the remainder: read-only path, default caching (x is the L2-resident vector) */
+__device__ __forceinline__ double ld_gather_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+/* one ELL group: 4 columns x 2 rows per lane */
+struct Group {
+    uint4 c;
+    double2 v0, v1, v2, v3;
+};
+
+__device__ __forceinline__ void load_group(Group &g, const uint4 *ec, const double2 *ev, int idx, uint64_t pol)
+{
+    g.c = ld_stream_u32x4(ec + idx * 32, pol);
+    g.v0 = ld_stream_f64x2(ev + (4 * idx + 0) * 32, pol);
+    g.v1 = ld_stream_f64x2(ev + (4 * idx + 1) * 32, pol);
+    g.v2 = ld_stream_f64x2(ev + (4 * idx + 2) * 32, pol);
+    g.v3 = ld_stream_f64x2(ev + (4 * idx + 3) * 32, pol);
+}
+
+__device__ __forceinline__ void fma_group(const Group &g, const double *xs, double &acc0, double &acc1)
+{
+    acc0 = fma(g.v0.x, xs[g.c.x & 0xffffu], acc0);
+    acc1 = fma(g.v0.y, xs[g.c.z & 0xffffu], acc1);
+    acc0 = fma(g.v1.x, xs[g.c.x >> 16], acc0);
+    acc1 = fma(g.v1.y, xs[g.c.z >> 16], acc1);
+    acc0 = fma(g.v2.x, xs[g.c.y & 0xffffu], acc0);
+    acc1 = fma(g.v2.y, xs[g.c.w & 0xffffu], acc1);
+    acc0 = fma(g.v3.x, xs[g.c.y >> 16], acc0);
+    acc1 = fma(g.v3.y, xs[g.c.w >> 16], acc1);
+}
+
+/* ---------------------------------------------------------------- main kernel ----- */
+
+/*
+ * grid  = nParts * kpp CTAs; CTA b serves partition b / kpp and the slices t of that partition
+ *         with t % kpp == b % kpp (static interleave - nothing global to reset between launches)
+ * block = any multiple of 32 up to 1024
+ * smem  = kSmemHeader + (W + 2) * 8 bytes (dynamic)
+ */
+template <int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(const MainArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    int *sliceCounter = reinterpret_cast<int *>(smem + 8);
+    double *win = reinterpret_cast<double *>(smem + kSmemHeader);
+
+    const int kpp = a.kpp;
+    const int p = blockIdx.x / kpp;
+    const int sub = blockIdx.x - p * kpp;
+    const int4 part = __ldg(reinterpret_cast<const int4 *>(a.parts) + p);
+    const int ps = part.x, pe = part.y;
+    if (pe <= ps) return; /* empty partition (uniform over the CTA) */
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+    /* ---- stage the x window: x[g0, winEnd) -> win[0, len), g0 = ps rounded down to even so
+     *      that the global source is 16-byte aligned; window element c lives at xs[c] ---- */
+    const int g0 = ps & ~1;
+    const int winEnd = min(ps + a.W, a.n);
+    const int len = winEnd - g0;
+    const double *xs = win + (ps - g0);
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    const uint32_t barAddr = smem_u32(bar);
+    if (tid == 0) {
+        *sliceCounter = nwarps;
+        mbar_init(barAddr, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tma_ok) {
+        if (tid == 0) {
+            const uint32_t bulkBytes = static_cast<uint32_t>(len & ~1) * 8u;
+            mbar_expect_tx(barAddr, bulkBytes);
+            const char *src = reinterpret_cast<const char *>(a.x + g0);
+            uint32_t dst = smem_u32(win);
+            for (uint32_t off = 0; off < bulkBytes; off += 32768u) {
+                const uint32_t chunk = min(32768u, bulkBytes - off);
+                tma_bulk_g2s(dst + off, src + off, chunk, barAddr);
+            }
+        } else if (tid == blockDim.x - 1 && (len & 1)) {
+            win[len - 1] = a.x[g0 + len - 1]; /* odd tail element */
+        }
+    } else {
+        for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
+    }
+
+    /* ---- slices of this CTA: local index t = sub + kpp*q, q handed out dynamically ---- */
+    const int nsl = part.w - part.z;
+    const int nq = (nsl - sub + kpp - 1) / kpp;
+    const uint64_t pol = make_evict_first_policy();
+    int q = warp;
+
+    /* first descriptor before waiting for the window (hides its latency) */
+    const uint2 *descs = reinterpret_cast<const uint2 *>(a.slices) + part.z + sub; /* {off256, w | wr<<16} */
+    uint2 d = make_uint2(0u, 0u);
+    if (q < nq) d = __ldg(descs + kpp * q);
+
+    if (tma_ok) {
+        while (!mbar_try_wait(barAddr, 0)) { }
+    }
+    __syncthreads(); /* tail element / fallback copy visible */
+
+    while (q < nq) {
+        const int t = sub + kpp * q;
+        const unsigned char *base = a.blob + static_cast<size_t>(d.x) * 256u;
+        const int w = d.y & 0xffffu, wr = d.y >> 16;
+        const double2 *ev = reinterpret_cast<const double2 *>(base) + lane;
+        const uint4 *ec = reinterpret_cast<const uint4 *>(base + static_cast<size_t>(w) * 512u) + lane;
+        double acc0 = 0.0, acc1 = 0.0;
+
+        /* ELL part, software pipelined by hand: the loads of group g+1 (one 128-bit column
+         * load + four 128-bit value loads = 2.5 KB per warp) are issued before group g is
+         * consumed, so a warp always has a full group in flight while it gathers and
+         * multiplies.  (Left to itself the compiler interleaves loads and their first uses and
+         * a warp ends up waiting on memory three times per group with < 2 KB outstanding.) */
+        const int nfull = w >> 2;
+        Group ga, gb;
+        if (nfull > 0) load_group(ga, ec, ev, 0, pol);
+        int g = 0;
+        for (; g + 2 <= nfull; g += 2) {
+            load_group(gb, ec, ev, g + 1, pol);
+            fma_group(ga, xs, acc0, acc1);
+            if (g + 2 < nfull) load_group(ga, ec, ev, g + 2, pol);
+            fma_group(gb, xs, acc0, acc1);
+        }
+        if (g < nfull) fma_group(ga, xs, acc0, acc1);
+        const int tail = w & 3;
+        if (tail) {
+            const uint4 c = ld_stream_u32x4(ec + nfull * 32, pol);
+            const double2 v0 = ld_stream_f64x2(ev + (4 * nfull + 0) * 32, pol);
+            double2 v1 = make_double2(0.0, 0.0), v2 = make_double2(0.0, 0.0);
+            if (tail > 1) v1 = ld_stream_f64x2(ev + (4 * nfull + 1) * 32, pol);
+            if (tail > 2) v2 = ld_stream_f64x2(ev + (4 * nfull + 2) * 32, pol);
+            acc0 = fma(v0.x, xs[c.x & 0xffffu], acc0);
+            acc1 = fma(v0.y, xs[c.z & 0xffffu], acc1);
+            if (tail > 1) {
+                acc0 = fma(v1.x, xs[c.x >> 16], acc0);
+                acc1 = fma(v1.y, xs[c.z >> 16], acc1);
+            }
+            if (tail > 2) {
+                acc0 = fma(v2.x, xs[c.y & 0xffffu], acc0);
+                acc1 = fma(v2.y, xs[c.w & 0xffffu], acc1);
+            }
+        }
+
+        /* in-slice remainder: 32-bit global columns, x gathered through L2.  Four columns
+         * at a time: all index/value loads first, then all gathers, then the FMAs, so that the
+         * two dependent memory latencies are paid once per four columns. */
+        if (wr) {
+            const size_t remOff = static_cast<size_t>(w) * 512u + static_cast<size_t>((w + 3) >> 2) * 512u;
+            const double2 *rv = reinterpret_cast<const double2 *>(base + remOff) + lane;
+            const int2 *rc = reinterpret_cast<const int2 *>(base + remOff + static_cast<size_t>(wr) * 512u) + lane;
+            double r0 = 0.0, r1 = 0.0;
+            int k = 0;
+            for (; k + 4 <= wr; k += 4) {
+                int2 c[4];
+                double2 v[4];
+                double xa[4], xb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c[i] = ld_stream_s32x2(rc + (k + i) * 32, pol);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = ld_stream_f64x2(rv + (k + i) * 32, pol);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    xa[i] = ld_gather_f64(a.x + c[i].x);
+                    xb[i] = ld_gather_f64(a.x + c[i].y);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    r0 = fma(v[i].x, xa[i], r0);
+                    r1 = fma(v[i].y, xb[i], r1);
+                }
+            }
+            for (; k < wr; ++k) {
+                const int2 c = ld_stream_s32x2(rc + k * 32, pol);
+                const double2 v = ld_stream_f64x2(rv + k * 32, pol);
+                r0 = fma(v.x, ld_gather_f64(a.x + c.x), r0);
+                r1 = fma(v.y, ld_gather_f64(a.x + c.y), r1);
+            }
+            acc0 += r0; /* y = dot_ell + dot_rem, as kernel.cu:162 + :76 */
+            acc1 += r1;
+        }
+
+        /* next slice + its descriptor while the stores drain */
+        int qn = 0;
+        if (lane == 0) qn = atomicAdd(sliceCounter, 1);
+        qn = __shfl_sync(0xffffffffu, qn, 0);
+        uint2 dn = make_uint2(0u, 0u);
+        if (qn < nq) dn = __ldg(descs + kpp * qn);
+
+        const int r = ps + t * EHYB_SLICE_ROWS + lane;
+        if (r < pe) a.y[r] = acc0;
+        if (r + 32 < pe) a.y[r + 32] = acc1;
+        q = qn;
+        d = dn;
+    }
+}
+
+/* ---------------------------------------------------------------- staged kernel --- */
+
+/*
+ * Same product, but the matrix stream itself goes through shared memory: every warp owns
+ * kSlotsPerWarp staging slots and keeps them filled with TMA bulk copies of the next chunks
+ * of its slices (a chunk = up to 16 ELL columns, or up to 8 remainder columns, of one 64-row
+ * slice: 10 KB).  The bytes in flight per SM are then set by the staging capacity
+ * (warps x slots x 10 KB, ~100 KB next to a 114 KB window) instead of by the registers a
+ * thread can devote to outstanding loads - ncu showed the direct kernel holding only ~24 KB
+ * per SM in flight and HBM 55 % busy.  Consumers read values (LDS.128), columns (LDS.128 /
+ * LDS.64) and gather x from the window (LDS.64).
+ *
+ * grid  = nParts * kpp, block = NW*32 threads,
+ * smem  = kStageHeader + align128((W+2)*8) + NW * kSlotsPerWarp * kSlotBytes
+ * Slices are dealt statically: warp i of CTA `sub` takes local slices sub + kpp*(i + NW*j).
+ */
+constexpr int kStageHeader = 512;  /* window mbarrier + 2*24 slot mbarriers */
+constexpr int kSlotsPerWarp = 2;
+constexpr int kMaxStageWarps = 24;
+/* a slot holds kcEll ELL columns (kc*512 B of values + kc/4*512 B of columns = kc*640 B) or
+ * kcRem remainder columns (kc*512 B of values + kc*256 B of columns); the column part starts
+ * at slot_val_bytes() in both cases */
+__host__ __device__ constexpr int slot_val_bytes(int kcEll, int kcRem) { return (kcEll > kcRem ? kcEll : kcRem) * 512; }
+__host__ __device__ constexpr int slot_bytes(int kcEll, int kcRem)
+{
+    return slot_val_bytes(kcEll, kcRem) + ((kcEll / 4) * 512 > kcRem * 256 ? (kcEll / 4) * 512 : kcRem * 256);
+}
+
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int2 lds_s32x2(uint32_t addr)
+{
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+/* walks the chunks of the slices of one warp; all members are warp-uniform */
+struct ChunkWalker {
+    const uint2 *descs; /* descriptors of this CTA's partition, offset by `sub` */
+    const unsigned char *blob;
+    int stride;         /* kpp * NW : distance between consecutive slices of this warp */
+    int kpp;
+    int nsl;            /* slices of the partition */
+    int t;              /* current slice (local index), >= nsl when exhausted */
+    uint2 d, dnext;     /* current / prefetched descriptor */
+    int ci;             /* chunk index inside the slice */
+    int kcE, kcR;       /* columns per ELL / remainder chunk */
+
+    __device__ __forceinline__ void start(const uint2 *descs_, const unsigned char *blob_, int sub, int kpp_, int warp, int nw, int nsl_, int kcEll, int kcRem)
+    {
+        descs = descs_; blob = blob_; kpp = kpp_; stride = kpp_ * nw; nsl = nsl_;
+        kcE = kcEll; kcR = kcRem;
+        t = sub + kpp_ * warp;
+        ci = 0;
+        d = make_uint2(0u, 0u); dnext = d;
+        if (t < nsl) d = __ldg(descs + (t - sub));
+        if (t + stride < nsl) dnext = __ldg(descs + (t + stride - sub));
+        sub_ = sub;
+    }
+    int sub_;
+    __device__ __forceinline__ bool done() const { return t >= nsl; }
+};
+
+struct ChunkMeta {
+    int kc;    /* columns in the chunk (0: empty slice) */
+    int flags; /* 1 = remainder chunk, 2 = last chunk of its slice, 4 = valid */
+    int t;     /* slice the chunk belongs to */
+};
+
+/* Describes the next chunk, advances the walker and (lane 0) starts its TMA copies. */
+__device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker &wk, uint32_t slotAddr, uint32_t barAddr, int lane)
+{
+    ChunkMeta m;
+    m.kc = 0; m.flags = 0; m.t = wk.t;
+    if (wk.done()) return m;
+    const int w = wk.d.y & 0xffffu, wr = wk.d.y >> 16;
+    const int nE = (w + wk.kcE - 1) / wk.kcE, nR = (wr + wk.kcR - 1) / wk.kcR;
+    const uint32_t slotValBytes = static_cast<uint32_t>(slot_val_bytes(wk.kcE, wk.kcR));
+    const int nc = max(1, nE + nR);
+    const unsigned char *base = wk.blob + static_cast<size_t>(wk.d.x) * 256u;
+    const unsigned char *src0 = base, *src1 = base;
+    uint32_t b0 = 0, b1 = 0;
+    m.flags = 4;
+    if (wk.ci < nE) {
+        const int k = wk.ci * wk.kcE;
+        m.kc = min(wk.kcE, w - k);
+        src0 = base + static_cast<size_t>(k) * 512u;
+        b0 = static_cast<uint32_t>(m.kc) * 512u;
+        src1 = base + static_cast<size_t>(w) * 512u + static_cast<size_t>(k >> 2) * 512u;
+        b1 = static_cast<uint32_t>((m.kc + 3) >> 2) * 512u;
+    } else if (wk.ci - nE < nR) {
+        const int k = (wk.ci - nE) * wk.kcR;
+        const size_t remOff = static_cast<size_t>(w) * 512u + static_cast<size_t>((w + 3) >> 2) * 512u;
+        m.kc = min(wk.kcR, wr - k);
+        m.flags |= 1;
+        src0 = base + remOff + static_cast<size_t>(k) * 512u;
+        b0 = static_cast<uint32_t>(m.kc) * 512u;
+        src1 = base + remOff + static_cast<size_t>(wr) * 512u + static_cast<size_t>(k) * 256u;
+        b1 = static_cast<uint32_t>(m.kc) * 256u;
+    }
+    if (wk.ci == nc - 1) m.flags |= 2;
+    if (lane == 0 && b0) {
+        mbar_expect_tx(barAddr, b0 + b1);
+        tma_bulk_g2s(slotAddr, src0, b0, barAddr);
+        tma_bulk_g2s(slotAddr + slotValBytes, src1, b1, barAddr);
+    }
+    /* advance */
+    if (wk.ci == nc - 1) {
+        wk.ci = 0;
+        wk.t += wk.stride;
+        wk.d = wk.dnext;
+        wk.dnext = make_uint2(0u, 0u);
+        if (wk.t + wk.stride < wk.nsl) wk.dnext = __ldg(wk.descs + (wk.t + wk.stride - wk.sub_));
+    } else {
+        wk.ci += 1;
+    }
+    return m;
+}
+
+template <int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int kpp = a.kpp;
+    const int p = blockIdx.x / kpp;
+    const int sub = blockIdx.x - p * kpp;
+    const int4 part = __ldg(reinterpret_cast<const int4 *>(a.parts) + p);
+    const int ps = part.x, pe = part.y;
+    if (pe <= ps) return;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = blockDim.x >> 5;
+    const int g0 = ps & ~1;
+    const int winEnd = min(ps + a.W, a.n);
+    const int len = winEnd - g0;
+    double *win = reinterpret_cast<double *>(smem + kStageHeader);
+    const uint32_t winBytes = (static_cast<uint32_t>(a.W + 2) * 8u + 127u) & ~127u;
+    const uint32_t xsAddr = smem_u32(win) + static_cast<uint32_t>(ps - g0) * 8u;
+    const uint32_t winBar = smem_u32(smem);
+    const uint32_t slotBar0 = smem_u32(smem + 16) + static_cast<uint32_t>(warp * kSlotsPerWarp) * 8u;
+    const uint32_t kSlotBytes = static_cast<uint32_t>(slot_bytes(a.kcEll, a.kcRem));
+    const uint32_t kSlotValBytes = static_cast<uint32_t>(slot_val_bytes(a.kcEll, a.kcRem));
+    const uint32_t slot0 = smem_u32(smem + kStageHeader) + winBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+
+    /* Programmatic dependent launch: let the next grid in the stream start as soon as SMs free
+     * up.  Its matrix stream (constant data) then overlaps this grid's tail; everything that
+     * touches x or y comes after its own griddepcontrol.wait below. */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid == 0) {
+        mbar_init(winBar, 1);
+        for (int i = 0; i < nw * kSlotsPerWarp; ++i) mbar_init(smem_u32(smem + 16) + i * 8u, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    /* the matrix stream does not depend on x, y or the previous grid: start it right away */
+    ChunkWalker wk;
+    wk.start(reinterpret_cast<const uint2 *>(a.slices) + part.z + sub, a.blob, sub, kpp, warp, nw, part.w - part.z, a.kcEll, a.kcRem);
+    ChunkMeta m0 = issue_chunk(wk, slot0, slotBar0, lane);
+    ChunkMeta m1 = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane);
+    uint32_t ph0 = 0, ph1 = 0;
+
+    /* x (and later y) belong to the stream's previous work: wait for it here.  Only the
+     * threads that touch x before the window barrier wait; everyone else is ordered behind
+     * them through that barrier. */
+    if (!tma_ok || tid == 0 || (tid == blockDim.x - 1 && (len & 1))) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tma_ok) {
+        if (tid == 0) {
+            const uint32_t bulkBytes = static_cast<uint32_t>(len & ~1) * 8u;
+            mbar_expect_tx(winBar, bulkBytes);
+            const char *src = reinterpret_cast<const char *>(a.x + g0);
+            const uint32_t dst = smem_u32(win);
+            for (uint32_t off = 0; off < bulkBytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, min(32768u, bulkBytes - off), winBar);
+        } else if (tid == nw * 32 - 1 && (len & 1)) {
+            win[len - 1] = a.x[g0 + len - 1]; /* odd tail element, by the last streaming thread */
+        }
+    } else {
+        for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
+    }
+
+
+    if (tma_ok) {
+        while (!mbar_try_wait(winBar, 0)) { }
+    }
+    __syncthreads(); /* odd tail element / fallback copy visible */
+
+    double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
+    auto consume = [&](const ChunkMeta &m, uint32_t slot, uint32_t bar, uint32_t &ph) {
+        if (m.kc) {
+            while (!mbar_try_wait(bar, ph)) { }
+            ph ^= 1u;
+            const uint32_t vAddr = slot + static_cast<uint32_t>(lane) * 16u;
+            if (a.dbg & ((m.flags & 1) ? 1 : 2)) {
+                /* timing experiment: stream the chunk, skip its arithmetic */
+            } else if (!(m.flags & 1)) {
+                const uint32_t cAddr = slot + kSlotValBytes + static_cast<uint32_t>(lane) * 16u;
+                const int nfull = m.kc >> 2;
+#pragma unroll 2
+                for (int g = 0; g < nfull; ++g) {
+                    const uint4 c = lds_u32x4(cAddr + g * 512u);
+                    const double2 v0 = lds_f64x2(vAddr + (4 * g + 0) * 512u);
+                    const double2 v1 = lds_f64x2(vAddr + (4 * g + 1) * 512u);
+                    const double2 v2 = lds_f64x2(vAddr + (4 * g + 2) * 512u);
+                    const double2 v3 = lds_f64x2(vAddr + (4 * g + 3) * 512u);
+                    double x00, x01, x10, x11, x20, x21, x30, x31;
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x00) : "r"(xsAddr + (c.x & 0xffffu) * 8u));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x01) : "r"(xsAddr + (c.z & 0xffffu) * 8u));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x10) : "r"(xsAddr + (c.x >> 16) * 8u));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x11) : "r"(xsAddr + (c.z >> 16) * 8u));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x20) : "r"(xsAddr + (c.y & 0xffffu) * 8u));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x21) : "r"(xsAddr + (c.w & 0xffffu) * 8u));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x30) : "r"(xsAddr + (c.y >> 16) * 8u));
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x31) : "r"(xsAddr + (c.w >> 16) * 8u));
+                    acc0 = fma(v0.x, x00, acc0);
+                    acc1 = fma(v0.y, x01, acc1);
+                    acc0 = fma(v1.x, x10, acc0);
+                    acc1 = fma(v1.y, x11, acc1);
+                    acc0 = fma(v2.x, x20, acc0);
+                    acc1 = fma(v2.y, x21, acc1);
+                    acc0 = fma(v3.x, x30, acc0);
+                    acc1 = fma(v3.y, x31, acc1);
+                }
+                const int tail = m.kc & 3;
+                if (tail) {
+                    const uint4 c = lds_u32x4(cAddr + nfull * 512u);
+                    const uint32_t cols[3] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu};
+                    const uint32_t cols1[3] = {c.z & 0xffffu, c.z >> 16, c.w & 0xffffu};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        if (i < tail) {
+                            const double2 v = lds_f64x2(vAddr + (4 * nfull + i) * 512u);
+                            double xa, xb;
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(xa) : "r"(xsAddr + cols[i] * 8u));
+                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(xb) : "r"(xsAddr + cols1[i] * 8u));
+                            acc0 = fma(v.x, xa, acc0);
+                            acc1 = fma(v.y, xb, acc1);
+                        }
+                    }
+                }
+            } else {
+                /* remainder chunk: all column loads, then all x gathers (L2), then the FMAs in
+                 * column order - the gather latency is paid once per four columns */
+                const uint32_t cAddr = slot + kSlotValBytes + static_cast<uint32_t>(lane) * 8u;
+                int k = 0;
+                for (; k + 8 <= m.kc; k += 8) {
+                    int2 c[8];
+                    double xa[8], xb[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) c[i] = lds_s32x2(cAddr + (k + i) * 256u);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        xa[i] = ld_gather_f64(a.x + c[i].x);
+                        xb[i] = ld_gather_f64(a.x + c[i].y);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const double2 v = lds_f64x2(vAddr + (k + i) * 512u);
+                        r0 = fma(v.x, xa[i], r0);
+                        r1 = fma(v.y, xb[i], r1);
+                    }
+                }
+                for (; k + 4 <= m.kc; k += 4) {
+                    int2 c[4];
+                    double xa[4], xb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c[i] = lds_s32x2(cAddr + (k + i) * 256u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        xa[i] = ld_gather_f64(a.x + c[i].x);
+                        xb[i] = ld_gather_f64(a.x + c[i].y);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double2 v = lds_f64x2(vAddr + (k + i) * 512u);
+                        r0 = fma(v.x, xa[i], r0);
+                        r1 = fma(v.y, xb[i], r1);
+                    }
+                }
+                for (; k < m.kc; ++k) {
+                    const int2 c = lds_s32x2(cAddr + k * 256u);
+                    const double2 v = lds_f64x2(vAddr + k * 512u);
+                    r0 = fma(v.x, ld_gather_f64(a.x + c.x), r0);
+                    r1 = fma(v.y, ld_gather_f64(a.x + c.y), r1);
+                }
+            }
+        }
+        if (m.flags & 2) {
+            const int r = ps + m.t * EHYB_SLICE_ROWS + lane;
+            if (r < pe) a.y[r] = acc0 + r0; /* y = dot_ell + dot_rem, as kernel.cu:162 + :76 */
+            if (r + 32 < pe) a.y[r + 32] = acc1 + r1;
+            acc0 = acc1 = r0 = r1 = 0.0;
+        }
+        __syncwarp(); /* every lane is done with the slot before it is refilled */
+    };
+
+    while (m0.flags & 4) {
+        consume(m0, slot0, slotBar0, ph0);
+        m0 = issue_chunk(wk, slot0, slotBar0, lane);
+        if (!(m1.flags & 4)) break;
+        consume(m1, slot0 + kSlotBytes, slotBar0 + 8u, ph1);
+        m1 = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane);
+    }
+}
+
+/* ---------------------------------------------------------------- overflow kernel -- */
+
+/*
+ * COO remainder (row-sorted): each warp takes kOvfPerWarp consecutive entries, 32 at a time;
+ * products are reduced per row with a warp-shuffle segmented scan and the last lane of every
+ * row segment adds its sum to y (the row's ELL + in-slice part is already there: this kernel
+ * runs after ehyb_main_kernel on the same stream).  A segment that continues into the next
+ * group of 32 is carried in registers instead of being flushed.
+ */
+constexpr int kOvfPerWarp = 32 * 8;
+
+__global__ void __launch_bounds__(256) ehyb_overflow_kernel(const OverflowArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warpId = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t begin = warpId * kOvfPerWarp;
+    if (begin >= a.count) return;
+    const int64_t end = min(begin + kOvfPerWarp, a.count);
+    int carryRow = -1;
+    double carry = 0.0;
+    for (int64_t base = begin; base < end; base += 32) {
+        const int64_t i = base + lane;
+        const bool live = i < end;
+        int r = -2 - lane; /* dead lanes: unique rows, never merged, never written */
+        double prod = 0.0;
+        if (live) {
+            r = __ldg(a.row + i);
+            prod = __ldg(a.val + i) * __ldg(a.x + __ldg(a.col + i));
+        }
+        if (lane == 0 && r == carryRow) prod += carry; /* continue the carried segment */
+        const int flushRow = (lane == 0 && carryRow >= 0 && r != carryRow) ? carryRow : -1;
+        if (flushRow >= 0) atomicAdd(a.y + flushRow, carry);
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, prod, off);
+            const int rr = __shfl_up_sync(0xffffffffu, r, off);
+            if (lane >= off && rr == r) prod += t;
+        }
+        const int rnext = __shfl_down_sync(0xffffffffu, r, 1);
+        const bool tailOfSeg = live && (lane == 31 || rnext != r);
+        /* the segment ending in lane 31 may continue in the next group: carry it */
+        const bool carries = lane == 31 && live && base + 32 < end;
+        if (tailOfSeg && !carries) atomicAdd(a.y + r, prod);
+        carryRow = __shfl_sync(0xffffffffu, carries ? r : -1, 31);
+        carry = __shfl_sync(0xffffffffu, prod, 31);
+    }
+    if (lane == 0 && carryRow >= 0) atomicAdd(a.y + carryRow, carry);
+}
+
+} /* namespace ehyb */

@@ -25,8 +25,9 @@
  *              by a segmented warp reduction and added to y.
  *
  * Unlike the reference layout (W/32 slices per partition, rows beyond the window in a
- * separate global list) every row of a partition belongs to a slice here: a row beyond the
- * window simply has no ELL entries.
+ * separate global list) every row of a partition belongs to a slice here; a row beyond the
+ * window has no ELL entries, all of its entries are remainder - the reference's
+ * classification (convert.c:128-134, :285-306).
  */
 #include <limits.h>
 #include <math.h>
@@ -86,7 +87,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     const int n = (int)n64, P = nParts, W = opts->W;
     const int64_t ncols = opts->ncols > 0 ? opts->ncols : n;
     const int longThr = opts->long_row_threshold > 0 ? opts->long_row_threshold : EHYB_REF_LONG_ROW;
-    const double fill = opts->er_fill < 0 ? 0.5 : opts->er_fill;
+    const double fill = opts->er_fill < 0 ? 0.0 : opts->er_fill;
     int need = (int)ceil(fill * SR);
     if (need < 1) need = 1;
     if (need > SR) need = SR;
@@ -118,20 +119,21 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     sliceOff = (int64_t *)calloc((size_t)nSlices + 1, sizeof(int64_t));
     if (!L->slices || !sliceOff) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
 
-    /* pass 1: classify rows, choose slice widths */
+    /* pass 1a: classify the entries of every row (ELL count; -1 marks a long row) */
     int64_t nnzEll = 0, nnzRemIn = 0, nnzOvf = 0, padEll = 0, padRem = 0, nLong = 0;
     int bad = 0;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nnzEll, nnzRemIn, nnzOvf, padEll, padRem, nLong) reduction(| : bad)
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nLong) reduction(| : bad)
     for (int p = 0; p < P; ++p) {
         const int ps = pb[p], pe = pb[p + 1];
         const int64_t winEnd = (int64_t)ps + W < n ? (int64_t)ps + W : n;
         int firstReg = ps, scanning = 1;
         for (int r = ps; r < pe; ++r) {
             int ell = 0;
+            const int inWindowRow = r - ps < W; /* rows beyond the window are remainder as a whole (convert.c:128-134) */
             for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
                 const int c = col[e];
                 if (c < 0 || c >= ncols) bad = 1;
-                ell += (c >= ps && c < winEnd);
+                ell += (inWindowRow && c >= ps && c < winEnd);
             }
             if (scanning && ell > longThr) { /* long rows sit at the head of the partition */
                 firstReg = r + 1;
@@ -142,6 +144,43 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
             L->rowEll[r] = ell;
         }
         nLong += firstReg - ps;
+    }
+
+    /* er_fill < 0: choose between "every remainder entry in its slice" (need = 1) and "a
+     * remainder column only while half of the lanes use it" (need = 32) by stored bytes:
+     * 12 B per in-slice slot (padding included), 16 B per overflow entry plus the cost of
+     * launching the overflow kernel at all (~5 us of streaming, 30 MB). */
+    if (opts->er_fill < 0) {
+        double cost[2] = {0.0, 0.0};
+        int64_t ovfB = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : cost[:2], ovfB)
+        for (int p = 0; p < P; ++p) {
+            const int ps = pb[p], pe = pb[p + 1];
+            for (int s = L->parts[p].sliceStart; s < L->parts[p].sliceEnd; ++s) {
+                const int r0 = ps + (s - L->parts[p].sliceStart) * SR;
+                const int r1 = r0 + SR < pe ? r0 + SR : pe;
+                int m = 0, rem[SR];
+                for (int r = r0; r < r1; ++r) {
+                    if (L->rowEll[r] < 0) continue;
+                    const int64_t sp = rowPtr[r + 1] - rowPtr[r] - L->rowEll[r];
+                    rem[m++] = sp > 65535 ? 65535 : (int)sp;
+                }
+                qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
+                const int wrA = m >= 1 ? rem[0] : 0, wrB = m >= SR / 2 ? rem[SR / 2 - 1] : 0;
+                cost[0] += 768.0 * wrA;
+                cost[1] += 768.0 * wrB;
+                for (int i = 0; i < m; ++i)
+                    if (rem[i] > wrB) { cost[1] += 16.0 * (rem[i] - wrB); ovfB += rem[i] - wrB; }
+            }
+        }
+        if (ovfB > 0) cost[1] += 30e6;
+        need = cost[0] <= cost[1] ? 1 : SR / 2;
+    }
+
+    /* pass 1b: slice widths, in-slice / overflow split */
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : nnzEll, nnzRemIn, nnzOvf, padEll, padRem) reduction(| : bad)
+    for (int p = 0; p < P; ++p) {
+        const int ps = pb[p], pe = pb[p + 1];
         for (int s = L->parts[p].sliceStart; s < L->parts[p].sliceEnd; ++s) {
             const int r0 = ps + (s - L->parts[p].sliceStart) * SR;
             const int r1 = r0 + SR < pe ? r0 + SR : pe;
@@ -214,7 +253,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
             int32_t *rcol = (int32_t *)(base + reg_rem_col(w, wr));
             for (int r = r0; r < r1; ++r) {
                 const int t = r - r0, lane = t % 32, h = t / 32;
-                const int isLong = L->rowEll[r] < 0;
+                const int isLong = L->rowEll[r] < 0 || r - ps >= W; /* no ELL entries: long row, or beyond the window */
                 int kE = 0, kR = 0;
                 int64_t o = L->ovfPtr[r];
                 for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
@@ -223,7 +262,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                         ev[((int64_t)kE * 32 + lane) * 2 + h] = val[e];
                         ec[(((int64_t)(kE / 4) * 32 + lane) * 2 + h) * 4 + kE % 4] = (uint16_t)(c - ps);
                         ++kE;
-                    } else if (!isLong && kR < wr) {
+                    } else if (L->rowEll[r] >= 0 && kR < wr) {
                         rv[((int64_t)kR * 32 + lane) * 2 + h] = val[e];
                         rcol[((int64_t)kR * 32 + lane) * 2 + h] = c;
                         ++kR;

@@ -47,7 +47,7 @@ int ehyb_build_graph(const matrixCOO *m, int symmetric, uint32_t **xadj_out, uin
          * entry order; duplicates are kept: reordering.c:56-89. */
         if (2 * nnz > (int64_t)UINT32_MAX) { free(xadj); return ehyb_fail(EHYB_ERR_LIMIT, "graph larger than 2^32 edges"); }
         uint32_t *fill = (uint32_t *)calloc((size_t)n + 1, sizeof(uint32_t));
-        adj = (uint32_t *)malloc((size_t)(2 * nnz ? 2 * nnz : 1) * sizeof(uint32_t));
+        adj = (uint32_t *)malloc((size_t)(nnz > 0 ? 2 * nnz : 1) * sizeof(uint32_t));
         if (!fill || !adj) { free(xadj); free(fill); free(adj); return ehyb_fail(EHYB_ERR_NOMEM, "graph: out of memory"); }
         for (int64_t e = 0; e < nnz; ++e) {
             fill[m->I[e]] += 1;

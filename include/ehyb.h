@@ -120,7 +120,8 @@ typedef struct ehyb_layout_opts {
     int W;                  /* x window length; 0 = matrixCOO.vectorCacheSize */
     int ctasPerPart;        /* 0 = matrixCOO.kernelPerPart (min 1) */
     double er_fill;         /* in-slice remainder column kept while >= er_fill*64 rows use it;
-                               0 = keep every remainder entry in its slice; default 0.5 */
+                               0 = keep every remainder entry in its slice; < 0 = choose between 0
+                               and 0.5 by stored bytes (the default of spmvGPuEHYB) */
     int long_row_threshold; /* rows at a partition head with more in-window entries than this go
                                whole to the overflow list; 0 = 512 (reference threadLongVec) */
     int64_t ncols;          /* columns of the local operator (n + halo); 0 = n */
@@ -181,7 +182,12 @@ typedef struct ehyb_session_opts {
     int use_graph;      /* capture the per-product launches in a CUDA graph (default 1) */
     int l2_persist_x;   /* L2 access-policy window on x for the remainder gathers (default 1) */
     int64_t halo_cols;  /* extra x entries after the n local ones (multi-GPU), default 0 */
+    int kernel;         /* 0 = default, 1 = direct (matrix streamed with 128-bit global loads),
+                           2 = staged (matrix streamed through shared memory by TMA) */
 } ehyb_session_opts;
+
+#define EHYB_KERNEL_DIRECT 1
+#define EHYB_KERNEL_STAGED 2
 
 void ehyb_session_opts_default(ehyb_session_opts *o);
 

@@ -6,11 +6,16 @@
  * (REF=/root/reference) and this file #includes solver_test.c from there so that its
  * static readers (matrixRead_sym / matrixRead_unsym) can be driven from the tests.
  *
- * Two things are intercepted, both at link level, neither by editing the reference:
+ * Three things are intercepted, all at link level, none by editing the reference:
  *   - exit(): the reference aborts with exit(0|1) on inconsistent input
  *     (convert.c:122-125, :136-139, ...).  This file defines its own exit() and the
  *     library is linked -Bsymbolic-functions, so the reference's calls bind to it; it
  *     longjmps back into the wrapper, which then returns a non-zero status.
+ *   - malloc(): the reference accumulates into malloc'd buffers it never zeroes (golden y,
+ *     solver_test.c:38,138; expandNumInRow, reordering.c:55 - SURVEY.md B-10, B-11) and only
+ *     works on freshly mapped zero pages.  Inside a long-lived test process malloc recycles
+ *     memory, so the library's own malloc() hands out zeroed memory - the state the reference
+ *     silently assumes.
  *   - MTMETIS_PartGraphKway / mtmetis_init_options: libmtmetis.a is not position
  *     independent and cannot be linked into a shared object.  The shim forwards the
  *     call - same arguments, same binary - to bin/ehyb_mtmetis (a 40-line main() around
@@ -42,6 +47,9 @@ extern "C" void exit(int status) noexcept
     fflush(stdout);
     _exit(status ? status : 97);
 }
+
+/* zero-filled malloc for the reference objects (bound through -Bsymbolic-functions) */
+extern "C" void *malloc(size_t n) noexcept { return calloc(1, n ? n : 1); }
 
 #define REF_GUARD(stmt)                       \
     do {                                      \

@@ -1,0 +1,110 @@
+"""GPU parity: the CUDA product (through the C ABI) against the oracle.
+
+Bars: y bit-identical to the oracle's FMA-ordered emulation of the reference kernels
+(kernel.cu:150-163, :176-189) when every remainder entry stays in its slice (er_fill=0), and
+within |y - y_ref| <= 1e-12 * (|A||x|) per row of the CPU CSR product in every configuration.
+"""
+import numpy as np
+import pytest
+
+from ehyb_spmv_gpu_b200 import api
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # kind, dims, nParts, W, kpp, threads
+    ("lap2d", (64, 64), 3, 2048, 1, 128),
+    ("lap2d", (256, 256), 10, 8192, 8, 1024),   # the reference's own plan for n=65536 (_small path)
+    ("lap2d", (256, 256), 37, 1856, 1, 256),
+    ("st27", (32, 32, 32), 8, 4224, 2, 512),
+    ("st27", (48, 48, 48), 20, 5632, 1, 512),
+    ("st27", (40, 40, 40), 5, 12864, 3, 1024),
+    ("elas", (16, 16, 16), 6, 2112, 1, 256),
+    ("st27", (32, 32, 32), 8, 2048, 1, 512),    # partitions larger than the window: rows beyond it
+]
+
+
+KERNELS = [1, 2]  # EHYB_KERNEL_DIRECT, EHYB_KERNEL_STAGED
+
+
+def _run(orc, kind, dims, P, W, kpp, threads, fill, x, kernel=0):
+    m = util.product_pipeline(kind, dims, P, W, kpp, x=x)
+    lay = api.Layout(m, er_fill=fill)
+    s = api.Session(lay, threads=threads, kernel=kernel)
+    xr = m.vector_reorder(x)
+    y_perm = s.spmv_host(xr)
+    y = m.vector_recover(y_perm)
+    st = lay.stats()
+    s.free(); lay.free()
+    return m, y_perm, y, st
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kind,dims,P,W,kpp,threads", CASES)
+def test_bit_exact_vs_fma_emulation(orc, kind, dims, P, W, kpp, threads, kernel):
+    n = util.lower_entries(kind, dims)[0]
+    x = orc.x_reference(n)
+    m, y_perm, y, st = _run(orc, kind, dims, P, W, kpp, threads, 0.0, x, kernel)
+    assert st["nOverflow"] == 0
+    mo, ro = util.oracle_pipeline(orc, kind, dims, P, W, x=x)
+    eo = orc.convert(ro)
+    y_emul = orc.emulate(eo, ro, orc.vector_reorder(x, ro["reorderList"]), use_fma=True)
+    assert np.array_equal(y_perm, y_emul), f"max diff {np.abs(y_perm - y_emul).max()}"
+    m.free()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kind,dims,P,W,kpp,threads", CASES)
+@pytest.mark.parametrize("fill", [0.0, 0.5, 1.0])
+def test_accuracy_gate(orc, kind, dims, P, W, kpp, threads, fill, kernel):
+    n = util.lower_entries(kind, dims)[0]
+    x = util.x_random(n, seed=P)
+    m, y_perm, y, st = _run(orc, kind, dims, P, W, kpp, threads, fill, x, kernel)
+    mo = orc.read_sym(*util.lower_entries(kind, dims), x)
+    y_ref = orc.csr_spmv(mo["rowIdx"], mo["J"], mo["V"], x)
+    absAx = orc.csr_abs_spmv(mo["rowIdx"], mo["J"], mo["V"], x)
+    util.assert_within_gate(y, y_ref, absAx)
+    util.assert_within_gate(y, mo["y"], absAx)  # the driver's golden y (file-order accumulation)
+    if fill >= 0.5:
+        assert st["nnzEll"] + st["nnzRemInSlice"] + st["nnzOverflow"] == st["nnz"]
+    m.free()
+
+
+def test_repeated_products_do_all_the_work(orc):
+    """The reference's remainder phase only runs in its first launch; here a
+    second product with a different x must be fully recomputed."""
+    kind, dims, P, W = "st27", (32, 32, 32), 8, 4224
+    n = util.lower_entries(kind, dims)[0]
+    m = util.product_pipeline(kind, dims, P, W, 1)
+    lay = api.Layout(m, er_fill=0.5)
+    s = api.Session(lay, threads=512)
+    mo = orc.read_sym(*util.lower_entries(kind, dims))
+    for seed in (1, 2, 3):
+        x = util.x_random(n, seed)
+        y = m.vector_recover(s.spmv_host(m.vector_reorder(x)))
+        util.assert_within_gate(y, orc.csr_spmv(mo["rowIdx"], mo["J"], mo["V"], x),
+                                orc.csr_abs_spmv(mo["rowIdx"], mo["J"], mo["V"], x))
+    s.free(); lay.free(); m.free()
+
+
+def test_timed_loop_and_batch(orc):
+    kind, dims, P, W = "st27", (32, 32, 32), 8, 4224
+    n = util.lower_entries(kind, dims)[0]
+    x = orc.x_reference(n)
+    m = util.product_pipeline(kind, dims, P, W, 1, x=x)
+    lay = api.Layout(m)
+    s = api.Session(lay)
+    xr = m.vector_reorder(x)
+    s.set_x(xr)
+    ms, kms = s.time_spmv(3, 10, kernel_only=True)
+    assert ms > 0 and kms > 0
+    y1 = s.get_y()
+    xs = [np.ascontiguousarray(xr * (i + 1)) for i in range(5)]
+    ys = [np.empty(n) for _ in range(5)]
+    s.spmv_host_batch(xs, ys)
+    for i in range(5):
+        assert np.array_equal(ys[i], s.spmv_host(xs[i]))
+    assert np.array_equal(ys[0], y1)
+    assert s.launches_per_spmv() in (1, 2)
+    s.free(); lay.free(); m.free()
