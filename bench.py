@@ -95,6 +95,24 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+class stdout_to_stderr:
+    """The C library prints the reference's log lines on stdout; keep stdout for the JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def build_matrix(grid, x=None):
     """generate -> matrixCOO -> plan -> mt-metis -> reorder -> tuned layout (all product code)."""
     from ehyb_spmv_gpu_b200 import api
@@ -111,7 +129,6 @@ def build_matrix(grid, x=None):
     pl = api.plan(n, dev)
     m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
     m.reorder()
-    arr_pb = m.arrays()["partBoundary"] if False else None
     lay = api.Layout(m, er_fill=float(os.environ.get("EHYB_ER_FILL", "-1")))
     return m, lay, x, pl, time.time() - t0
 
@@ -138,7 +155,8 @@ def run_ours(args):
         from ehyb_spmv_gpu_b200 import multigpu
         return multigpu.bench(args, rank, world, local, GRID, WORKLOAD)
 
-    m, lay, x, pl, t_prep = build_matrix(GRID)
+    with stdout_to_stderr():
+        m, lay, x, pl, t_prep = build_matrix(GRID)
     st = lay.stats()
     s = api.Session(lay, device=local)
     xr = m.vector_reorder(x)

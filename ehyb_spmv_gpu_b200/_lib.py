@@ -63,7 +63,7 @@ class Plan(C.Structure):
 
 class LayoutOpts(C.Structure):
     _fields_ = [("W", C.c_int), ("ctasPerPart", C.c_int), ("er_fill", C.c_double),
-                ("long_row_threshold", C.c_int), ("ncols", C.c_int64)]
+                ("long_row_threshold", C.c_int), ("ncols", C.c_int64), ("halo_in_overflow", C.c_int)]
 
 
 class SliceDesc(C.Structure):
@@ -112,6 +112,11 @@ EXPORTS = [
     "ehyb_launches_per_spmv", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
     "ehyb_gen_lower", "ehyb_coo_from_lower", "ehyb_coo_from_general", "ehyb_gen_rmat", "ehyb_x_reference",
     "ehyb_read_mtx", "ehyb_write_mtx", "ehyb_coo_free",
+    "ehyb_mg_local_build", "ehyb_mg_local_halo", "ehyb_mg_local_set_send", "ehyb_mg_local_graph",
+    "ehyb_mg_local_finish", "ehyb_mg_local_view", "ehyb_mg_local_free", "ehyb_mg_unique_id",
+    "ehyb_mg_session_create", "ehyb_mg_session_handle", "ehyb_mg_spmv", "ehyb_mg_time_spmv",
+    "ehyb_mg_session_free", "ehyb_gen_stencil27_rows", "ehyb_host_alloc_pinned", "ehyb_host_free_pinned",
+    "ehyb_session_info",
 ]
 
 _lib = None

@@ -264,7 +264,7 @@ extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, 
 }
 
 /* the launches of one product, on `s` */
-static int launch_product(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
+static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
 {
     MainArgs a;
     a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
@@ -288,15 +288,25 @@ static int launch_product(ehyb_handle *h, const double *x_d, double *y_d, cudaSt
         k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, s>>>(a);
         CU(cudaGetLastError());
     }
-    if (h->nOvf > 0) {
-        OverflowArgs o;
-        o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = x_d; o.y = y_d;
-        const int64_t warps = (h->nOvf + kOvfPerWarp - 1) / kOvfPerWarp;
-        const unsigned blocks = (unsigned)((warps + 7) / 8);
-        ehyb_overflow_kernel<<<blocks, 256, 0, s>>>(o);
-        CU(cudaGetLastError());
-    }
     return EHYB_OK;
+}
+
+static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
+{
+    if (h->nOvf <= 0) return EHYB_OK;
+    OverflowArgs o;
+    o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = x_d; o.y = y_d;
+    const int64_t warps = (h->nOvf + kOvfPerWarp - 1) / kOvfPerWarp;
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    ehyb_overflow_kernel<<<blocks, 256, 0, s>>>(o);
+    CU(cudaGetLastError());
+    return EHYB_OK;
+}
+
+static int launch_product(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
+{
+    int rc = launch_main(h, x_d, y_d, s);
+    return rc ? rc : launch_overflow(h, x_d, y_d, s);
 }
 
 extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h) { return h ? (h->nOvf > 0 ? 2 : 1) : 0; }
@@ -499,5 +509,220 @@ extern "C" int ehyb_host_alloc_pinned(size_t bytes, void **out)
 extern "C" int ehyb_host_free_pinned(void *p)
 {
     CU(cudaFreeHost(p));
+    return EHYB_OK;
+}
+
+/* ====================================================================================== */
+/* multi-GPU: one process per GPU, x halo exchanged with NCCL send/recv every product       */
+/* ====================================================================================== */
+#include <dlfcn.h>
+#include <nccl.h>
+
+/* host side (host/mg.c) */
+extern "C" int ehyb_mg_local_view(const ehyb_mg_local *L, const matrixCOO **coo, const ehyb_layout **layout, int64_t *nSend,
+                                  const int32_t **sendIdx, const int64_t **sendCount);
+extern "C" int ehyb_mg_local_halo(const ehyb_mg_local *L, int64_t *nHalo, const int64_t **haloGlobal, const int64_t **recvCount);
+
+/* NCCL is bound at run time (the library must load on hosts without it; under PyTorch the
+ * process-wide libnccl.so.2 is the one torch already loaded) */
+struct NcclApi {
+    void *dl;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)(void);
+    ncclResult_t (*GroupEnd)(void);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+static NcclApi g_nccl;
+
+static int nccl_load(void)
+{
+    if (g_nccl.dl) return EHYB_OK;
+    const char *names[] = {getenv("EHYB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *dl = NULL;
+    for (int i = 0; i < 3 && !dl; ++i)
+        if (names[i] && names[i][0]) dl = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!dl) return ehyb_fail(EHYB_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                  \
+    *(void **)(&g_nccl.field) = dlsym(dl, name);                                          \
+    if (!g_nccl.field) return ehyb_fail(EHYB_ERR_NCCL, "libnccl lacks %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.dl = dl;
+    return EHYB_OK;
+}
+
+#define NC(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r__ = (call);                                                                        \
+        if (r__ != ncclSuccess)                                                                           \
+            return ehyb_fail(EHYB_ERR_NCCL, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
+    } while (0)
+
+struct ehyb_mg_session {
+    ehyb_handle *h;
+    int rank, nranks;
+    ncclComm_t comm;
+    cudaStream_t commStream;
+    cudaEvent_t evX, evHalo;
+    int64_t nSend, nHalo;
+    int32_t *sendIdx_d;
+    double *sendBuf_d;
+    int64_t *sendCount, *recvCount; /* host copies */
+};
+
+__global__ void ehyb_pack_kernel(const double *__restrict__ x, const int32_t *__restrict__ idx, double *__restrict__ out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = x[idx[i]];
+}
+
+extern "C" int ehyb_mg_unique_id(void *id128)
+{
+    if (!id128) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_unique_id: NULL");
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return EHYB_OK;
+}
+
+extern "C" void ehyb_mg_session_free(ehyb_mg_session *s)
+{
+    if (!s) return;
+    if (s->h) cudaSetDevice(s->h->device);
+    if (s->commStream) cudaStreamSynchronize(s->commStream);
+    if (s->comm && g_nccl.dl) g_nccl.CommDestroy(s->comm);
+    cudaFree(s->sendIdx_d); cudaFree(s->sendBuf_d);
+    if (s->evX) cudaEventDestroy(s->evX);
+    if (s->evHalo) cudaEventDestroy(s->evHalo);
+    if (s->commStream) cudaStreamDestroy(s->commStream);
+    free(s->sendCount); free(s->recvCount);
+    ehyb_free(s->h);
+    free(s);
+}
+
+/* Collective over all ranks (ncclCommInitRank).  id128 comes from rank 0's ehyb_mg_unique_id,
+ * distributed by the caller. */
+extern "C" int ehyb_mg_session_create(const ehyb_mg_local *L, int rank, int nranks, int device, const void *id128,
+                                      ehyb_mg_session **out)
+{
+    if (!L || !id128 || !out || nranks <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_session_create: bad argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    const ehyb_layout *layout = NULL;
+    const int32_t *sendIdx = NULL;
+    const int64_t *sendCount = NULL, *recvCount = NULL;
+    int64_t nSend = 0, nHalo = 0;
+    rc = ehyb_mg_local_view(L, NULL, &layout, &nSend, &sendIdx, &sendCount);
+    if (rc) return rc;
+    ehyb_mg_local_halo(L, &nHalo, NULL, &recvCount);
+    ehyb_mg_session *s = (ehyb_mg_session *)calloc(1, sizeof *s);
+    if (!s) return ehyb_fail(EHYB_ERR_NOMEM, "mg session: out of memory");
+    s->rank = rank; s->nranks = nranks; s->nSend = nSend; s->nHalo = nHalo;
+    ehyb_session_opts o;
+    ehyb_session_opts_default(&o);
+    o.device = device;
+    rc = ehyb_upload(layout, &o, &s->h);
+    if (rc) { free(s); return rc; }
+#define MG(call) do { int r2__ = (call); if (r2__) { char m__[512]; snprintf(m__, sizeof m__, "%s", ehyb_last_error()); ehyb_mg_session_free(s); return ehyb_fail(r2__, "%s", m__); } } while (0)
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(device));
+        s->sendCount = (int64_t *)malloc(sizeof(int64_t) * (size_t)nranks);
+        s->recvCount = (int64_t *)malloc(sizeof(int64_t) * (size_t)nranks);
+        if (!s->sendCount || !s->recvCount) return ehyb_fail(EHYB_ERR_NOMEM, "mg session: out of memory");
+        memcpy(s->sendCount, sendCount, sizeof(int64_t) * (size_t)nranks);
+        memcpy(s->recvCount, recvCount, sizeof(int64_t) * (size_t)nranks);
+        CU(cudaStreamCreateWithFlags(&s->commStream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->evX, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->evHalo, cudaEventDisableTiming));
+        CU(cudaMalloc(&s->sendIdx_d, sizeof(int32_t) * (size_t)(nSend ? nSend : 1)));
+        CU(cudaMalloc(&s->sendBuf_d, sizeof(double) * (size_t)(nSend ? nSend : 1)));
+        if (nSend) CU(cudaMemcpy(s->sendIdx_d, sendIdx, sizeof(int32_t) * (size_t)nSend, cudaMemcpyHostToDevice));
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof id);
+        NC(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
+        return EHYB_OK;
+    };
+    MG(body());
+#undef MG
+    *out = s;
+    return EHYB_OK;
+}
+
+/*
+ * One distributed product.  x_d holds the local x in its first n entries; the halo part
+ * x_d[n, n+nHalo) is filled here.  Order of work:
+ *   comm stream : pack (gather the x entries peers need) -> grouped ncclSend/ncclRecv
+ *   main stream : main kernel (needs only local x: every halo entry lives in the overflow
+ *                 list) || exchange ; then the overflow kernel after the halo has arrived.
+ */
+extern "C" int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d)
+{
+    if (!s || !x_d || !y_d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv: NULL argument");
+    ehyb_handle *h = s->h;
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(s->evX, h->stream)); /* x is ready / previous product done with the halo */
+    CU(cudaStreamWaitEvent(s->commStream, s->evX, 0));
+    if (s->nSend > 0) {
+        ehyb_pack_kernel<<<(unsigned)((s->nSend + 255) / 256), 256, 0, s->commStream>>>(x_d, s->sendIdx_d, s->sendBuf_d, s->nSend);
+        CU(cudaGetLastError());
+    }
+    NC(g_nccl.GroupStart());
+    int64_t so = 0, ro = 0;
+    for (int g = 0; g < s->nranks; ++g) {
+        if (s->sendCount[g] > 0) NC(g_nccl.Send(s->sendBuf_d + so, (size_t)s->sendCount[g], ncclDouble, g, s->comm, s->commStream));
+        if (s->recvCount[g] > 0) NC(g_nccl.Recv(x_d + h->n + ro, (size_t)s->recvCount[g], ncclDouble, g, s->comm, s->commStream));
+        so += s->sendCount[g];
+        ro += s->recvCount[g];
+    }
+    NC(g_nccl.GroupEnd());
+    CU(cudaEventRecord(s->evHalo, s->commStream));
+    int rc = launch_main(h, x_d, y_d, h->stream);
+    if (rc) return rc;
+    CU(cudaStreamWaitEvent(h->stream, s->evHalo, 0));
+    return launch_overflow(h, x_d, y_d, h->stream);
+}
+
+extern "C" int ehyb_mg_session_handle(ehyb_mg_session *s, ehyb_handle **h)
+{
+    if (!s || !h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_session_handle: NULL");
+    *h = s->h;
+    return EHYB_OK;
+}
+
+/* `iters` distributed products of the session's own x between two events on the main
+ * stream (the caller brackets this with its barrier and takes the max over ranks). */
+extern "C" int ehyb_mg_time_spmv(ehyb_mg_session *s, int warmup, int iters, float *ms_total)
+{
+    if (!s || !ms_total || iters <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_time_spmv: bad argument");
+    ehyb_handle *h = s->h;
+    CU(cudaSetDevice(h->device));
+    for (int i = 0; i < warmup; ++i) {
+        int rc = ehyb_mg_spmv(s, h->x, h->y);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(s->commStream));
+    CU(cudaEventRecord(h->ev0, h->stream));
+    for (int i = 0; i < iters; ++i) {
+        int rc = ehyb_mg_spmv(s, h->x, h->y);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(s->commStream));
+    CU(cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
     return EHYB_OK;
 }

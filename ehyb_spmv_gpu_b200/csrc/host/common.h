@@ -14,6 +14,9 @@ int ehyb_fail(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3
 /* Prints the last error and aborts: used by the void-returning drop-in wrappers. */
 void ehyb_die(const char *where) __attribute__((noreturn));
 
+/* reorder.c: ehyb_reorder_with_partition for a local block with halo columns [n, ncols) */
+int ehyb_reorder_core(matrixCOO *m, const uint32_t *partVec, int ncols);
+
 static inline int64_t ehyb_round_up64(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 
 #ifdef __cplusplus

@@ -50,6 +50,7 @@ struct ehyb_layout {
     /* host-only bookkeeping for the de-interleave */
     int32_t *rowEll;   /* [n] ELL entries of the row */
     int32_t *rowRemIn; /* [n] remainder entries kept in the slice */
+    int32_t *rowHalo;  /* [n] entries with a halo column (always in the overflow list), or NULL */
     int64_t *ovfPtr;   /* [n+1] overflow entries of the row */
 };
 
@@ -60,7 +61,7 @@ void ehyb_layout_free(ehyb_layout *L)
     if (!L) return;
     free(L->parts); free(L->slices); free(L->blob);
     free(L->ovfRow); free(L->ovfCol); free(L->ovfVal);
-    free(L->rowEll); free(L->rowRemIn); free(L->ovfPtr);
+    free(L->rowEll); free(L->rowRemIn); free(L->rowHalo); free(L->ovfPtr);
     free(L);
 }
 
@@ -106,6 +107,13 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     L->rowRemIn = (int32_t *)calloc((size_t)n, sizeof(int32_t));
     L->ovfPtr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
     if (!L->parts || !L->rowEll || !L->rowRemIn || !L->ovfPtr) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
+    /* distributed blocks: entries whose column is in the halo [n, ncols) never stay in a slice;
+     * they form (part of) the overflow list, which runs after the halo exchange */
+    const int haloOvf = opts->halo_in_overflow && ncols > n;
+    if (haloOvf) {
+        L->rowHalo = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+        if (!L->rowHalo) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
+    }
 
     int nSlices = 0;
     for (int p = 0; p < P; ++p) {
@@ -134,6 +142,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                 const int c = col[e];
                 if (c < 0 || c >= ncols) bad = 1;
                 ell += (inWindowRow && c >= ps && c < winEnd);
+                if (haloOvf && c >= n) L->rowHalo[r] += 1;
             }
             if (scanning && ell > longThr) { /* long rows sit at the head of the partition */
                 firstReg = r + 1;
@@ -162,7 +171,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                 int m = 0, rem[SR];
                 for (int r = r0; r < r1; ++r) {
                     if (L->rowEll[r] < 0) continue;
-                    const int64_t sp = rowPtr[r + 1] - rowPtr[r] - L->rowEll[r];
+                    const int64_t sp = rowPtr[r + 1] - rowPtr[r] - L->rowEll[r] - (haloOvf ? L->rowHalo[r] : 0);
                     rem[m++] = sp > 65535 ? 65535 : (int)sp;
                 }
                 qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
@@ -188,7 +197,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
             for (int r = r0; r < r1; ++r) {
                 if (L->rowEll[r] < 0) continue;
                 if (L->rowEll[r] > w) w = L->rowEll[r];
-                const int64_t sp = rowPtr[r + 1] - rowPtr[r] - L->rowEll[r];
+                const int64_t sp = rowPtr[r + 1] - rowPtr[r] - L->rowEll[r] - (haloOvf ? L->rowHalo[r] : 0);
                 rem[m++] = sp > 65535 ? 65535 : (int)sp;
             }
             qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
@@ -205,13 +214,14 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                     nnzOvf += len;
                     continue;
                 }
-                const int64_t sp = len - L->rowEll[r];
+                const int halo = haloOvf ? L->rowHalo[r] : 0;
+                const int64_t sp = len - L->rowEll[r] - halo;
                 const int in = sp < wr ? (int)sp : wr;
                 L->rowRemIn[r] = in;
-                L->ovfPtr[r + 1] = sp - in;
+                L->ovfPtr[r + 1] = sp - in + halo;
                 sumE += L->rowEll[r];
                 sumR += in;
-                nnzOvf += sp - in;
+                nnzOvf += sp - in + halo;
             }
             nnzEll += sumE;
             nnzRemIn += sumR;
@@ -262,7 +272,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                         ev[((int64_t)kE * 32 + lane) * 2 + h] = val[e];
                         ec[(((int64_t)(kE / 4) * 32 + lane) * 2 + h) * 4 + kE % 4] = (uint16_t)(c - ps);
                         ++kE;
-                    } else if (L->rowEll[r] >= 0 && kR < wr) {
+                    } else if (L->rowEll[r] >= 0 && kR < wr && !(haloOvf && c >= n)) {
                         rv[((int64_t)kR * 32 + lane) * 2 + h] = val[e];
                         rcol[((int64_t)kR * 32 + lane) * 2 + h] = c;
                         ++kR;

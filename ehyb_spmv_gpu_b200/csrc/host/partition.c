@@ -96,6 +96,10 @@ int ehyb_partition_graph(uint32_t n, const uint32_t *xadj, const uint32_t *adjnc
                          uint32_t nthreads, uint32_t *where)
 {
     if (!xadj || !adjncy || !where || nparts == 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_partition_graph: bad argument");
+    if (nparts == 1) { /* nothing to partition (k-way partitioners reject or mishandle k = 1) */
+        memset(where, 0, (size_t)n * sizeof(uint32_t));
+        return EHYB_OK;
+    }
     const float ub = 1.001f; /* reordering.c:273 */
     int rc = g_fn ? g_fn(n, xadj, adjncy, nparts, nthreads, ub, where, g_user)
                   : helper_partition(n, xadj, adjncy, nparts, nthreads, ub, where);

@@ -82,7 +82,15 @@ static int row_key_cmp(const void *a, const void *b)
 
 int ehyb_reorder_with_partition(matrixCOO *m, const uint32_t *partVec)
 {
-    if (!m || !partVec || m->dimension <= 0 || m->nParts <= 0)
+    return ehyb_reorder_core(m, partVec, m ? m->dimension : 0);
+}
+
+/* Rows and the first n columns are permuted; columns in [n, ncols) are the halo of a local
+ * block of a distributed matrix: they keep their index, belong to no partition and to no
+ * window.  ncols == n is the reference's case. */
+int ehyb_reorder_core(matrixCOO *m, const uint32_t *partVec, int ncols)
+{
+    if (!m || !partVec || m->dimension <= 0 || m->nParts <= 0 || ncols < m->dimension)
         return ehyb_fail(EHYB_ERR_ARG, "ehyb_reorder_with_partition: bad argument");
     const int n = m->dimension, P = m->nParts;
     const int64_t nnz = m->totalNum;
@@ -114,11 +122,11 @@ int ehyb_reorder_with_partition(matrixCOO *m, const uint32_t *partVec)
     int sorted = 1;
     for (int64_t e = 0; e < nnz; ++e) {
         const int i = m->I[e], j = m->J[e];
-        if ((unsigned)i >= (unsigned)n || (unsigned)j >= (unsigned)n) {
+        if ((unsigned)i >= (unsigned)n || (unsigned)j >= (unsigned)ncols) {
             rc = ehyb_fail(EHYB_ERR_ARG, "entry %lld outside the matrix", (long long)e);
             goto done;
         }
-        same[i] += partVec[i] == partVec[j];
+        same[i] += j < n && partVec[i] == partVec[j];
         if (e && m->I[e - 1] > i) sorted = 0;
     }
     if (sorted)
@@ -157,7 +165,7 @@ int ehyb_reorder_with_partition(matrixCOO *m, const uint32_t *partVec)
             int64_t dst = newPtr[r];
             int inWin = 0;
             for (int e = m->rowIdx[i]; e < m->rowIdx[i + 1]; ++e, ++dst) {
-                const int c = perm[m->J[e]];
+                const int c = m->J[e] < n ? perm[m->J[e]] : m->J[e];
                 mismatch |= m->I[e] != i;
                 newI[dst] = r;
                 newJ[dst] = c;
@@ -174,7 +182,7 @@ int ehyb_reorder_with_partition(matrixCOO *m, const uint32_t *partVec)
     } else {
         for (int64_t e = 0; e < nnz; ++e) {
             const int i = m->I[e];
-            const int r = perm[i], c = perm[m->J[e]];
+            const int r = perm[i], c = m->J[e] < n ? perm[m->J[e]] : m->J[e];
             const int64_t dst = newPtr[r] + m->numInRow[r]++;
             const int ps = bound[partVec[i]];
             newI[dst] = r;

@@ -18,8 +18,6 @@
 #include "common.h"
 #include "kernel.h"
 
-/* declared in cuda/ehyb_device.cu (not part of the installed header set) */
-int ehyb_session_info(const ehyb_handle *h, int *threads, int *ctasPerSM, int *grid, int64_t *smemBytes, int *l2_persist);
 
 #define EHYB_NOMINAL_HBM_GBS 8000.0 /* BASELINE.json: "~8 TB/s per-GPU roofline" */
 

@@ -125,6 +125,8 @@ typedef struct ehyb_layout_opts {
     int long_row_threshold; /* rows at a partition head with more in-window entries than this go
                                whole to the overflow list; 0 = 512 (reference threadLongVec) */
     int64_t ncols;          /* columns of the local operator (n + halo); 0 = n */
+    int halo_in_overflow;   /* entries with a halo column (>= n) always go to the overflow list,
+                               which the multi-GPU product runs after the halo exchange */
 } ehyb_layout_opts;
 
 typedef struct ehyb_slice_desc {
@@ -221,6 +223,57 @@ void ehyb_free(ehyb_handle *h);
  * `d` with dimension/nParts/... and d->b200 = h.  No arrays in the reference layout exist
  * on the device. */
 int ehyb_describe(ehyb_handle *h, matrixEHYB *d);
+
+/* ------------------------------------------------------------------------------------ */
+/* multi-GPU: one process per GPU, rows distributed in contiguous blocks, x halo exchanged    */
+/* with NCCL send/recv every product (no reference counterpart)        */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct ehyb_mg_local ehyb_mg_local;     /* host: a rank's block, halo and send lists */
+typedef struct ehyb_mg_session ehyb_mg_session; /* device: the block on its GPU + NCCL communicator */
+
+/* rowStarts[nranks+1]: global row range of every rank.  rowPtr/colGlobal/val: the rank's rows
+ * (CSR, global column indices).  Computes the halo (sorted external columns, grouped by owner). */
+int ehyb_mg_local_build(int rank, int nranks, const int64_t *rowStarts, const int64_t *rowPtr,
+                        const int64_t *colGlobal, const double *val, ehyb_mg_local **out);
+/* What this rank receives: haloGlobal[nHalo] (sorted; halo column k is local column n+k) and
+ * recvCount[nranks].  Peer g must be told the slice of haloGlobal it owns (any transport). */
+int ehyb_mg_local_halo(const ehyb_mg_local *L, int64_t *nHalo, const int64_t **haloGlobal,
+                       const int64_t **recvCount);
+/* What peers asked from this rank: sendCount[nranks] and the concatenated global rows. */
+int ehyb_mg_local_set_send(ehyb_mg_local *L, const int64_t *sendCount, const int64_t *sendGlobal);
+/* Graph of the block's own columns for the level-2 partitioner (malloc'd, ehyb_free_host). */
+int ehyb_mg_local_graph(const ehyb_mg_local *L, uint32_t **xadj, uint32_t **adjncy);
+/* Level-2 partition (partVec[n_local], NULL = contiguous blocks), permutation, tuned layout
+ * with every halo entry in the overflow list. */
+int ehyb_mg_local_finish(ehyb_mg_local *L, int nParts, int W, int ctasPerPart, const uint32_t *partVec,
+                         double er_fill);
+int ehyb_mg_local_view(const ehyb_mg_local *L, const matrixCOO **coo, const ehyb_layout **layout,
+                       int64_t *nSend, const int32_t **sendIdx, const int64_t **sendCount);
+void ehyb_mg_local_free(ehyb_mg_local *L);
+
+/* 128-byte NCCL unique id (rank 0 creates it, the caller distributes it). */
+int ehyb_mg_unique_id(void *id128);
+/* Collective: uploads the block and joins the communicator. */
+int ehyb_mg_session_create(const ehyb_mg_local *L, int rank, int nranks, int device, const void *id128,
+                           ehyb_mg_session **out);
+int ehyb_mg_session_handle(ehyb_mg_session *s, ehyb_handle **h);
+/* y_local = A_block [x_local | halo]: pack + grouped ncclSend/ncclRecv on a second stream,
+ * overlapped with the main kernel; the overflow kernel (all halo entries) follows. */
+int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d);
+int ehyb_mg_time_spmv(ehyb_mg_session *s, int warmup, int iters, float *ms_total);
+void ehyb_mg_session_free(ehyb_mg_session *s);
+/* Rows of z-planes [z0, z1) of the 27-point stencil on nx x ny x nz (full rows, global
+ * columns ascending): a rank's slab of BASELINE.json config 5, generated in place. */
+int ehyb_gen_stencil27_rows(int nx, int ny, int64_t nz, int64_t z0, int64_t z1, int64_t **rowPtr,
+                            int64_t **col, double **val);
+
+/* pinned host memory for asynchronous host-vector products */
+int ehyb_host_alloc_pinned(size_t bytes, void **out);
+int ehyb_host_free_pinned(void *p);
+/* launch geometry chosen by ehyb_upload */
+int ehyb_session_info(const ehyb_handle *h, int *threads, int *ctasPerSM, int *grid, int64_t *smemBytes,
+                      int *l2_persist);
 
 /* ------------------------------------------------------------------------------------ */
 /* synthetic matrices (BASELINE.json configs) and Matrix Market I/O    */

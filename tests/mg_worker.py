@@ -1,0 +1,83 @@
+"""Worker of tests/test_multigpu_host.py: one rank of a world_size-N gloo job on CPU.
+
+Exercises the host side of the multi-GPU layer (ehyb_mg_local_*: halo, send lists, level-2
+reorder with halo columns, layout with halo entries in the overflow list) and emulates the
+per-product exchange with gloo send/recv, checking the distributed product against the
+global CSR product."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("EHYB_MTMETIS_BIN", str(ROOT / "bin" / "ehyb_mtmetis"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from ehyb_spmv_gpu_b200 import multigpu as mg
+    from oracle import oracle as O
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    partition = sys.argv[1] if len(sys.argv) > 1 else "blocks"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    grid = (24, 20, 9) if partition == "metis" else (10, 9, 5)  # per rank
+    blk, rowStarts = mg.setup_slab(rank, world, grid, dist, partition)
+    orc = O.Oracle()
+
+    # --- structural checks -------------------------------------------------------------
+    N = int(rowStarts[-1])
+    r0, r1 = int(rowStarts[rank]), int(rowStarts[rank + 1])
+    plane = grid[0] * grid[1]
+    expect_halo = plane * ((rank > 0) + (rank < world - 1))
+    assert blk.nHalo == expect_halo, (blk.nHalo, expect_halo)
+    assert np.all((blk.haloGlobal < r0) | (blk.haloGlobal >= r1)) and np.all(np.diff(blk.haloGlobal) > 0)
+    assert blk.stats["ncols"] == blk.n + blk.nHalo
+    # every halo entry sits in the overflow list
+    J = blk.coo["J"]
+    assert blk.stats["nOverflow"] >= int(np.count_nonzero(J >= blk.n))
+    assert blk.stats["nnzEll"] + blk.stats["nnzRemInSlice"] + blk.stats["nnzOverflow"] == blk.stats["nnz"]
+
+    # --- one emulated product ---------------------------------------------------------
+    x_nat = mg.x_of_global(np.arange(r0, r1))
+    x_perm = np.empty(blk.n)
+    x_perm[blk.coo["reorderList"]] = x_nat
+    packed = x_perm[blk.sendIdx]                        # what ehyb_pack_kernel gathers
+    halo = np.empty(blk.nHalo)
+    reqs, so, ro = [], 0, 0
+    send_bufs = []
+    for g in range(world):
+        sc, rc = int(blk.sendCount[g]), int(blk.recvCount[g])
+        if sc:
+            t = torch.from_numpy(np.ascontiguousarray(packed[so:so + sc]))
+            send_bufs.append(t)
+            reqs.append(dist.isend(t, g))
+        if rc:
+            t = torch.from_numpy(halo[ro:ro + rc])
+            reqs.append(dist.irecv(t, g))
+        so += sc
+        ro += rc
+    for q in reqs:
+        q.wait()
+    assert np.array_equal(halo, mg.x_of_global(blk.haloGlobal)), "halo exchange delivered the wrong entries"
+    x_ext = np.concatenate([x_perm, halo])
+    y_perm = orc.csr_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_ext)
+    y_nat = y_perm[blk.coo["reorderList"]]
+
+    # global reference: the whole stencil, natural order
+    rp, col, val = mg.gen_stencil27_rows(grid[0], grid[1], grid[2] * world, 0, grid[2] * world)
+    xg = mg.x_of_global(np.arange(N))
+    yg = orc.csr_spmv(rp.astype(np.int32), col.astype(np.int32), val, xg)
+    ag = orc.csr_abs_spmv(rp.astype(np.int32), col.astype(np.int32), val, xg)
+    assert np.all(np.abs(y_nat - yg[r0:r1]) <= 1e-12 * ag[r0:r1]), np.abs(y_nat - yg[r0:r1]).max()
+    blk.free()
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank %d ok" % rank)
+
+
+if __name__ == "__main__":
+    main()

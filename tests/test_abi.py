@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported(lib):
             "ehyb_spmv", "ehyb_layout_build"} <= decl
     missing = sorted(s for s in decl if not hasattr(lib, s))
     assert not missing, missing
-    assert set(_lib.EXPORTS) <= decl | {"ehyb_session_info", "ehyb_host_alloc_pinned", "ehyb_host_free_pinned"}
+    assert set(_lib.EXPORTS) <= decl
 
 
 def test_struct_layouts_match_the_reference(ref):
