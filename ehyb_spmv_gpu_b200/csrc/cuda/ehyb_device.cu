@@ -22,6 +22,10 @@
 
 using namespace ehyb;
 
+/* chunk sizes of the staged kernel are compile-time (see ChunkWalker); the variants below are
+ * selectable with EHYB_CHUNK for experiments, the default is 8 ELL / 4 remainder columns
+ * (5 KB slots) */
+
 #define CU(call)                                                                                     \
     do {                                                                                             \
         cudaError_t e__ = (call);                                                                    \
@@ -94,10 +98,27 @@ extern "C" void ehyb_session_opts_default(ehyb_session_opts *o)
 typedef void (*main_kernel_t)(const MainArgs);
 static main_kernel_t pick_kernel(int kernel, int threads, int ctasPerSM)
 {
-    if (kernel == EHYB_KERNEL_STAGED) return threads <= 512 ? ehyb_staged_kernel<512> : ehyb_staged_kernel<768>;
+    if (kernel == EHYB_KERNEL_STAGED) return NULL; /* see pick_staged */
     /* 64 K registers per SM: <= 64 per thread at 1024 resident threads, <= 32 at 2048 */
     if (threads * ctasPerSM > 1024) return ehyb_main_kernel<1024, 2>;
     return ehyb_main_kernel<1024, 1>;
+}
+
+struct StagedVariant {
+    int kcE, kcR;
+    main_kernel_t k512, k768;
+};
+static const StagedVariant kStaged[] = {
+    {8, 4, ehyb_staged_kernel<512, 8, 4>, ehyb_staged_kernel<768, 8, 4>},
+    {4, 4, ehyb_staged_kernel<512, 4, 4>, ehyb_staged_kernel<768, 4, 4>},
+    {8, 8, ehyb_staged_kernel<512, 8, 8>, ehyb_staged_kernel<768, 8, 8>},
+    {16, 8, ehyb_staged_kernel<512, 16, 8>, ehyb_staged_kernel<768, 16, 8>},
+};
+static const StagedVariant *staged_variant(int kcE, int kcR)
+{
+    for (size_t i = 0; i < sizeof kStaged / sizeof kStaged[0]; ++i)
+        if (kStaged[i].kcE == kcE && kStaged[i].kcR == kcR) return &kStaged[i];
+    return &kStaged[0];
 }
 
 static int env_int(const char *name, int dflt)
@@ -147,12 +168,8 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     const size_t winBytes = (((size_t)v->W + 2) * sizeof(double) + 127) & ~(size_t)127;
     if (kernel == EHYB_KERNEL_STAGED) {
         /* warps = staging capacity: 2 slots each, as many as fit next to the window */
-        int kc = env_int("EHYB_CHUNK", 8);
-        if (kc < 4) kc = 4;
-        kc = kc / 4 * 4;
-        if (kc > 32) kc = 32;
-        int kr = env_int("EHYB_CHUNK_REM", 4);
-        kr = kr < 4 ? 4 : (kr > 32 ? 32 : kr / 4 * 4);
+        const StagedVariant *sv = staged_variant(env_int("EHYB_CHUNK", 8), env_int("EHYB_CHUNK_REM", 4));
+        const int kc = sv->kcE, kr = sv->kcR;
         h->kcEll = kc;
         h->kcRem = kr;
         const size_t fixed = (size_t)kStageHeader + winBytes;
@@ -213,10 +230,12 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(ehyb_staged_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-    CU(cudaFuncSetAttribute(ehyb_staged_kernel<768>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CU(cudaFuncSetAttribute(ehyb_staged_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-    CU(cudaFuncSetAttribute(ehyb_staged_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (size_t i = 0; i < sizeof kStaged / sizeof kStaged[0]; ++i) {
+        CU(cudaFuncSetAttribute(kStaged[i].k512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        CU(cudaFuncSetAttribute(kStaged[i].k768, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        CU(cudaFuncSetAttribute(kStaged[i].k512, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(cudaFuncSetAttribute(kStaged[i].k768, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
 
     h->use_graph = o->use_graph;
     h->pdl = env_int("EHYB_PDL", 1);
@@ -263,13 +282,22 @@ extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, 
     return EHYB_OK;
 }
 
+static main_kernel_t main_kernel_of(const ehyb_handle *h)
+{
+    if (h->kernel == EHYB_KERNEL_STAGED) {
+        const StagedVariant *sv = staged_variant(h->kcEll, h->kcRem);
+        return h->threads <= 512 ? sv->k512 : sv->k768;
+    }
+    return pick_kernel(h->kernel, h->threads, h->ctasPerSM);
+}
+
 /* the launches of one product, on `s` */
 static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
 {
     MainArgs a;
     a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
-    a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.kcEll = h->kcEll; a.kcRem = h->kcRem; a.dbg = env_int("EHYB_DEBUG_SKIP", 0);
-    main_kernel_t k = pick_kernel(h->kernel, h->threads, h->ctasPerSM);
+    a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = env_int("EHYB_DEBUG_SKIP", 0);
+    main_kernel_t k = main_kernel_of(h);
     if (h->kernel == EHYB_KERNEL_STAGED && h->pdl) {
         /* programmatic dependent launch: this grid may start while the previous kernel of the
          * stream drains; it orders itself with griddepcontrol.wait before touching x or y */
@@ -444,8 +472,8 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
         /* main kernel alone: one event pair per launch, summed */
         MainArgs a;
         a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
-        a.x = h->x; a.y = h->y; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.kcEll = h->kcEll; a.kcRem = h->kcRem; a.dbg = env_int("EHYB_DEBUG_SKIP", 0);
-        main_kernel_t k = pick_kernel(h->kernel, h->threads, h->ctasPerSM);
+        a.x = h->x; a.y = h->y; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = env_int("EHYB_DEBUG_SKIP", 0);
+        main_kernel_t k = main_kernel_of(h);
         cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)iters * 2, sizeof(cudaEvent_t));
         if (!ev) return ehyb_fail(EHYB_ERR_NOMEM, "ehyb_time_spmv: out of memory");
         for (int i = 0; i < 2 * iters; ++i) cudaEventCreate(&ev[i]);

@@ -38,8 +38,6 @@ struct MainArgs {
     int n;    /* local rows == end of the windowable x range */
     int W;    /* window length in elements */
     int kpp;  /* CTAs per partition */
-    int kcEll; /* staged kernel: ELL columns per chunk (multiple of 4) */
-    int kcRem; /* staged kernel: remainder columns per chunk (multiple of 4) */
     int dbg;   /* development only (EHYB_DEBUG_SKIP): 1 = skip remainder math, 2 = skip ELL math */
 };
 
@@ -374,6 +372,12 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t addr)
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ int2 lds_s32x2(uint32_t addr)
 {
     int2 v;
@@ -381,31 +385,46 @@ __device__ __forceinline__ int2 lds_s32x2(uint32_t addr)
     return v;
 }
 
-/* walks the chunks of the slices of one warp; all members are warp-uniform */
+/* Walks the chunks of the slices of one warp; every member is warp-uniform.  Chunk sizes are
+ * compile-time powers of two so that the per-chunk bookkeeping is a handful of shifts (ncu on
+ * the first version showed the consumers spending most of their issue slots on this
+ * bookkeeping, integer divisions included, rather than on the matrix entries). */
+template <int KCE, int KCR>
 struct ChunkWalker {
-    const uint2 *descs; /* descriptors of this CTA's partition, offset by `sub` */
+    const uint2 *descs;        /* descriptors of this warp's slices: descs[j * stride] */
     const unsigned char *blob;
-    int stride;         /* kpp * NW : distance between consecutive slices of this warp */
-    int kpp;
-    int nsl;            /* slices of the partition */
-    int t;              /* current slice (local index), >= nsl when exhausted */
-    uint2 d, dnext;     /* current / prefetched descriptor */
-    int ci;             /* chunk index inside the slice */
-    int kcE, kcR;       /* columns per ELL / remainder chunk */
+    const unsigned char *base; /* current slice */
+    int stride;                /* kpp * NW: distance between consecutive slices of this warp */
+    int left;                  /* slices still to start after the current one */
+    int t;                     /* current slice (local index in the partition) */
+    int w, wr, nE, nc, ci;     /* current slice: widths, ELL chunks, all chunks, next chunk */
+    uint2 dnext;               /* prefetched descriptor of the next slice */
+    bool live;
 
-    __device__ __forceinline__ void start(const uint2 *descs_, const unsigned char *blob_, int sub, int kpp_, int warp, int nw, int nsl_, int kcEll, int kcRem)
+    __device__ __forceinline__ void load_slice(uint2 d)
     {
-        descs = descs_; blob = blob_; kpp = kpp_; stride = kpp_ * nw; nsl = nsl_;
-        kcE = kcEll; kcR = kcRem;
-        t = sub + kpp_ * warp;
+        base = blob + static_cast<size_t>(d.x) * 256u;
+        w = static_cast<int>(d.y & 0xffffu);
+        wr = static_cast<int>(d.y >> 16);
+        nE = (w + KCE - 1) / KCE;
+        nc = max(1, nE + (wr + KCR - 1) / KCR);
         ci = 0;
-        d = make_uint2(0u, 0u); dnext = d;
-        if (t < nsl) d = __ldg(descs + (t - sub));
-        if (t + stride < nsl) dnext = __ldg(descs + (t + stride - sub));
-        sub_ = sub;
     }
-    int sub_;
-    __device__ __forceinline__ bool done() const { return t >= nsl; }
+
+    __device__ __forceinline__ void start(const uint2 *partDescs, const unsigned char *blob_, int sub, int kpp, int warp, int nw, int nsl)
+    {
+        blob = blob_;
+        stride = kpp * nw;
+        t = sub + kpp * warp;
+        live = t < nsl;
+        descs = partDescs + t;
+        left = live ? (nsl - 1 - t) / stride : 0;
+        dnext = make_uint2(0u, 0u);
+        if (live) {
+            load_slice(__ldg(descs));
+            if (left > 0) dnext = __ldg(descs + stride);
+        }
+    }
 };
 
 struct ChunkMeta {
@@ -415,59 +434,59 @@ struct ChunkMeta {
 };
 
 /* Describes the next chunk, advances the walker and (lane 0) starts its TMA copies. */
-__device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker &wk, uint32_t slotAddr, uint32_t barAddr, int lane)
+template <int KCE, int KCR>
+__device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE, KCR> &wk, uint32_t slotAddr, uint32_t barAddr, int lane)
 {
+    constexpr uint32_t kValBytes = static_cast<uint32_t>(slot_val_bytes(KCE, KCR));
     ChunkMeta m;
     m.kc = 0; m.flags = 0; m.t = wk.t;
-    if (wk.done()) return m;
-    const int w = wk.d.y & 0xffffu, wr = wk.d.y >> 16;
-    const int nE = (w + wk.kcE - 1) / wk.kcE, nR = (wr + wk.kcR - 1) / wk.kcR;
-    const uint32_t slotValBytes = static_cast<uint32_t>(slot_val_bytes(wk.kcE, wk.kcR));
-    const int nc = max(1, nE + nR);
-    const unsigned char *base = wk.blob + static_cast<size_t>(wk.d.x) * 256u;
-    const unsigned char *src0 = base, *src1 = base;
-    uint32_t b0 = 0, b1 = 0;
+    if (!wk.live) return m;
+    const unsigned char *src0, *src1;
+    uint32_t b0, b1;
     m.flags = 4;
-    if (wk.ci < nE) {
-        const int k = wk.ci * wk.kcE;
-        m.kc = min(wk.kcE, w - k);
-        src0 = base + static_cast<size_t>(k) * 512u;
+    if (wk.ci < wk.nE) {
+        const int k = wk.ci * KCE;
+        m.kc = min(KCE, wk.w - k);
+        src0 = wk.base + static_cast<uint32_t>(k) * 512u;
         b0 = static_cast<uint32_t>(m.kc) * 512u;
-        src1 = base + static_cast<size_t>(w) * 512u + static_cast<size_t>(k >> 2) * 512u;
+        src1 = wk.base + static_cast<uint32_t>(wk.w) * 512u + static_cast<uint32_t>(k >> 2) * 512u;
         b1 = static_cast<uint32_t>((m.kc + 3) >> 2) * 512u;
-    } else if (wk.ci - nE < nR) {
-        const int k = (wk.ci - nE) * wk.kcR;
-        const size_t remOff = static_cast<size_t>(w) * 512u + static_cast<size_t>((w + 3) >> 2) * 512u;
-        m.kc = min(wk.kcR, wr - k);
+    } else {
+        const int k = (wk.ci - wk.nE) * KCR;
+        const uint32_t remOff = static_cast<uint32_t>(wk.w) * 512u + static_cast<uint32_t>((wk.w + 3) >> 2) * 512u;
+        m.kc = max(0, min(KCR, wk.wr - k)); /* 0 only for a slice without any entry */
         m.flags |= 1;
-        src0 = base + remOff + static_cast<size_t>(k) * 512u;
+        src0 = wk.base + remOff + static_cast<uint32_t>(k) * 512u;
         b0 = static_cast<uint32_t>(m.kc) * 512u;
-        src1 = base + remOff + static_cast<size_t>(wr) * 512u + static_cast<size_t>(k) * 256u;
+        src1 = wk.base + remOff + static_cast<uint32_t>(wk.wr) * 512u + static_cast<uint32_t>(k) * 256u;
         b1 = static_cast<uint32_t>(m.kc) * 256u;
     }
-    if (wk.ci == nc - 1) m.flags |= 2;
     if (lane == 0 && b0) {
         mbar_expect_tx(barAddr, b0 + b1);
         tma_bulk_g2s(slotAddr, src0, b0, barAddr);
-        tma_bulk_g2s(slotAddr + slotValBytes, src1, b1, barAddr);
+        tma_bulk_g2s(slotAddr + kValBytes, src1, b1, barAddr);
     }
-    /* advance */
-    if (wk.ci == nc - 1) {
-        wk.ci = 0;
-        wk.t += wk.stride;
-        wk.d = wk.dnext;
-        wk.dnext = make_uint2(0u, 0u);
-        if (wk.t + wk.stride < wk.nsl) wk.dnext = __ldg(wk.descs + (wk.t + wk.stride - wk.sub_));
-    } else {
-        wk.ci += 1;
+    if (++wk.ci == wk.nc) { /* last chunk of the slice: move on */
+        m.flags |= 2;
+        if (wk.left > 0) {
+            wk.left -= 1;
+            wk.t += wk.stride;
+            wk.descs += wk.stride;
+            wk.load_slice(wk.dnext);
+            if (wk.left > 0) wk.dnext = __ldg(wk.descs + wk.stride);
+        } else {
+            wk.live = false;
+        }
     }
     return m;
 }
 
-template <int kMaxThreads>
+template <int kMaxThreads, int KCE, int KCR>
 __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr uint32_t kSlotBytes = static_cast<uint32_t>(slot_bytes(KCE, KCR));
+    constexpr uint32_t kSlotValBytes = static_cast<uint32_t>(slot_val_bytes(KCE, KCR));
     const int kpp = a.kpp;
     const int p = blockIdx.x / kpp;
     const int sub = blockIdx.x - p * kpp;
@@ -485,8 +504,6 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     const uint32_t xsAddr = smem_u32(win) + static_cast<uint32_t>(ps - g0) * 8u;
     const uint32_t winBar = smem_u32(smem);
     const uint32_t slotBar0 = smem_u32(smem + 16) + static_cast<uint32_t>(warp * kSlotsPerWarp) * 8u;
-    const uint32_t kSlotBytes = static_cast<uint32_t>(slot_bytes(a.kcEll, a.kcRem));
-    const uint32_t kSlotValBytes = static_cast<uint32_t>(slot_val_bytes(a.kcEll, a.kcRem));
     const uint32_t slot0 = smem_u32(smem + kStageHeader) + winBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
     const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
 
@@ -502,11 +519,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     __syncthreads();
 
     /* the matrix stream does not depend on x, y or the previous grid: start it right away */
-    ChunkWalker wk;
-    wk.start(reinterpret_cast<const uint2 *>(a.slices) + part.z + sub, a.blob, sub, kpp, warp, nw, part.w - part.z, a.kcEll, a.kcRem);
-    ChunkMeta m0 = issue_chunk(wk, slot0, slotBar0, lane);
-    ChunkMeta m1 = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane);
-    uint32_t ph0 = 0, ph1 = 0;
+    ChunkWalker<KCE, KCR> wk;
+    wk.start(reinterpret_cast<const uint2 *>(a.slices) + part.z, a.blob, sub, kpp, warp, nw, part.w - part.z);
+    ChunkMeta meta[2];
+    meta[0] = issue_chunk(wk, slot0, slotBar0, lane);
+    meta[1] = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane);
+    uint32_t phases = 0; /* bit s = parity to wait for on slot s */
 
     /* x (and later y) belong to the stream's previous work: wait for it here.  Only the
      * threads that touch x before the window barrier wait; everyone else is ordered behind
@@ -519,24 +537,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
             const char *src = reinterpret_cast<const char *>(a.x + g0);
             const uint32_t dst = smem_u32(win);
             for (uint32_t off = 0; off < bulkBytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, min(32768u, bulkBytes - off), winBar);
-        } else if (tid == nw * 32 - 1 && (len & 1)) {
-            win[len - 1] = a.x[g0 + len - 1]; /* odd tail element, by the last streaming thread */
+        } else if (tid == blockDim.x - 1 && (len & 1)) {
+            win[len - 1] = a.x[g0 + len - 1]; /* odd tail element */
         }
     } else {
         for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
     }
-
-
     if (tma_ok) {
         while (!mbar_try_wait(winBar, 0)) { }
     }
     __syncthreads(); /* odd tail element / fallback copy visible */
 
     double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
-    auto consume = [&](const ChunkMeta &m, uint32_t slot, uint32_t bar, uint32_t &ph) {
+    int s = 0; /* slot in use: chunks alternate between the two slots of the warp */
+#pragma unroll 1
+    while (meta[0].flags | meta[1].flags) {
+        const ChunkMeta m = s ? meta[1] : meta[0];
+        if (!(m.flags & 4)) break;
+        const uint32_t slot = slot0 + static_cast<uint32_t>(s) * kSlotBytes;
+        const uint32_t bar = slotBar0 + static_cast<uint32_t>(s) * 8u;
         if (m.kc) {
-            while (!mbar_try_wait(bar, ph)) { }
-            ph ^= 1u;
+            while (!mbar_try_wait(bar, (phases >> s) & 1u)) { }
+            phases ^= 1u << s;
             const uint32_t vAddr = slot + static_cast<uint32_t>(lane) * 16u;
             if (a.dbg & ((m.flags & 1) ? 1 : 2)) {
                 /* timing experiment: stream the chunk, skip its arithmetic */
@@ -550,15 +572,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
                     const double2 v1 = lds_f64x2(vAddr + (4 * g + 1) * 512u);
                     const double2 v2 = lds_f64x2(vAddr + (4 * g + 2) * 512u);
                     const double2 v3 = lds_f64x2(vAddr + (4 * g + 3) * 512u);
-                    double x00, x01, x10, x11, x20, x21, x30, x31;
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x00) : "r"(xsAddr + (c.x & 0xffffu) * 8u));
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x01) : "r"(xsAddr + (c.z & 0xffffu) * 8u));
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x10) : "r"(xsAddr + (c.x >> 16) * 8u));
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x11) : "r"(xsAddr + (c.z >> 16) * 8u));
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x20) : "r"(xsAddr + (c.y & 0xffffu) * 8u));
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x21) : "r"(xsAddr + (c.w & 0xffffu) * 8u));
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x30) : "r"(xsAddr + (c.y >> 16) * 8u));
-                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x31) : "r"(xsAddr + (c.w >> 16) * 8u));
+                    const double x00 = lds_f64(xsAddr + (c.x & 0xffffu) * 8u), x01 = lds_f64(xsAddr + (c.z & 0xffffu) * 8u);
+                    const double x10 = lds_f64(xsAddr + (c.x >> 16) * 8u), x11 = lds_f64(xsAddr + (c.z >> 16) * 8u);
+                    const double x20 = lds_f64(xsAddr + (c.y & 0xffffu) * 8u), x21 = lds_f64(xsAddr + (c.w & 0xffffu) * 8u);
+                    const double x30 = lds_f64(xsAddr + (c.y >> 16) * 8u), x31 = lds_f64(xsAddr + (c.w >> 16) * 8u);
                     acc0 = fma(v0.x, x00, acc0);
                     acc1 = fma(v0.y, x01, acc1);
                     acc0 = fma(v1.x, x10, acc0);
@@ -571,64 +588,45 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
                 const int tail = m.kc & 3;
                 if (tail) {
                     const uint4 c = lds_u32x4(cAddr + nfull * 512u);
-                    const uint32_t cols[3] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu};
+                    const uint32_t cols0[3] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu};
                     const uint32_t cols1[3] = {c.z & 0xffffu, c.z >> 16, c.w & 0xffffu};
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
                         if (i < tail) {
                             const double2 v = lds_f64x2(vAddr + (4 * nfull + i) * 512u);
-                            double xa, xb;
-                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(xa) : "r"(xsAddr + cols[i] * 8u));
-                            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(xb) : "r"(xsAddr + cols1[i] * 8u));
-                            acc0 = fma(v.x, xa, acc0);
-                            acc1 = fma(v.y, xb, acc1);
+                            acc0 = fma(v.x, lds_f64(xsAddr + cols0[i] * 8u), acc0);
+                            acc1 = fma(v.y, lds_f64(xsAddr + cols1[i] * 8u), acc1);
                         }
                     }
                 }
             } else {
                 /* remainder chunk: all column loads, then all x gathers (L2), then the FMAs in
-                 * column order - the gather latency is paid once per four columns */
+                 * column order - the gather latency is paid once per chunk */
                 const uint32_t cAddr = slot + kSlotValBytes + static_cast<uint32_t>(lane) * 8u;
-                int k = 0;
-                for (; k + 8 <= m.kc; k += 8) {
-                    int2 c[8];
-                    double xa[8], xb[8];
+                int2 c[KCR];
+                double xa[KCR], xb[KCR];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) c[i] = lds_s32x2(cAddr + (k + i) * 256u);
+                for (int i = 0; i < KCR; ++i) c[i] = i < m.kc ? lds_s32x2(cAddr + i * 256u) : make_int2(0, 0);
+                if (a.dbg & 4) { /* timing experiment: remainder x from shared memory (wrong values) */
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < KCR; ++i) {
+                        xa[i] = lds_f64(xsAddr + (static_cast<uint32_t>(c[i].x) & 8191u) * 8u);
+                        xb[i] = lds_f64(xsAddr + (static_cast<uint32_t>(c[i].y) & 8191u) * 8u);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KCR; ++i) {
                         xa[i] = ld_gather_f64(a.x + c[i].x);
                         xb[i] = ld_gather_f64(a.x + c[i].y);
                     }
+                }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const double2 v = lds_f64x2(vAddr + (k + i) * 512u);
+                for (int i = 0; i < KCR; ++i) {
+                    if (i < m.kc) {
+                        const double2 v = lds_f64x2(vAddr + i * 512u);
                         r0 = fma(v.x, xa[i], r0);
                         r1 = fma(v.y, xb[i], r1);
                     }
-                }
-                for (; k + 4 <= m.kc; k += 4) {
-                    int2 c[4];
-                    double xa[4], xb[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) c[i] = lds_s32x2(cAddr + (k + i) * 256u);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        xa[i] = ld_gather_f64(a.x + c[i].x);
-                        xb[i] = ld_gather_f64(a.x + c[i].y);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double2 v = lds_f64x2(vAddr + (k + i) * 512u);
-                        r0 = fma(v.x, xa[i], r0);
-                        r1 = fma(v.y, xb[i], r1);
-                    }
-                }
-                for (; k < m.kc; ++k) {
-                    const int2 c = lds_s32x2(cAddr + k * 256u);
-                    const double2 v = lds_f64x2(vAddr + k * 512u);
-                    r0 = fma(v.x, ld_gather_f64(a.x + c.x), r0);
-                    r1 = fma(v.y, ld_gather_f64(a.x + c.y), r1);
                 }
             }
         }
@@ -639,14 +637,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
             acc0 = acc1 = r0 = r1 = 0.0;
         }
         __syncwarp(); /* every lane is done with the slot before it is refilled */
-    };
-
-    while (m0.flags & 4) {
-        consume(m0, slot0, slotBar0, ph0);
-        m0 = issue_chunk(wk, slot0, slotBar0, lane);
-        if (!(m1.flags & 4)) break;
-        consume(m1, slot0 + kSlotBytes, slotBar0 + 8u, ph1);
-        m1 = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane);
+        const ChunkMeta mn = issue_chunk(wk, slot, bar, lane);
+        if (s) meta[1] = mn; else meta[0] = mn;
+        s ^= 1;
     }
 }
 
@@ -663,6 +656,9 @@ constexpr int kOvfPerWarp = 32 * 8;
 
 __global__ void __launch_bounds__(256) ehyb_overflow_kernel(const OverflowArgs a)
 {
+    /* let the next product's main kernel start its matrix stream while this one runs (it waits
+     * for this grid's completion before it touches x or y) */
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int64_t warpId = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t begin = warpId * kOvfPerWarp;
