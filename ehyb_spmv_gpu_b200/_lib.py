@@ -63,7 +63,7 @@ class Plan(C.Structure):
 
 class LayoutOpts(C.Structure):
     _fields_ = [("W", C.c_int), ("ctasPerPart", C.c_int), ("er_fill", C.c_double),
-                ("long_row_threshold", C.c_int), ("ncols", C.c_int64), ("halo_in_overflow", C.c_int)]
+                ("long_row_threshold", C.c_int), ("ncols", C.c_int64), ("halo_in_overflow", C.c_int), ("cache_cap", C.c_int)]
 
 
 class SliceDesc(C.Structure):
@@ -71,7 +71,8 @@ class SliceDesc(C.Structure):
 
 
 class PartDesc(C.Structure):
-    _fields_ = [("rowStart", C.c_int32), ("rowEnd", C.c_int32), ("sliceStart", C.c_int32), ("sliceEnd", C.c_int32)]
+    _fields_ = [("rowStart", C.c_int32), ("rowEnd", C.c_int32), ("sliceStart", C.c_int32), ("sliceEnd", C.c_int32),
+                ("cacheStart", C.c_int32), ("cacheCount", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class LayoutView(C.Structure):
@@ -81,6 +82,7 @@ class LayoutView(C.Structure):
         ("parts", C.POINTER(PartDesc)), ("slices", C.POINTER(SliceDesc)), ("blob", C.c_void_p),
         ("blobBytes", C.c_int64), ("nOverflow", C.c_int64),
         ("ovfRow", C.POINTER(C.c_int32)), ("ovfCol", C.POINTER(C.c_int32)), ("ovfVal", c_dbl_p),
+        ("cacheCols", C.POINTER(C.c_int32)), ("cacheTotal", C.c_int64), ("cacheMax", C.c_int32), ("reserved", C.c_int32),
         ("nnzEll", C.c_int64), ("nnzRemInSlice", C.c_int64), ("nnzOverflow", C.c_int64),
         ("padEll", C.c_int64), ("padRem", C.c_int64), ("nLongRows", C.c_int64),
         ("algBytes", C.c_int64), ("formatBytes", C.c_int64),

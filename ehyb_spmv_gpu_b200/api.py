@@ -250,10 +250,10 @@ class Layout:
     """ehyb_layout: the Blackwell-tuned layout on the host."""
 
     def __init__(self, m: CooMatrix, W: int = 0, ctasPerPart: int = 0, er_fill: float = -1.0,
-                 long_row_threshold: int = 0, ncols: int = 0, halo_in_overflow: bool = False):
+                 long_row_threshold: int = 0, ncols: int = 0, halo_in_overflow: bool = False, cache_cap: int = 0):
         self.lib = L.load()
         self.h = C.c_void_p()
-        o = LayoutOpts(W, ctasPerPart, er_fill, long_row_threshold, ncols, int(halo_in_overflow))
+        o = LayoutOpts(W, ctasPerPart, er_fill, long_row_threshold, ncols, int(halo_in_overflow), cache_cap)
         check(self.lib, self.lib.ehyb_layout_build(C.byref(m.c), C.byref(o), C.byref(self.h)), "ehyb_layout_build")
         self.v = LayoutView()
         check(self.lib, self.lib.ehyb_layout_get(self.h, C.byref(self.v)), "ehyb_layout_get")
@@ -262,16 +262,17 @@ class Layout:
         v = self.v
         return {k: getattr(v, k) for k in ("n", "ncols", "nnz", "nParts", "W", "ctasPerPart", "nSlices", "blobBytes",
                                            "nOverflow", "nnzEll", "nnzRemInSlice", "nnzOverflow", "padEll", "padRem",
-                                           "nLongRows", "algBytes", "formatBytes")}
+                                           "nLongRows", "algBytes", "formatBytes", "cacheTotal", "cacheMax")}
 
     def raw(self):
         """Copies of the device-facing arrays (for the independent numpy decoder in tests)."""
         v = self.v
-        parts = _np(v.parts, v.nParts * 4, np.int32).reshape(v.nParts, 4)
+        parts = _np(v.parts, v.nParts * 8, np.int32).reshape(v.nParts, 8)
         sl = np.frombuffer(C.string_at(C.cast(v.slices, C.c_void_p).value, v.nSlices * 8) if v.nSlices else b"",
                            dtype=np.dtype([("off256", "<u4"), ("w", "<u2"), ("wr", "<u2")]))
         blob = np.frombuffer(C.string_at(v.blob, v.blobBytes) if v.blobBytes else b"", dtype=np.uint8)
-        return dict(parts=parts, slices=sl, blob=blob, ovfRow=_np(v.ovfRow, v.nOverflow, np.int32),
+        return dict(parts=parts, slices=sl, blob=blob, cacheCols=_np(v.cacheCols, v.cacheTotal, np.int32),
+                    ovfRow=_np(v.ovfRow, v.nOverflow, np.int32),
                     ovfCol=_np(v.ovfCol, v.nOverflow, np.int32), ovfVal=_np(v.ovfVal, v.nOverflow, np.float64))
 
     def to_reference(self):

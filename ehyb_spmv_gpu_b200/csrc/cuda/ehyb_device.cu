@@ -22,9 +22,8 @@
 
 using namespace ehyb;
 
-/* chunk sizes of the staged kernel are compile-time (see ChunkWalker); the variants below are
- * selectable with EHYB_CHUNK for experiments, the default is 8 ELL / 4 remainder columns
- * (5 KB slots) */
+/* the chunk size of the staged kernel is compile-time (see ChunkWalker); the variants below are
+ * selectable with EHYB_CHUNK for experiments, the default is 4 columns (2.5 KB slots) */
 
 #define CU(call)                                                                                     \
     do {                                                                                             \
@@ -44,6 +43,8 @@ struct ehyb_handle {
     unsigned char *blob;
     int32_t *ovfRow, *ovfCol;
     double *ovfVal;
+    int32_t *cacheCols;
+    int cacheCap;        /* elements of the shared-memory remainder cache */
     double *x, *y;       /* session vectors */
     double *xb[2], *yb[2]; /* double buffers of the pipelined host path (lazy) */
     cudaEvent_t evX[2], evK[2], evY[2], ev0, ev1;
@@ -105,19 +106,18 @@ static main_kernel_t pick_kernel(int kernel, int threads, int ctasPerSM)
 }
 
 struct StagedVariant {
-    int kcE, kcR;
+    int kc;
     main_kernel_t k512, k768;
 };
 static const StagedVariant kStaged[] = {
-    {8, 4, ehyb_staged_kernel<512, 8, 4>, ehyb_staged_kernel<768, 8, 4>},
-    {4, 4, ehyb_staged_kernel<512, 4, 4>, ehyb_staged_kernel<768, 4, 4>},
-    {8, 8, ehyb_staged_kernel<512, 8, 8>, ehyb_staged_kernel<768, 8, 8>},
-    {16, 8, ehyb_staged_kernel<512, 16, 8>, ehyb_staged_kernel<768, 16, 8>},
+    {4, ehyb_staged_kernel<512, 4>, ehyb_staged_kernel<768, 4>}, /* default: 2.5 KB slots, most warps */
+    {8, ehyb_staged_kernel<512, 8>, ehyb_staged_kernel<768, 8>},
+    {16, ehyb_staged_kernel<512, 16>, ehyb_staged_kernel<768, 16>},
 };
-static const StagedVariant *staged_variant(int kcE, int kcR)
+static const StagedVariant *staged_variant(int kc)
 {
     for (size_t i = 0; i < sizeof kStaged / sizeof kStaged[0]; ++i)
-        if (kStaged[i].kcE == kcE && kStaged[i].kcR == kcR) return &kStaged[i];
+        if (kStaged[i].kc == kc) return &kStaged[i];
     return &kStaged[0];
 }
 
@@ -134,7 +134,7 @@ extern "C" void ehyb_free(ehyb_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     cudaFree(h->parts); cudaFree(h->slices); cudaFree(h->blob);
-    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal);
+    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->cacheCols);
     cudaFree(h->x); cudaFree(h->y);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->xb[i]); cudaFree(h->yb[i]);
@@ -166,14 +166,16 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     int kernel = o->kernel > 0 ? o->kernel : env_int("EHYB_KERNEL", EHYB_KERNEL_STAGED);
     int threads = o->threads > 0 ? o->threads : env_int("EHYB_THREADS", 0);
     const size_t winBytes = (((size_t)v->W + 2) * sizeof(double) + 127) & ~(size_t)127;
+    h->cacheCap = (v->cacheMax + 15) & ~15;
+    const size_t cacheBytes = ((size_t)h->cacheCap * sizeof(double) + 127) & ~(size_t)127;
     if (kernel == EHYB_KERNEL_STAGED) {
         /* warps = staging capacity: 2 slots each, as many as fit next to the window */
-        const StagedVariant *sv = staged_variant(env_int("EHYB_CHUNK", 8), env_int("EHYB_CHUNK_REM", 4));
-        const int kc = sv->kcE, kr = sv->kcR;
+        const StagedVariant *sv = staged_variant(env_int("EHYB_CHUNK", 4));
+        const int kc = sv->kc;
         h->kcEll = kc;
-        h->kcRem = kr;
-        const size_t fixed = (size_t)kStageHeader + winBytes;
-        const size_t perWarp = (size_t)kSlotsPerWarp * slot_bytes(kc, kr);
+        h->kcRem = kc;
+        const size_t fixed = (size_t)kStageHeader + winBytes + cacheBytes;
+        const size_t perWarp = (size_t)kSlotsPerWarp * slot_bytes(kc);
         int nw = fixed + perWarp <= prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - fixed) / perWarp) : 0;
         if (nw > kMaxStageWarps) nw = kMaxStageWarps;
         if (threads > 0 && threads / 32 < nw) nw = threads / 32 > 0 ? threads / 32 : 1;
@@ -187,7 +189,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     }
     if (kernel != EHYB_KERNEL_STAGED) {
         kernel = EHYB_KERNEL_DIRECT;
-        h->smemBytes = (size_t)kSmemHeader + ((size_t)v->W + 2) * sizeof(double);
+        h->smemBytes = (size_t)kSmemHeader + (size_t)((v->W + 2 + 15) & ~15) * sizeof(double) + cacheBytes;
         if (h->smemBytes > prop.sharedMemPerBlockOptin)
             return ehyb_fail(EHYB_ERR_LIMIT, "window of %d doubles needs %zu bytes of shared memory, device allows %zu", v->W,
                              h->smemBytes, (size_t)prop.sharedMemPerBlockOptin);
@@ -212,6 +214,8 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     CU(cudaMemcpyAsync(h->parts, v->parts, sizeof(ehyb_part_desc) * (size_t)h->nParts, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->slices, v->slices, sizeof(ehyb_slice_desc) * (size_t)h->nSlices, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->blob, v->blob, (size_t)h->blobBytes, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMalloc(&h->cacheCols, sizeof(int32_t) * (size_t)(v->cacheTotal ? v->cacheTotal : 1)));
+    if (v->cacheTotal) CU(cudaMemcpyAsync(h->cacheCols, v->cacheCols, sizeof(int32_t) * (size_t)v->cacheTotal, cudaMemcpyHostToDevice, h->stream));
     if (h->nOvf > 0) {
         CU(cudaMalloc(&h->ovfRow, sizeof(int32_t) * (size_t)h->nOvf));
         CU(cudaMalloc(&h->ovfCol, sizeof(int32_t) * (size_t)h->nOvf));
@@ -285,7 +289,7 @@ extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, 
 static main_kernel_t main_kernel_of(const ehyb_handle *h)
 {
     if (h->kernel == EHYB_KERNEL_STAGED) {
-        const StagedVariant *sv = staged_variant(h->kcEll, h->kcRem);
+        const StagedVariant *sv = staged_variant(h->kcEll);
         return h->threads <= 512 ? sv->k512 : sv->k768;
     }
     return pick_kernel(h->kernel, h->threads, h->ctasPerSM);
@@ -296,7 +300,7 @@ static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStrea
 {
     MainArgs a;
     a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
-    a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = env_int("EHYB_DEBUG_SKIP", 0);
+    a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = env_int("EHYB_DEBUG_SKIP", 0); a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
     main_kernel_t k = main_kernel_of(h);
     if (h->kernel == EHYB_KERNEL_STAGED && h->pdl) {
         /* programmatic dependent launch: this grid may start while the previous kernel of the
@@ -472,7 +476,7 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
         /* main kernel alone: one event pair per launch, summed */
         MainArgs a;
         a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
-        a.x = h->x; a.y = h->y; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = env_int("EHYB_DEBUG_SKIP", 0);
+        a.x = h->x; a.y = h->y; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = env_int("EHYB_DEBUG_SKIP", 0); a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
         main_kernel_t k = main_kernel_of(h);
         cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)iters * 2, sizeof(cudaEvent_t));
         if (!ev) return ehyb_fail(EHYB_ERR_NOMEM, "ehyb_time_spmv: out of memory");

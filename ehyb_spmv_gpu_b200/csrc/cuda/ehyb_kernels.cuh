@@ -39,6 +39,8 @@ struct MainArgs {
     int W;    /* window length in elements */
     int kpp;  /* CTAs per partition */
     int dbg;   /* development only (EHYB_DEBUG_SKIP): 1 = skip remainder math, 2 = skip ELL math */
+    const int32_t *cacheCols; /* per-partition remainder cache lists (permuted columns) */
+    int cacheCap;             /* shared-memory cache capacity in elements (>= longest list) */
 };
 
 struct OverflowArgs {
@@ -170,7 +172,7 @@ __device__ __forceinline__ void fma_group(const Group &g, const double *xs, doub
  * grid  = nParts * kpp CTAs; CTA b serves partition b / kpp and the slices t of that partition
  *         with t % kpp == b % kpp (static interleave - nothing global to reset between launches)
  * block = any multiple of 32 up to 1024
- * smem  = kSmemHeader + (W + 2) * 8 bytes (dynamic)
+ * smem  = kSmemHeader + align16(W + 2) * 8 + cacheCap * 8 bytes (dynamic)
  */
 template <int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(const MainArgs a)
@@ -183,11 +185,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(cons
     const int kpp = a.kpp;
     const int p = blockIdx.x / kpp;
     const int sub = blockIdx.x - p * kpp;
-    const int4 part = __ldg(reinterpret_cast<const int4 *>(a.parts) + p);
+    const int4 part = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p);
+    const int4 part2 = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p + 1); /* cacheStart, cacheCount */
     const int ps = part.x, pe = part.y;
     if (pe <= ps) return; /* empty partition (uniform over the CTA) */
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    double *cache = win + ((a.W + 2 + 15) & ~15); /* remainder cache behind the window */
 
     /* ---- stage the x window: x[g0, winEnd) -> win[0, len), g0 = ps rounded down to even so
      *      that the global source is 16-byte aligned; window element c lives at xs[c] ---- */
@@ -219,6 +223,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(cons
     } else {
         for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
     }
+    /* remainder cache: x at the partition's most referenced columns outside the window */
+    for (int i = tid; i < part2.y; i += blockDim.x) cache[i] = ld_gather_f64(a.x + __ldg(a.cacheCols + part2.x + i));
 
     /* ---- slices of this CTA: local index t = sub + kpp*q, q handed out dynamically ---- */
     const int nsl = part.w - part.z;
@@ -279,41 +285,34 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(cons
             }
         }
 
-        /* in-slice remainder: 32-bit global columns, x gathered through L2.  Four columns
-         * at a time: all index/value loads first, then all gathers, then the FMAs, so that the
-         * two dependent memory latencies are paid once per four columns. */
+        /* in-slice remainder: same geometry as the ELL part, 16-bit indices into the
+         * remainder cache, own accumulators (y = dot_ell + dot_rem, kernel.cu:162 + :76) */
         if (wr) {
             const size_t remOff = static_cast<size_t>(w) * 512u + static_cast<size_t>((w + 3) >> 2) * 512u;
             const double2 *rv = reinterpret_cast<const double2 *>(base + remOff) + lane;
-            const int2 *rc = reinterpret_cast<const int2 *>(base + remOff + static_cast<size_t>(wr) * 512u) + lane;
+            const uint4 *rc = reinterpret_cast<const uint4 *>(base + remOff + static_cast<size_t>(wr) * 512u) + lane;
             double r0 = 0.0, r1 = 0.0;
-            int k = 0;
-            for (; k + 4 <= wr; k += 4) {
-                int2 c[4];
-                double2 v[4];
-                double xa[4], xb[4];
+            const int rfull = wr >> 2;
+            for (int q2 = 0; q2 < rfull; ++q2) {
+                Group gr;
+                load_group(gr, rc, rv, q2, pol);
+                fma_group(gr, cache, r0, r1);
+            }
+            const int rtail = wr & 3;
+            if (rtail) {
+                const uint4 c = ld_stream_u32x4(rc + rfull * 32, pol);
+                const uint32_t c0[3] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu};
+                const uint32_t c1[3] = {c.z & 0xffffu, c.z >> 16, c.w & 0xffffu};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) c[i] = ld_stream_s32x2(rc + (k + i) * 32, pol);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = ld_stream_f64x2(rv + (k + i) * 32, pol);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    xa[i] = ld_gather_f64(a.x + c[i].x);
-                    xb[i] = ld_gather_f64(a.x + c[i].y);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    r0 = fma(v[i].x, xa[i], r0);
-                    r1 = fma(v[i].y, xb[i], r1);
+                for (int i = 0; i < 3; ++i) {
+                    if (i < rtail) {
+                        const double2 v = ld_stream_f64x2(rv + (4 * rfull + i) * 32, pol);
+                        r0 = fma(v.x, cache[c0[i]], r0);
+                        r1 = fma(v.y, cache[c1[i]], r1);
+                    }
                 }
             }
-            for (; k < wr; ++k) {
-                const int2 c = ld_stream_s32x2(rc + k * 32, pol);
-                const double2 v = ld_stream_f64x2(rv + k * 32, pol);
-                r0 = fma(v.x, ld_gather_f64(a.x + c.x), r0);
-                r1 = fma(v.y, ld_gather_f64(a.x + c.y), r1);
-            }
-            acc0 += r0; /* y = dot_ell + dot_rem, as kernel.cu:162 + :76 */
+            acc0 += r0;
             acc1 += r1;
         }
 
@@ -351,14 +350,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(cons
 constexpr int kStageHeader = 512;  /* window mbarrier + 2*24 slot mbarriers */
 constexpr int kSlotsPerWarp = 2;
 constexpr int kMaxStageWarps = 24;
-/* a slot holds kcEll ELL columns (kc*512 B of values + kc/4*512 B of columns = kc*640 B) or
- * kcRem remainder columns (kc*512 B of values + kc*256 B of columns); the column part starts
- * at slot_val_bytes() in both cases */
-__host__ __device__ constexpr int slot_val_bytes(int kcEll, int kcRem) { return (kcEll > kcRem ? kcEll : kcRem) * 512; }
-__host__ __device__ constexpr int slot_bytes(int kcEll, int kcRem)
-{
-    return slot_val_bytes(kcEll, kcRem) + ((kcEll / 4) * 512 > kcRem * 256 ? (kcEll / 4) * 512 : kcRem * 256);
-}
+/* a slot holds one chunk: kc columns of one slice, ELL or remainder alike (kc*512 B of values
+ * followed at slot_val_bytes() by kc/4*512 B of 16-bit indices) */
+__host__ __device__ constexpr int slot_val_bytes(int kc) { return kc * 512; }
+__host__ __device__ constexpr int slot_bytes(int kc) { return kc * 640; }
 
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
 {
@@ -389,7 +384,7 @@ __device__ __forceinline__ int2 lds_s32x2(uint32_t addr)
  * compile-time powers of two so that the per-chunk bookkeeping is a handful of shifts (ncu on
  * the first version showed the consumers spending most of their issue slots on this
  * bookkeeping, integer divisions included, rather than on the matrix entries). */
-template <int KCE, int KCR>
+template <int KCE>
 struct ChunkWalker {
     const uint2 *descs;        /* descriptors of this warp's slices: descs[j * stride] */
     const unsigned char *blob;
@@ -407,7 +402,7 @@ struct ChunkWalker {
         w = static_cast<int>(d.y & 0xffffu);
         wr = static_cast<int>(d.y >> 16);
         nE = (w + KCE - 1) / KCE;
-        nc = max(1, nE + (wr + KCR - 1) / KCR);
+        nc = max(1, nE + (wr + KCE - 1) / KCE);
         ci = 0;
     }
 
@@ -434,10 +429,10 @@ struct ChunkMeta {
 };
 
 /* Describes the next chunk, advances the walker and (lane 0) starts its TMA copies. */
-template <int KCE, int KCR>
-__device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE, KCR> &wk, uint32_t slotAddr, uint32_t barAddr, int lane)
+template <int KCE>
+__device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE> &wk, uint32_t slotAddr, uint32_t barAddr, int lane)
 {
-    constexpr uint32_t kValBytes = static_cast<uint32_t>(slot_val_bytes(KCE, KCR));
+    constexpr uint32_t kValBytes = static_cast<uint32_t>(slot_val_bytes(KCE));
     ChunkMeta m;
     m.kc = 0; m.flags = 0; m.t = wk.t;
     if (!wk.live) return m;
@@ -452,14 +447,14 @@ __device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE, KCR> &wk, uint
         src1 = wk.base + static_cast<uint32_t>(wk.w) * 512u + static_cast<uint32_t>(k >> 2) * 512u;
         b1 = static_cast<uint32_t>((m.kc + 3) >> 2) * 512u;
     } else {
-        const int k = (wk.ci - wk.nE) * KCR;
-        const uint32_t remOff = static_cast<uint32_t>(wk.w) * 512u + static_cast<uint32_t>((wk.w + 3) >> 2) * 512u;
-        m.kc = max(0, min(KCR, wk.wr - k)); /* 0 only for a slice without any entry */
+        const int k = (wk.ci - wk.nE) * KCE;
+        const unsigned char *rem = wk.base + static_cast<uint32_t>(wk.w) * 512u + static_cast<uint32_t>((wk.w + 3) >> 2) * 512u;
+        m.kc = max(0, min(KCE, wk.wr - k)); /* 0 only for a slice without any entry */
         m.flags |= 1;
-        src0 = wk.base + remOff + static_cast<uint32_t>(k) * 512u;
+        src0 = rem + static_cast<uint32_t>(k) * 512u;
         b0 = static_cast<uint32_t>(m.kc) * 512u;
-        src1 = wk.base + remOff + static_cast<uint32_t>(wk.wr) * 512u + static_cast<uint32_t>(k) * 256u;
-        b1 = static_cast<uint32_t>(m.kc) * 256u;
+        src1 = rem + static_cast<uint32_t>(wk.wr) * 512u + static_cast<uint32_t>(k >> 2) * 512u;
+        b1 = static_cast<uint32_t>((m.kc + 3) >> 2) * 512u;
     }
     if (lane == 0 && b0) {
         mbar_expect_tx(barAddr, b0 + b1);
@@ -481,16 +476,17 @@ __device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE, KCR> &wk, uint
     return m;
 }
 
-template <int kMaxThreads, int KCE, int KCR>
+template <int kMaxThreads, int KCE>
 __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr uint32_t kSlotBytes = static_cast<uint32_t>(slot_bytes(KCE, KCR));
-    constexpr uint32_t kSlotValBytes = static_cast<uint32_t>(slot_val_bytes(KCE, KCR));
+    constexpr uint32_t kSlotBytes = static_cast<uint32_t>(slot_bytes(KCE));
+    constexpr uint32_t kSlotValBytes = static_cast<uint32_t>(slot_val_bytes(KCE));
     const int kpp = a.kpp;
     const int p = blockIdx.x / kpp;
     const int sub = blockIdx.x - p * kpp;
-    const int4 part = __ldg(reinterpret_cast<const int4 *>(a.parts) + p);
+    const int4 part = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p);
+    const int4 part2 = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p + 1); /* cacheStart, cacheCount */
     const int ps = part.x, pe = part.y;
     if (pe <= ps) return;
 
@@ -504,7 +500,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     const uint32_t xsAddr = smem_u32(win) + static_cast<uint32_t>(ps - g0) * 8u;
     const uint32_t winBar = smem_u32(smem);
     const uint32_t slotBar0 = smem_u32(smem + 16) + static_cast<uint32_t>(warp * kSlotsPerWarp) * 8u;
-    const uint32_t slot0 = smem_u32(smem + kStageHeader) + winBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
+    const uint32_t cacheBytes = (static_cast<uint32_t>(a.cacheCap) * 8u + 127u) & ~127u;
+    double *cache = reinterpret_cast<double *>(smem + kStageHeader + winBytes);
+    const uint32_t cacheAddr = smem_u32(cache);
+    const uint32_t slot0 = cacheAddr + cacheBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
     const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
 
     /* Programmatic dependent launch: let the next grid in the stream start as soon as SMs free
@@ -519,17 +518,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     __syncthreads();
 
     /* the matrix stream does not depend on x, y or the previous grid: start it right away */
-    ChunkWalker<KCE, KCR> wk;
+    ChunkWalker<KCE> wk;
     wk.start(reinterpret_cast<const uint2 *>(a.slices) + part.z, a.blob, sub, kpp, warp, nw, part.w - part.z);
     ChunkMeta meta[2];
     meta[0] = issue_chunk(wk, slot0, slotBar0, lane);
     meta[1] = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane);
     uint32_t phases = 0; /* bit s = parity to wait for on slot s */
 
-    /* x (and later y) belong to the stream's previous work: wait for it here.  Only the
-     * threads that touch x before the window barrier wait; everyone else is ordered behind
-     * them through that barrier. */
-    if (!tma_ok || tid == 0 || (tid == blockDim.x - 1 && (len & 1))) asm volatile("griddepcontrol.wait;" ::: "memory");
+    /* x (and later y) belong to the stream's previous work: wait for it here (every thread
+     * reads x below: the window tail / fallback copy and the remainder cache) */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (tma_ok) {
         if (tid == 0) {
             const uint32_t bulkBytes = static_cast<uint32_t>(len & ~1) * 8u;
@@ -543,10 +541,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     } else {
         for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
     }
+    /* remainder cache: x at the partition's most referenced columns outside the window,
+     * gathered once per CTA (the list is ascending: neighbouring lanes mostly share sectors) */
+    for (int i = tid; i < part2.y; i += blockDim.x) cache[i] = ld_gather_f64(a.x + __ldg(a.cacheCols + part2.x + i));
     if (tma_ok) {
         while (!mbar_try_wait(winBar, 0)) { }
     }
-    __syncthreads(); /* odd tail element / fallback copy visible */
+    __syncthreads(); /* odd tail element / fallback copy / remainder cache visible */
 
     double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
     int s = 0; /* slot in use: chunks alternate between the two slots of the warp */
@@ -560,9 +561,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
             while (!mbar_try_wait(bar, (phases >> s) & 1u)) { }
             phases ^= 1u << s;
             const uint32_t vAddr = slot + static_cast<uint32_t>(lane) * 16u;
-            if (a.dbg & ((m.flags & 1) ? 1 : 2)) {
-                /* timing experiment: stream the chunk, skip its arithmetic */
-            } else if (!(m.flags & 1)) {
+            if (!(a.dbg & ((m.flags & 1) ? 1 : 2))) { /* (dbg: timing experiments skip the arithmetic) */
+                /* ELL chunk: indices into the x window, accumulators acc0/acc1; remainder
+                 * chunk: indices into the remainder cache, accumulators r0/r1 */
+                const bool rem = (m.flags & 1) != 0;
+                const uint32_t xb = rem ? cacheAddr : xsAddr;
+                double s0 = rem ? r0 : acc0, s1 = rem ? r1 : acc1;
                 const uint32_t cAddr = slot + kSlotValBytes + static_cast<uint32_t>(lane) * 16u;
                 const int nfull = m.kc >> 2;
 #pragma unroll 2
@@ -572,18 +576,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
                     const double2 v1 = lds_f64x2(vAddr + (4 * g + 1) * 512u);
                     const double2 v2 = lds_f64x2(vAddr + (4 * g + 2) * 512u);
                     const double2 v3 = lds_f64x2(vAddr + (4 * g + 3) * 512u);
-                    const double x00 = lds_f64(xsAddr + (c.x & 0xffffu) * 8u), x01 = lds_f64(xsAddr + (c.z & 0xffffu) * 8u);
-                    const double x10 = lds_f64(xsAddr + (c.x >> 16) * 8u), x11 = lds_f64(xsAddr + (c.z >> 16) * 8u);
-                    const double x20 = lds_f64(xsAddr + (c.y & 0xffffu) * 8u), x21 = lds_f64(xsAddr + (c.w & 0xffffu) * 8u);
-                    const double x30 = lds_f64(xsAddr + (c.y >> 16) * 8u), x31 = lds_f64(xsAddr + (c.w >> 16) * 8u);
-                    acc0 = fma(v0.x, x00, acc0);
-                    acc1 = fma(v0.y, x01, acc1);
-                    acc0 = fma(v1.x, x10, acc0);
-                    acc1 = fma(v1.y, x11, acc1);
-                    acc0 = fma(v2.x, x20, acc0);
-                    acc1 = fma(v2.y, x21, acc1);
-                    acc0 = fma(v3.x, x30, acc0);
-                    acc1 = fma(v3.y, x31, acc1);
+                    const double x00 = lds_f64(xb + (c.x & 0xffffu) * 8u), x01 = lds_f64(xb + (c.z & 0xffffu) * 8u);
+                    const double x10 = lds_f64(xb + (c.x >> 16) * 8u), x11 = lds_f64(xb + (c.z >> 16) * 8u);
+                    const double x20 = lds_f64(xb + (c.y & 0xffffu) * 8u), x21 = lds_f64(xb + (c.w & 0xffffu) * 8u);
+                    const double x30 = lds_f64(xb + (c.y >> 16) * 8u), x31 = lds_f64(xb + (c.w >> 16) * 8u);
+                    s0 = fma(v0.x, x00, s0);
+                    s1 = fma(v0.y, x01, s1);
+                    s0 = fma(v1.x, x10, s0);
+                    s1 = fma(v1.y, x11, s1);
+                    s0 = fma(v2.x, x20, s0);
+                    s1 = fma(v2.y, x21, s1);
+                    s0 = fma(v3.x, x30, s0);
+                    s1 = fma(v3.y, x31, s1);
                 }
                 const int tail = m.kc & 3;
                 if (tail) {
@@ -594,40 +598,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
                     for (int i = 0; i < 3; ++i) {
                         if (i < tail) {
                             const double2 v = lds_f64x2(vAddr + (4 * nfull + i) * 512u);
-                            acc0 = fma(v.x, lds_f64(xsAddr + cols0[i] * 8u), acc0);
-                            acc1 = fma(v.y, lds_f64(xsAddr + cols1[i] * 8u), acc1);
+                            s0 = fma(v.x, lds_f64(xb + cols0[i] * 8u), s0);
+                            s1 = fma(v.y, lds_f64(xb + cols1[i] * 8u), s1);
                         }
                     }
                 }
-            } else {
-                /* remainder chunk: all column loads, then all x gathers (L2), then the FMAs in
-                 * column order - the gather latency is paid once per chunk */
-                const uint32_t cAddr = slot + kSlotValBytes + static_cast<uint32_t>(lane) * 8u;
-                int2 c[KCR];
-                double xa[KCR], xb[KCR];
-#pragma unroll
-                for (int i = 0; i < KCR; ++i) c[i] = i < m.kc ? lds_s32x2(cAddr + i * 256u) : make_int2(0, 0);
-                if (a.dbg & 4) { /* timing experiment: remainder x from shared memory (wrong values) */
-#pragma unroll
-                    for (int i = 0; i < KCR; ++i) {
-                        xa[i] = lds_f64(xsAddr + (static_cast<uint32_t>(c[i].x) & 8191u) * 8u);
-                        xb[i] = lds_f64(xsAddr + (static_cast<uint32_t>(c[i].y) & 8191u) * 8u);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < KCR; ++i) {
-                        xa[i] = ld_gather_f64(a.x + c[i].x);
-                        xb[i] = ld_gather_f64(a.x + c[i].y);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < KCR; ++i) {
-                    if (i < m.kc) {
-                        const double2 v = lds_f64x2(vAddr + i * 512u);
-                        r0 = fma(v.x, xa[i], r0);
-                        r1 = fma(v.y, xb[i], r1);
-                    }
-                }
+                if (rem) { r0 = s0; r1 = s1; } else { acc0 = s0; acc1 = s1; }
             }
         }
         if (m.flags & 2) {

@@ -9,18 +9,23 @@
  *   slice      64 consecutive rows of one partition (never straddles a partition).  Lane l of
  *              the warp that processes the slice owns rows l and l+32 ("halves" h=0,1).
  *   slice blob [ELL values ][ELL columns ][remainder values ][remainder columns]
- *                w*512 B     ceil4(w)*128 B   wr*512 B          wr*256 B
- *              ELL values     double  [k][lane][h]         one 128-bit load per lane per k
- *              ELL columns    uint16  [k/4][lane][h][k%4]  one 128-bit load per lane per 4 k
- *              rem. values    double  [k][lane][h]
- *              rem. columns   int32   [k][lane][h]         one 64-bit load per lane per k
+ *                w*512 B     ceil4(w)*128 B   wr*512 B          ceil4(wr)*128 B
+ *              values         double  [k][lane][h]         one 128-bit access per lane per k
+ *              columns        uint16  [k/4][lane][h][k%4]  one 128-bit access per lane per 4 k
+ *              ELL columns index the x window of the partition (J - partStart); remainder
+ *              columns index the partition's REMAINDER CACHE: the ascending list of the (at
+ *              most cache_cap) most referenced columns outside the window, whose x values the
+ *              kernel gathers into shared memory once per CTA - the explicit cache extended
+ *              to the remainder, so that the steady-state loop never gathers from global
+ *              memory (the L1 tag stage serialises 32 uncoalesced sectors per warp load).
  *              Every region is a multiple of 256 bytes, so slices start 256-byte aligned and
  *              a slice is addressed by a 32-bit offset in 256-byte units.
  *   w          max in-window count over the slice's rows (the reference's rule, per 64 rows)
- *   wr         in-slice remainder width: the ceil(er_fill*64)-th largest spill count of the
- *              slice (er_fill=0: the largest).  Spill beyond wr, and whole "long" rows (more
- *              than long_row_threshold in-window entries at a partition head, the
- *              reference's longVec rule), go to the overflow list.
+ *   wr         in-slice remainder width: the ceil(er_fill*64)-th largest count of cached
+ *              remainder entries in the slice (er_fill=0: the largest).  Remainder entries
+ *              beyond wr or with an uncached column, and whole "long" rows (more than
+ *              long_row_threshold in-window entries at a partition head, the reference's
+ *              longVec rule), go to the overflow list.
  *   overflow   COO (row, col, val), sorted by row, entry order kept; reduced on the device
  *              by a segmented warp reduction and added to y.
  *
@@ -50,7 +55,8 @@ struct ehyb_layout {
     /* host-only bookkeeping for the de-interleave */
     int32_t *rowEll;   /* [n] ELL entries of the row */
     int32_t *rowRemIn; /* [n] remainder entries kept in the slice */
-    int32_t *rowHalo;  /* [n] entries with a halo column (always in the overflow list), or NULL */
+    int32_t *rowCached; /* [n] remainder entries whose column is in the partition's cache */
+    int32_t *cacheCols; /* concatenated per-partition cache lists (ascending permuted columns) */
     int64_t *ovfPtr;   /* [n+1] overflow entries of the row */
 };
 
@@ -61,7 +67,7 @@ void ehyb_layout_free(ehyb_layout *L)
     if (!L) return;
     free(L->parts); free(L->slices); free(L->blob);
     free(L->ovfRow); free(L->ovfCol); free(L->ovfVal);
-    free(L->rowEll); free(L->rowRemIn); free(L->rowHalo); free(L->ovfPtr);
+    free(L->rowEll); free(L->rowRemIn); free(L->rowCached); free(L->cacheCols); free(L->ovfPtr);
     free(L);
 }
 
@@ -76,9 +82,36 @@ int ehyb_layout_get(const ehyb_layout *L, ehyb_layout_view *view)
 static inline int64_t reg_ell_col(int w) { return (int64_t)w * 512; }
 static inline int64_t reg_rem_val(int w) { return (int64_t)w * 512 + (int64_t)((w + 3) / 4) * 512; }
 static inline int64_t reg_rem_col(int w, int wr) { return reg_rem_val(w) + (int64_t)wr * 512; }
-static inline int64_t slice_bytes(int w, int wr) { return reg_rem_col(w, wr) + (int64_t)wr * 256; }
+static inline int64_t slice_bytes(int w, int wr) { return reg_rem_col(w, wr) + (int64_t)((wr + 3) / 4) * 512; }
 
 static int cmp_int_desc(const void *a, const void *b) { return *(const int *)b - *(const int *)a; }
+
+typedef struct { int32_t col; int32_t cnt; } col_count;
+
+static int cmp_i32(const void *a, const void *b)
+{
+    const int32_t x = *(const int32_t *)a, y = *(const int32_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+static int cmp_col_count(const void *a, const void *b) /* more references first, then column */
+{
+    const col_count *x = (const col_count *)a, *y = (const col_count *)b;
+    if (x->cnt != y->cnt) return x->cnt > y->cnt ? -1 : 1;
+    return x->col < y->col ? -1 : x->col > y->col;
+}
+
+/* position of c in the ascending list, or -1 */
+static inline int cache_find(const int32_t *list, int count, int32_t c)
+{
+    int lo = 0, hi = count - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        if (list[mid] == c) return mid;
+        if (list[mid] < c) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
 
 int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col, const double *val, int nParts,
                           const int32_t *pb, const ehyb_layout_opts *opts, ehyb_layout **out)
@@ -92,7 +125,9 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     int need = (int)ceil(fill * SR);
     if (need < 1) need = 1;
     if (need > SR) need = SR;
+    int cacheCap = opts->cache_cap > 0 ? opts->cache_cap : (opts->cache_cap < 0 ? 0 : EHYB_DEFAULT_CACHE_CAP);
     if (W <= 0 || W > 65536) return ehyb_fail(EHYB_ERR_LIMIT, "window %d outside (0, 65536]: column indices are 16-bit", W);
+    if (cacheCap > 65536) cacheCap = 65536;
     if (ncols < n || ncols > INT_MAX) return ehyb_fail(EHYB_ERR_ARG, "ncols %lld must be in [n, 2^31)", (long long)ncols);
     if (pb[0] != 0 || pb[P] != n) return ehyb_fail(EHYB_ERR_ARG, "partBoundary must run from 0 to n");
     for (int p = 0; p < P; ++p)
@@ -102,18 +137,16 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     if (!L) return ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory");
     int rc = EHYB_OK;
     int64_t *sliceOff = NULL;
+    int32_t **cacheList = (int32_t **)calloc((size_t)P, sizeof(int32_t *)); /* per partition, ascending */
     L->parts = (ehyb_part_desc *)calloc((size_t)P, sizeof(ehyb_part_desc));
     L->rowEll = (int32_t *)calloc((size_t)n, sizeof(int32_t));
     L->rowRemIn = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+    L->rowCached = (int32_t *)calloc((size_t)n, sizeof(int32_t));
     L->ovfPtr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
-    if (!L->parts || !L->rowEll || !L->rowRemIn || !L->ovfPtr) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
-    /* distributed blocks: entries whose column is in the halo [n, ncols) never stay in a slice;
-     * they form (part of) the overflow list, which runs after the halo exchange */
+    if (!cacheList || !L->parts || !L->rowEll || !L->rowRemIn || !L->rowCached || !L->ovfPtr) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
+    /* distributed blocks: an entry whose column is in the halo [n, ncols) arrives with the
+     * exchange, after the main kernel has started: it is never cached, always overflow */
     const int haloOvf = opts->halo_in_overflow && ncols > n;
-    if (haloOvf) {
-        L->rowHalo = (int32_t *)calloc((size_t)n, sizeof(int32_t));
-        if (!L->rowHalo) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
-    }
 
     int nSlices = 0;
     for (int p = 0; p < P; ++p) {
@@ -127,7 +160,9 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     sliceOff = (int64_t *)calloc((size_t)nSlices + 1, sizeof(int64_t));
     if (!L->slices || !sliceOff) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
 
-    /* pass 1a: classify the entries of every row (ELL count; -1 marks a long row) */
+    /* pass 1a, per partition: classify the entries of every row (ELL count; -1 marks a long
+     * row), then choose the remainder cache: the cacheCap most referenced columns outside the
+     * window, kept in ascending order (position = 16-bit index stored in the slices) */
     int64_t nnzEll = 0, nnzRemIn = 0, nnzOvf = 0, padEll = 0, padRem = 0, nLong = 0;
     int bad = 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : nLong) reduction(| : bad)
@@ -135,6 +170,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
         const int ps = pb[p], pe = pb[p + 1];
         const int64_t winEnd = (int64_t)ps + W < n ? (int64_t)ps + W : n;
         int firstReg = ps, scanning = 1;
+        int64_t nExt = 0;
         for (int r = ps; r < pe; ++r) {
             int ell = 0;
             const int inWindowRow = r - ps < W; /* rows beyond the window are remainder as a whole (convert.c:128-134) */
@@ -142,7 +178,6 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                 const int c = col[e];
                 if (c < 0 || c >= ncols) bad = 1;
                 ell += (inWindowRow && c >= ps && c < winEnd);
-                if (haloOvf && c >= n) L->rowHalo[r] += 1;
             }
             if (scanning && ell > longThr) { /* long rows sit at the head of the partition */
                 firstReg = r + 1;
@@ -151,18 +186,87 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
             }
             scanning = 0;
             L->rowEll[r] = ell;
+            nExt += rowPtr[r + 1] - rowPtr[r] - ell;
         }
         nLong += firstReg - ps;
+        if (cacheCap == 0 || nExt == 0 || bad) continue;
+        int32_t *ext = (int32_t *)malloc((size_t)nExt * sizeof(int32_t));
+        if (!ext) { bad = 2; continue; }
+        int64_t m = 0;
+        for (int r = firstReg; r < pe; ++r) {
+            const int inWindowRow = r - ps < W;
+            for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
+                const int c = col[e];
+                if (inWindowRow && c >= ps && c < winEnd) continue;
+                if (haloOvf && c >= n) continue;
+                ext[m++] = c;
+            }
+        }
+        qsort(ext, (size_t)m, sizeof(int32_t), cmp_i32);
+        int64_t u = 0;
+        for (int64_t i = 0; i < m; ++i)
+            if (i == 0 || ext[i] != ext[i - 1]) ++u;
+        int32_t *chosen;
+        int nChosen;
+        if (u <= cacheCap) { /* everything fits: the unique list itself */
+            chosen = ext;
+            nChosen = 0;
+            for (int64_t i = 0; i < m; ++i)
+                if (i == 0 || ext[i] != ext[i - 1]) chosen[nChosen++] = ext[i];
+        } else {
+            col_count *cc = (col_count *)malloc((size_t)u * sizeof(col_count));
+            if (!cc) { free(ext); bad = 2; continue; }
+            int64_t k = -1;
+            for (int64_t i = 0; i < m; ++i) {
+                if (i == 0 || ext[i] != ext[i - 1]) { ++k; cc[k].col = ext[i]; cc[k].cnt = 0; }
+                cc[k].cnt += 1;
+            }
+            qsort(cc, (size_t)u, sizeof(col_count), cmp_col_count);
+            chosen = ext;
+            nChosen = cacheCap;
+            for (int i = 0; i < nChosen; ++i) chosen[i] = cc[i].col;
+            qsort(chosen, (size_t)nChosen, sizeof(int32_t), cmp_i32);
+            free(cc);
+        }
+        cacheList[p] = chosen;
+        L->parts[p].cacheCount = nChosen;
+        for (int r = firstReg; r < pe; ++r) {
+            const int inWindowRow = r - ps < W;
+            /* the in-slice part of a row's remainder is a PREFIX of its remainder sequence
+             * (so that in-slice + overflow, concatenated, is the original order): count the
+             * leading remainder entries whose column is cached */
+            int cached = 0;
+            for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
+                const int c = col[e];
+                if (inWindowRow && c >= ps && c < winEnd) continue;
+                if ((haloOvf && c >= n) || cache_find(chosen, nChosen, c) < 0) break;
+                cached += 1;
+            }
+            L->rowCached[r] = cached;
+        }
     }
+    if (bad) { rc = bad == 2 ? ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory") : ehyb_fail(EHYB_ERR_ARG, "layout: a column index is outside [0, ncols)"); goto fail; }
+    int64_t cacheTotal = 0;
+    int cacheMax = 0;
+    for (int p = 0; p < P; ++p) {
+        L->parts[p].cacheStart = (int32_t)cacheTotal;
+        cacheTotal += L->parts[p].cacheCount;
+        if (L->parts[p].cacheCount > cacheMax) cacheMax = L->parts[p].cacheCount;
+    }
+    if (cacheTotal > INT_MAX) { rc = ehyb_fail(EHYB_ERR_LIMIT, "remainder cache lists exceed 2^31 entries"); goto fail; }
+    L->cacheCols = (int32_t *)malloc((size_t)(cacheTotal ? cacheTotal : 1) * sizeof(int32_t));
+    if (!L->cacheCols) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
+    for (int p = 0; p < P; ++p)
+        if (L->parts[p].cacheCount) memcpy(L->cacheCols + L->parts[p].cacheStart, cacheList[p], (size_t)L->parts[p].cacheCount * sizeof(int32_t));
 
-    /* er_fill < 0: choose between "every remainder entry in its slice" (need = 1) and "a
+    /* er_fill < 0: choose between "every cached remainder entry in its slice" (need = 1) and "a
      * remainder column only while half of the lanes use it" (need = 32) by stored bytes:
-     * 12 B per in-slice slot (padding included), 16 B per overflow entry plus the cost of
+     * 10 B per in-slice slot (padding included), 16 B per overflow entry plus the cost of
      * launching the overflow kernel at all (~5 us of streaming, 30 MB). */
     if (opts->er_fill < 0) {
         double cost[2] = {0.0, 0.0};
-        int64_t ovfB = 0;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : cost[:2], ovfB)
+        int64_t ovfB = 0, ovfAlways = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : cost[:2], ovfB, ovfAlways)
         for (int p = 0; p < P; ++p) {
             const int ps = pb[p], pe = pb[p + 1];
             for (int s = L->parts[p].sliceStart; s < L->parts[p].sliceEnd; ++s) {
@@ -170,19 +274,20 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                 const int r1 = r0 + SR < pe ? r0 + SR : pe;
                 int m = 0, rem[SR];
                 for (int r = r0; r < r1; ++r) {
-                    if (L->rowEll[r] < 0) continue;
-                    const int64_t sp = rowPtr[r + 1] - rowPtr[r] - L->rowEll[r] - (haloOvf ? L->rowHalo[r] : 0);
-                    rem[m++] = sp > 65535 ? 65535 : (int)sp;
+                    const int64_t len = rowPtr[r + 1] - rowPtr[r];
+                    if (L->rowEll[r] < 0) { ovfAlways += len; continue; }
+                    rem[m++] = L->rowCached[r];
+                    ovfAlways += len - L->rowEll[r] - L->rowCached[r];
                 }
                 qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
                 const int wrA = m >= 1 ? rem[0] : 0, wrB = m >= SR / 2 ? rem[SR / 2 - 1] : 0;
-                cost[0] += 768.0 * wrA;
-                cost[1] += 768.0 * wrB;
+                cost[0] += 640.0 * wrA;
+                cost[1] += 640.0 * wrB;
                 for (int i = 0; i < m; ++i)
                     if (rem[i] > wrB) { cost[1] += 16.0 * (rem[i] - wrB); ovfB += rem[i] - wrB; }
             }
         }
-        if (ovfB > 0) cost[1] += 30e6;
+        if (ovfB > 0 && ovfAlways == 0) cost[1] += 30e6; /* the overflow launch would exist only because of this choice */
         need = cost[0] <= cost[1] ? 1 : SR / 2;
     }
 
@@ -197,8 +302,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
             for (int r = r0; r < r1; ++r) {
                 if (L->rowEll[r] < 0) continue;
                 if (L->rowEll[r] > w) w = L->rowEll[r];
-                const int64_t sp = rowPtr[r + 1] - rowPtr[r] - L->rowEll[r] - (haloOvf ? L->rowHalo[r] : 0);
-                rem[m++] = sp > 65535 ? 65535 : (int)sp;
+                rem[m++] = L->rowCached[r] > 65535 ? 65535 : L->rowCached[r];
             }
             qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
             const int wr = m >= need ? rem[need - 1] : 0;
@@ -214,14 +318,12 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                     nnzOvf += len;
                     continue;
                 }
-                const int halo = haloOvf ? L->rowHalo[r] : 0;
-                const int64_t sp = len - L->rowEll[r] - halo;
-                const int in = sp < wr ? (int)sp : wr;
+                const int in = L->rowCached[r] < wr ? L->rowCached[r] : wr;
                 L->rowRemIn[r] = in;
-                L->ovfPtr[r + 1] = sp - in + halo;
+                L->ovfPtr[r + 1] = len - L->rowEll[r] - in;
                 sumE += L->rowEll[r];
                 sumR += in;
-                nnzOvf += sp - in + halo;
+                nnzOvf += len - L->rowEll[r] - in;
             }
             nnzEll += sumE;
             nnzRemIn += sumR;
@@ -229,7 +331,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
             padRem += (int64_t)SR * wr - sumR;
         }
     }
-    if (bad) { rc = ehyb_fail(EHYB_ERR_ARG, "layout: a column index is outside [0, ncols) or a slice is wider than 65535"); goto fail; }
+    if (bad) { rc = ehyb_fail(EHYB_ERR_LIMIT, "layout: a slice is wider than 65535"); goto fail; }
 
     for (int s = 0; s < nSlices; ++s) {
         if (sliceOff[s] / 256 > (int64_t)UINT32_MAX) { rc = ehyb_fail(EHYB_ERR_LIMIT, "layout larger than 1 TiB"); goto fail; }
@@ -247,11 +349,13 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     L->ovfVal = (double *)malloc((size_t)(nOvf ? nOvf : 1) * sizeof(double));
     if (!L->blob || !L->ovfRow || !L->ovfCol || !L->ovfVal) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory (%lld bytes)", (long long)blobBytes); goto fail; }
 
-    /* pass 2: fill.  Padding stays zero (value 0.0, column 0: a valid window/global index). */
+    /* pass 2: fill.  Padding stays zero (value 0.0, index 0: a valid window / cache position). */
 #pragma omp parallel for schedule(dynamic, 1)
     for (int p = 0; p < P; ++p) {
         const int ps = pb[p], pe = pb[p + 1];
         const int64_t winEnd = (int64_t)ps + W < n ? (int64_t)ps + W : n;
+        const int32_t *cl = cacheList[p];
+        const int cn = L->parts[p].cacheCount;
         for (int s = L->parts[p].sliceStart; s < L->parts[p].sliceEnd; ++s) {
             const int r0 = ps + (s - L->parts[p].sliceStart) * SR;
             const int r1 = r0 + SR < pe ? r0 + SR : pe;
@@ -260,21 +364,23 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
             double *ev = (double *)base;
             uint16_t *ec = (uint16_t *)(base + reg_ell_col(w));
             double *rv = (double *)(base + reg_rem_val(w));
-            int32_t *rcol = (int32_t *)(base + reg_rem_col(w, wr));
+            uint16_t *rcol = (uint16_t *)(base + reg_rem_col(w, wr));
             for (int r = r0; r < r1; ++r) {
                 const int t = r - r0, lane = t % 32, h = t / 32;
-                const int isLong = L->rowEll[r] < 0 || r - ps >= W; /* no ELL entries: long row, or beyond the window */
+                const int isLong = L->rowEll[r] < 0;
+                const int inWindowRow = !isLong && r - ps < W;
                 int kE = 0, kR = 0;
                 int64_t o = L->ovfPtr[r];
                 for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
                     const int c = col[e];
-                    if (!isLong && c >= ps && c < winEnd) {
+                    int ci = -1;
+                    if (inWindowRow && c >= ps && c < winEnd) {
                         ev[((int64_t)kE * 32 + lane) * 2 + h] = val[e];
                         ec[(((int64_t)(kE / 4) * 32 + lane) * 2 + h) * 4 + kE % 4] = (uint16_t)(c - ps);
                         ++kE;
-                    } else if (L->rowEll[r] >= 0 && kR < wr && !(haloOvf && c >= n)) {
+                    } else if (!isLong && kR < L->rowRemIn[r] && (ci = cache_find(cl, cn, c)) >= 0) {
                         rv[((int64_t)kR * 32 + lane) * 2 + h] = val[e];
-                        rcol[((int64_t)kR * 32 + lane) * 2 + h] = c;
+                        rcol[(((int64_t)(kR / 4) * 32 + lane) * 2 + h) * 4 + kR % 4] = (uint16_t)ci;
                         ++kR;
                     } else {
                         L->ovfRow[o] = r;
@@ -287,26 +393,29 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
         }
     }
     for (int r = 0; r < n; ++r)
-        if (L->rowEll[r] < 0) L->rowEll[r] = 0; /* long rows own no ELL entries; flagged via rowRemIn = -1 */
-    /* (long rows are recognisable afterwards as rows whose overflow count equals their length
-     *  and exceeds the threshold; the de-interleave recomputes it from the columns) */
+        if (L->rowEll[r] < 0) L->rowEll[r] = 0; /* long rows own no ELL entries */
 
     ehyb_layout_view *v = &L->v;
     v->n = n; v->ncols = ncols; v->nnz = rowPtr[n];
     v->nParts = P; v->W = W; v->ctasPerPart = opts->ctasPerPart > 0 ? opts->ctasPerPart : 1; v->nSlices = nSlices;
     v->parts = L->parts; v->slices = L->slices; v->blob = L->blob; v->blobBytes = blobBytes;
     v->nOverflow = nOvf; v->ovfRow = L->ovfRow; v->ovfCol = L->ovfCol; v->ovfVal = L->ovfVal;
+    v->cacheCols = L->cacheCols; v->cacheTotal = cacheTotal; v->cacheMax = cacheMax;
     v->nnzEll = nnzEll; v->nnzRemInSlice = nnzRemIn; v->nnzOverflow = nnzOvf;
     v->padEll = padEll; v->padRem = padRem; v->nLongRows = nLong;
     v->algBytes = 8 * v->nnz + 2 * nnzEll + 4 * (v->nnz - nnzEll) + 8 * ncols + 8 * (int64_t)n;
     v->formatBytes = blobBytes + (int64_t)nSlices * (int64_t)sizeof(ehyb_slice_desc) +
-                     (int64_t)P * (int64_t)sizeof(ehyb_part_desc) + nOvf * 16;
+                     (int64_t)P * (int64_t)sizeof(ehyb_part_desc) + nOvf * 16 + cacheTotal * 4;
     if (nnzEll + nnzRemIn + nnzOvf != v->nnz) { rc = ehyb_fail(EHYB_ERR_ARG, "layout: entry count mismatch"); goto fail; }
+    for (int p = 0; p < P; ++p) free(cacheList[p]);
+    free(cacheList);
     free(sliceOff);
     *out = L;
     return EHYB_OK;
 
 fail:
+    if (cacheList) for (int p = 0; p < P; ++p) free(cacheList[p]);
+    free(cacheList);
     free(sliceOff);
     ehyb_layout_free(L);
     return rc;
@@ -378,7 +487,8 @@ int ehyb_layout_to_reference(const ehyb_layout *L, matrixEHYB *out, int *sizeBlo
             const double *ev = (const double *)base;
             const uint16_t *ec = (const uint16_t *)(base + reg_ell_col(w));
             const double *rv = (const double *)(base + reg_rem_val(w));
-            const int32_t *rcol = (const int32_t *)(base + reg_rem_col(w, wr));
+            const uint16_t *rcol = (const uint16_t *)(base + reg_rem_col(w, wr));
+            const int32_t *cl = v->cacheCols + v->parts[p].cacheStart;
             for (int r = r0; r < r1; ++r) {
                 const int t = r - r0, lane = t % 32, h = t / 32;
                 int dst = c.rowIdx[r];
@@ -391,7 +501,7 @@ int ehyb_layout_to_reference(const ehyb_layout *L, matrixEHYB *out, int *sizeBlo
                 }
                 for (int k = 0; k < L->rowRemIn[r]; ++k, ++dst) {
                     c.I[dst] = r;
-                    c.J[dst] = rcol[((int64_t)k * 32 + lane) * 2 + h];
+                    c.J[dst] = cl[rcol[(((int64_t)(k / 4) * 32 + lane) * 2 + h) * 4 + k % 4]];
                     c.V[dst] = rv[((int64_t)k * 32 + lane) * 2 + h];
                 }
                 for (int64_t o = L->ovfPtr[r]; o < L->ovfPtr[r + 1]; ++o, ++dst) {

@@ -6,11 +6,11 @@
  * and stores the window in a 16-bit integer, which wraps for n > ~2.6 M (SURVEY.md B-7,
  * Appendix C).  ehyb_plan() derives the parameters from the queried device instead:
  *
- *   - one CTA is resident per SM and its shared memory is split between the x window and the
- *     staging slots of the matrix stream (the staged kernel keeps ~100 KB of TMA copies in
- *     flight per SM); the window may use what is left;
- *   - the number of partitions is a multiple of the SM count, so every SM streams the same
- *     number of partitions (one wave when n/sm_count rows fit the window);
+ *   - one CTA is resident per SM and its shared memory is split between the x window, the
+ *     remainder cache and the staging slots of the matrix stream (the staged kernel keeps
+ *     ~130 KB of TMA copies in flight per SM); the window may use what is left;
+ *   - the number of partitions is a multiple of the SM count (two per SM by default), so
+ *     every SM streams the same number of partitions;
  *   - the window is sized from the partition size with 2.5 % head-room for the partitioner's
  *     imbalance (mt-metis: <= 0.1 % on stencils, 3 % on the elasticity graph)
  *     - rows beyond the window still work, they just have no ELL entries;
@@ -52,10 +52,12 @@ int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out)
 {
     if (n <= 0 || !dev || !out || dev->sm_count <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan: bad argument");
     const int sms = dev->sm_count;
-    int partsPerSM = env_int("EHYB_PARTS_PER_SM", 1);
+    int partsPerSM = env_int("EHYB_PARTS_PER_SM", 2);
     int ctasPerSM = env_int("EHYB_CTAS_PER_SM", 1);
     int threads = env_int("EHYB_THREADS", 0);
-    const long staging = (long)env_int("EHYB_STAGING_KB", 96) * 1024; /* matrix stream in flight per CTA */
+    /* shared memory next to the window: staging slots of the matrix stream (what is in flight
+     * per SM) and the remainder cache (EHYB_DEFAULT_CACHE_CAP doubles) */
+    const long staging = (long)env_int("EHYB_STAGING_KB", 128) * 1024 + (long)EHYB_DEFAULT_CACHE_CAP * 8;
     if (partsPerSM < 1) partsPerSM = 1;
     if (ctasPerSM < 1) ctasPerSM = 1;
     if (threads < 0 || threads > 1024 || threads % 32) threads = 0; /* 0: the session decides */

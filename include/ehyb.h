@@ -127,17 +127,24 @@ typedef struct ehyb_layout_opts {
     int64_t ncols;          /* columns of the local operator (n + halo); 0 = n */
     int halo_in_overflow;   /* entries with a halo column (>= n) always go to the overflow list,
                                which the multi-GPU product runs after the halo exchange */
+    int cache_cap;          /* remainder cache: at most this many columns outside the window are
+                               cached per partition (0 = 4096, < 0 = none: all remainder entries
+                               go to the overflow list) */
 } ehyb_layout_opts;
+
+#define EHYB_DEFAULT_CACHE_CAP 4096
 
 typedef struct ehyb_slice_desc {
     uint32_t off256; /* byte offset of the slice in the blob / 256 */
     uint16_t w;      /* ELL width (columns), 16-bit window-local indices */
-    uint16_t wr;     /* in-slice remainder width, 32-bit column indices */
+    uint16_t wr;     /* in-slice remainder width, 16-bit indices into the partition's cache */
 } ehyb_slice_desc;
 
 typedef struct ehyb_part_desc {
-    int32_t rowStart, rowEnd;     /* permuted rows of the partition */
-    int32_t sliceStart, sliceEnd; /* its slices */
+    int32_t rowStart, rowEnd;       /* permuted rows of the partition */
+    int32_t sliceStart, sliceEnd;   /* its slices */
+    int32_t cacheStart, cacheCount; /* its remainder cache list in cacheCols */
+    int32_t reserved[2];
 } ehyb_part_desc;
 
 /* Read-only view of a built layout (pointers stay owned by the layout). */
@@ -151,6 +158,10 @@ typedef struct ehyb_layout_view {
     int64_t nOverflow;             /* overflow (COO, row-sorted, entry order kept) */
     const int32_t *ovfRow, *ovfCol;
     const double *ovfVal;
+    const int32_t *cacheCols;      /* [cacheTotal] per-partition remainder cache lists */
+    int64_t cacheTotal;
+    int32_t cacheMax;              /* longest list: sizes the shared-memory cache */
+    int32_t reserved;
     /* statistics */
     int64_t nnzEll, nnzRemInSlice, nnzOverflow, padEll, padRem, nLongRows;
     int64_t algBytes;              /* 8 nnz + 2 nnzEll + 4 (nnz - nnzEll) + 16 n, BASELINE.md sec. 3 */

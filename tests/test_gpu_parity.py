@@ -28,9 +28,9 @@ CASES = [
 KERNELS = [1, 2]  # EHYB_KERNEL_DIRECT, EHYB_KERNEL_STAGED
 
 
-def _run(orc, kind, dims, P, W, kpp, threads, fill, x, kernel=0):
+def _run(orc, kind, dims, P, W, kpp, threads, fill, x, kernel=0, cache_cap=0):
     m = util.product_pipeline(kind, dims, P, W, kpp, x=x)
-    lay = api.Layout(m, er_fill=fill)
+    lay = api.Layout(m, er_fill=fill, cache_cap=cache_cap)
     s = api.Session(lay, threads=threads, kernel=kernel)
     xr = m.vector_reorder(x)
     y_perm = s.spmv_host(xr)
@@ -45,7 +45,8 @@ def _run(orc, kind, dims, P, W, kpp, threads, fill, x, kernel=0):
 def test_bit_exact_vs_fma_emulation(orc, kind, dims, P, W, kpp, threads, kernel):
     n = util.lower_entries(kind, dims)[0]
     x = orc.x_reference(n)
-    m, y_perm, y, st = _run(orc, kind, dims, P, W, kpp, threads, 0.0, x, kernel)
+    # a remainder cache large enough for every column outside the window: nothing overflows
+    m, y_perm, y, st = _run(orc, kind, dims, P, W, kpp, threads, 0.0, x, kernel, cache_cap=16384)
     assert st["nOverflow"] == 0
     mo, ro = util.oracle_pipeline(orc, kind, dims, P, W, x=x)
     eo = orc.convert(ro)
@@ -56,11 +57,11 @@ def test_bit_exact_vs_fma_emulation(orc, kind, dims, P, W, kpp, threads, kernel)
 
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("kind,dims,P,W,kpp,threads", CASES)
-@pytest.mark.parametrize("fill", [0.0, 0.5, 1.0])
-def test_accuracy_gate(orc, kind, dims, P, W, kpp, threads, fill, kernel):
+@pytest.mark.parametrize("fill,cache_cap", [(0.0, 0), (0.5, 0), (1.0, 0), (-1.0, 64), (0.0, -1)])
+def test_accuracy_gate(orc, kind, dims, P, W, kpp, threads, fill, cache_cap, kernel):
     n = util.lower_entries(kind, dims)[0]
     x = util.x_random(n, seed=P)
-    m, y_perm, y, st = _run(orc, kind, dims, P, W, kpp, threads, fill, x, kernel)
+    m, y_perm, y, st = _run(orc, kind, dims, P, W, kpp, threads, fill, x, kernel, cache_cap)
     mo = orc.read_sym(*util.lower_entries(kind, dims), x)
     y_ref = orc.csr_spmv(mo["rowIdx"], mo["J"], mo["V"], x)
     absAx = orc.csr_abs_spmv(mo["rowIdx"], mo["J"], mo["V"], x)

@@ -76,7 +76,9 @@ def test_independent_numpy_decode_of_the_tuned_layout(orc):
     blob = raw["blob"]
     rows = {}
     for p in range(P):
-        rs, re_, s0, s1 = raw["parts"][p]
+        rs, re_, s0, s1, cs, cc = raw["parts"][p][:6]
+        cache = raw["cacheCols"][cs:cs + cc]
+        assert np.all(np.diff(cache) > 0) and not np.any((cache >= rs) & (cache < min(rs + W, a["n"])))
         for s in range(s0, s1):
             off = int(raw["slices"]["off256"][s]) * 256
             w, wr = int(raw["slices"]["w"][s]), int(raw["slices"]["wr"][s])
@@ -85,14 +87,15 @@ def test_independent_numpy_decode_of_the_tuned_layout(orc):
             ec = blob[off + w * 512:off + w * 512 + w4 * 512].view(np.uint16).reshape(w4, 32, 2, 4)
             ro = off + w * 512 + w4 * 512
             rv = blob[ro:ro + wr * 512].view(np.float64).reshape(wr, 32, 2)
-            rc = blob[ro + wr * 512:ro + wr * 768].view(np.int32).reshape(wr, 32, 2)
+            wr4 = (wr + 3) // 4
+            rc = blob[ro + wr * 512:ro + wr * 512 + wr4 * 512].view(np.uint16).reshape(wr4, 32, 2, 4)
             for t in range(64):
                 r = rs + (s - s0) * 64 + t
                 if r >= re_:
                     continue
                 lane, h = t % 32, t // 32
                 ent = [(rs + int(ec[k // 4, lane, h, k % 4]), float(ev[k, lane, h])) for k in range(w)]
-                ent += [(int(rc[k, lane, h]), float(rv[k, lane, h])) for k in range(wr)]
+                ent += [(int(cache[rc[k // 4, lane, h, k % 4]]) if cc else 0, float(rv[k, lane, h])) for k in range(wr)]
                 rows[r] = ent
     for r_, c_, v_ in zip(raw["ovfRow"], raw["ovfCol"], raw["ovfVal"]):
         rows[int(r_)].append((int(c_), float(v_)))
