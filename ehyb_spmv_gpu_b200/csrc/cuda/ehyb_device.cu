@@ -45,6 +45,7 @@ struct ehyb_handle {
     double *ovfVal;
     int32_t *cacheCols;
     int cacheCap;        /* elements of the shared-memory remainder cache */
+    int smCount;
     double *x, *y;       /* session vectors */
     double *xb[2], *yb[2]; /* double buffers of the pipelined host path (lazy) */
     cudaEvent_t evX[2], evK[2], evY[2], ev0, ev1;
@@ -160,6 +161,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
         return ehyb_fail(EHYB_ERR_CUDA, "device %d (%s, sm_%d%d) has no TMA bulk copies; this engine targets sm_100a", o->device,
                          prop.name, prop.major, prop.minor);
     h->device = o->device;
+    h->smCount = prop.multiProcessorCount;
     h->n = v->n; h->ncols = v->ncols + (o->halo_cols > 0 && v->ncols == v->n ? o->halo_cols : 0);
     h->nnz = v->nnz; h->nOvf = v->nOverflow; h->blobBytes = v->blobBytes; h->algBytes = v->algBytes;
     h->nParts = v->nParts; h->W = v->W; h->kpp = v->ctasPerPart > 0 ? v->ctasPerPart : 1; h->nSlices = v->nSlices;
@@ -323,15 +325,41 @@ static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStrea
     return EHYB_OK;
 }
 
+/* entries per warp of the overflow kernel: 32 while that still fits ~4 waves of the machine,
+ * more (up to kOvfPerWarp) for long lists */
+static int overflow_per_warp(const ehyb_handle *h)
+{
+    const int64_t warpsPerWave = (int64_t)h->smCount * 64;
+    int64_t per = (h->nOvf + 4 * warpsPerWave - 1) / (4 * warpsPerWave);
+    per = (per + 31) / 32 * 32;
+    if (per < 32) per = 32;
+    if (per > kOvfPerWarp) per = kOvfPerWarp;
+    return (int)per;
+}
+
 static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
 {
     if (h->nOvf <= 0) return EHYB_OK;
     OverflowArgs o;
     o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = x_d; o.y = y_d;
-    const int64_t warps = (h->nOvf + kOvfPerWarp - 1) / kOvfPerWarp;
+    o.perWarp = overflow_per_warp(h);
+    const int64_t warps = (h->nOvf + o.perWarp - 1) / o.perWarp;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
-    ehyb_overflow_kernel<<<blocks, 256, 0, s>>>(o);
-    CU(cudaGetLastError());
+    if (h->pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks);
+        cfg.blockDim = dim3(256);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, ehyb_overflow_kernel, o));
+    } else {
+        ehyb_overflow_kernel<<<blocks, 256, 0, s>>>(o);
+        CU(cudaGetLastError());
+    }
     return EHYB_OK;
 }
 
@@ -485,12 +513,7 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
             cudaEventRecord(ev[2 * i], h->stream);
             k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, h->stream>>>(a);
             cudaEventRecord(ev[2 * i + 1], h->stream);
-            if (h->nOvf > 0) {
-                OverflowArgs o;
-                o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = h->x; o.y = h->y;
-                const int64_t warps = (h->nOvf + kOvfPerWarp - 1) / kOvfPerWarp;
-                ehyb_overflow_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, h->stream>>>(o);
-            }
+            launch_overflow(h, h->x, h->y, h->stream);
         }
         cudaError_t e = cudaStreamSynchronize(h->stream);
         float sum = 0.f;

@@ -49,6 +49,7 @@ struct OverflowArgs {
     int64_t count;
     const double *x;
     double *y;
+    int perWarp; /* consecutive entries per warp, a multiple of 32 */
 };
 
 /* ---------------------------------------------------------------- PTX helpers ----- */
@@ -622,7 +623,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
 /* ---------------------------------------------------------------- overflow kernel -- */
 
 /*
- * COO remainder (row-sorted): each warp takes kOvfPerWarp consecutive entries, 32 at a time;
+ * COO remainder (row-sorted): each warp takes perWarp consecutive entries, 32 at a time (the
+ * launcher keeps perWarp at 32 for short lists, so that the kernel is one wave of independent
+ * warps instead of a few warps walking dependent loads; long lists use up to kOvfPerWarp);
  * products are reduced per row with a warp-shuffle segmented scan and the last lane of every
  * row segment adds its sum to y (the row's ELL + in-slice part is already there: this kernel
  * runs after ehyb_main_kernel on the same stream).  A segment that continues into the next
@@ -633,13 +636,15 @@ constexpr int kOvfPerWarp = 32 * 8;
 __global__ void __launch_bounds__(256) ehyb_overflow_kernel(const OverflowArgs a)
 {
     /* let the next product's main kernel start its matrix stream while this one runs (it waits
-     * for this grid's completion before it touches x or y) */
+     * for this grid's completion before it touches x or y); this grid itself is launched
+     * programmatically behind the main kernel and waits here for its y */
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int64_t warpId = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const int64_t begin = warpId * kOvfPerWarp;
+    const int64_t begin = warpId * a.perWarp;
     if (begin >= a.count) return;
-    const int64_t end = min(begin + kOvfPerWarp, a.count);
+    const int64_t end = min(begin + a.perWarp, a.count);
     int carryRow = -1;
     double carry = 0.0;
     for (int64_t base = begin; base < end; base += 32) {

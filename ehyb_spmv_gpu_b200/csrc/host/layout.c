@@ -125,7 +125,13 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     int need = (int)ceil(fill * SR);
     if (need < 1) need = 1;
     if (need > SR) need = SR;
-    int cacheCap = opts->cache_cap > 0 ? opts->cache_cap : (opts->cache_cap < 0 ? 0 : EHYB_DEFAULT_CACHE_CAP);
+    /* remainder cache capacity: explicit, none (< 0), or what a B200 CTA can hold next to the
+     * window while leaving ~100 KB of staging slots for the matrix stream */
+    int cacheCap = opts->cache_cap > 0 ? opts->cache_cap : 0;
+    if (opts->cache_cap == 0) {
+        const long room = 232448L - 512 - ((long)W + 2) * 8 - 100 * 1024;
+        cacheCap = room > (long)EHYB_DEFAULT_CACHE_CAP * 8 ? (int)(room / 8) : EHYB_DEFAULT_CACHE_CAP;
+    }
     if (W <= 0 || W > 65536) return ehyb_fail(EHYB_ERR_LIMIT, "window %d outside (0, 65536]: column indices are 16-bit", W);
     if (cacheCap > 65536) cacheCap = 65536;
     if (ncols < n || ncols > INT_MAX) return ehyb_fail(EHYB_ERR_ARG, "ncols %lld must be in [n, 2^31)", (long long)ncols);

@@ -128,8 +128,9 @@ typedef struct ehyb_layout_opts {
     int halo_in_overflow;   /* entries with a halo column (>= n) always go to the overflow list,
                                which the multi-GPU product runs after the halo exchange */
     int cache_cap;          /* remainder cache: at most this many columns outside the window are
-                               cached per partition (0 = 4096, < 0 = none: all remainder entries
-                               go to the overflow list) */
+                               cached per partition (0 = what fits a B200 CTA next to the window
+                               and ~100 KB of staging, at least 4096; < 0 = none: all remainder
+                               entries go to the overflow list) */
 } ehyb_layout_opts;
 
 #define EHYB_DEFAULT_CACHE_CAP 4096
