@@ -82,7 +82,7 @@ class LayoutView(C.Structure):
         ("parts", C.POINTER(PartDesc)), ("slices", C.POINTER(SliceDesc)), ("blob", C.c_void_p),
         ("blobBytes", C.c_int64), ("nOverflow", C.c_int64),
         ("ovfRow", C.POINTER(C.c_int32)), ("ovfCol", C.POINTER(C.c_int32)), ("ovfVal", c_dbl_p),
-        ("cacheCols", C.POINTER(C.c_int32)), ("cacheTotal", C.c_int64), ("cacheMax", C.c_int32), ("reserved", C.c_int32),
+        ("cacheCols", C.POINTER(C.c_int32)), ("cacheTotal", C.c_int64), ("cacheMax", C.c_int32), ("haloInOverflow", C.c_int32),
         ("nnzEll", C.c_int64), ("nnzRemInSlice", C.c_int64), ("nnzOverflow", C.c_int64),
         ("padEll", C.c_int64), ("padRem", C.c_int64), ("nLongRows", C.c_int64),
         ("algBytes", C.c_int64), ("formatBytes", C.c_int64),
@@ -111,12 +111,14 @@ EXPORTS = [
     "ehyb_layout_build", "ehyb_layout_build_csr", "ehyb_layout_get", "ehyb_layout_to_reference",
     "ehyb_layout_free", "ehyb_session_opts_default", "ehyb_upload", "ehyb_spmv", "ehyb_spmv_host",
     "ehyb_spmv_host_batch", "ehyb_session_vectors", "ehyb_set_x", "ehyb_get_y", "ehyb_time_spmv",
-    "ehyb_launches_per_spmv", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
+    "ehyb_launches_per_spmv", "ehyb_trace_read", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
     "ehyb_gen_lower", "ehyb_coo_from_lower", "ehyb_coo_from_general", "ehyb_gen_rmat", "ehyb_x_reference",
     "ehyb_read_mtx", "ehyb_write_mtx", "ehyb_coo_free",
     "ehyb_mg_local_build", "ehyb_mg_local_halo", "ehyb_mg_local_set_send", "ehyb_mg_local_graph",
     "ehyb_mg_local_finish", "ehyb_mg_local_view", "ehyb_mg_local_free", "ehyb_mg_unique_id",
     "ehyb_mg_session_create", "ehyb_mg_session_handle", "ehyb_mg_spmv", "ehyb_mg_time_spmv",
+    "ehyb_mg_p2p_supported", "ehyb_mg_session_create_p2p", "ehyb_mg_p2p_export", "ehyb_mg_p2p_connect",
+    "ehyb_mg_status", "ehyb_mg_launches_per_spmv",
     "ehyb_mg_session_free", "ehyb_gen_stencil27_rows", "ehyb_host_alloc_pinned", "ehyb_host_free_pinned",
     "ehyb_session_info",
 ]

@@ -44,12 +44,14 @@ struct ehyb_handle {
     int32_t *ovfRow, *ovfCol;
     double *ovfVal;
     int32_t *cacheCols;
+    int32_t *order;      /* CTA slot -> partition (NULL: identity), see ehyb_staged_kernel */
+    unsigned long long *trace; /* development: per-CTA timeline of the last product (EHYB_TRACE=1) */
     int cacheCap;        /* elements of the shared-memory remainder cache */
     int smCount;
     double *x, *y;       /* session vectors */
     double *xb[2], *yb[2]; /* double buffers of the pipelined host path (lazy) */
     cudaEvent_t evX[2], evK[2], evY[2], ev0, ev1;
-    int use_graph, l2_persist, pdl;
+    int use_graph, l2_persist, pdl, dbgSkip, haloInOverflow;
     cudaGraphExec_t gexec;
     const double *gx;
     double *gy;
@@ -135,7 +137,7 @@ extern "C" void ehyb_free(ehyb_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     cudaFree(h->parts); cudaFree(h->slices); cudaFree(h->blob);
-    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->cacheCols);
+    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->trace);
     cudaFree(h->x); cudaFree(h->y);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->xb[i]); cudaFree(h->yb[i]);
@@ -245,6 +247,12 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
 
     h->use_graph = o->use_graph;
     h->pdl = env_int("EHYB_PDL", 1);
+    h->dbgSkip = env_int("EHYB_DEBUG_SKIP", 0); /* development: timing experiments without the arithmetic */
+    h->haloInOverflow = v->haloInOverflow;
+    if (env_int("EHYB_TRACE", 0)) {
+        CU(cudaMalloc(&h->trace, sizeof(unsigned long long) * 8 * (size_t)h->nParts * (size_t)h->kpp));
+        CU(cudaMemset(h->trace, 0, sizeof(unsigned long long) * 8 * (size_t)h->nParts * (size_t)h->kpp));
+    }
     h->l2_persist = 0;
     if (o->l2_persist_x && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
         size_t want = sizeof(double) * (size_t)h->ncols;
@@ -297,12 +305,30 @@ static main_kernel_t main_kernel_of(const ehyb_handle *h)
     return pick_kernel(h->kernel, h->threads, h->ctasPerSM);
 }
 
-/* the launches of one product, on `s` */
-static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
+/* no exchange inside the kernels: halo columns (if any) are the tail of x */
+static PeerArgs no_peer(const ehyb_handle *h, const double *x_d)
+{
+    PeerArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.xh = x_d + h->n;
+    return pa;
+}
+
+static MainArgs main_args(const ehyb_handle *h, const double *x_d, double *y_d, const PeerArgs *pa)
 {
     MainArgs a;
     a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
-    a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = env_int("EHYB_DEBUG_SKIP", 0); a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
+    a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = h->dbgSkip; a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
+    a.order = h->order;
+    a.trace = h->trace;
+    a.peer = pa ? *pa : no_peer(h, x_d);
+    return a;
+}
+
+/* the launches of one product, on `s` */
+static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s, const PeerArgs *pa)
+{
+    const MainArgs a = main_args(h, x_d, y_d, pa);
     main_kernel_t k = main_kernel_of(h);
     if (h->kernel == EHYB_KERNEL_STAGED && h->pdl) {
         /* programmatic dependent launch: this grid may start while the previous kernel of the
@@ -337,12 +363,14 @@ static int overflow_per_warp(const ehyb_handle *h)
     return (int)per;
 }
 
-static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
+static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s, const PeerArgs *pa)
 {
     if (h->nOvf <= 0) return EHYB_OK;
     OverflowArgs o;
     o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = x_d; o.y = y_d;
     o.perWarp = overflow_per_warp(h);
+    o.n = (int)h->n;
+    o.peer = pa ? *pa : no_peer(h, x_d);
     const int64_t warps = (h->nOvf + o.perWarp - 1) / o.perWarp;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
     if (h->pdl) {
@@ -365,8 +393,8 @@ static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaS
 
 static int launch_product(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s)
 {
-    int rc = launch_main(h, x_d, y_d, s);
-    return rc ? rc : launch_overflow(h, x_d, y_d, s);
+    int rc = launch_main(h, x_d, y_d, s, NULL);
+    return rc ? rc : launch_overflow(h, x_d, y_d, s, NULL);
 }
 
 extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h) { return h ? (h->nOvf > 0 ? 2 : 1) : 0; }
@@ -502,9 +530,7 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
     CU(cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
     if (kernel_ms) {
         /* main kernel alone: one event pair per launch, summed */
-        MainArgs a;
-        a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
-        a.x = h->x; a.y = h->y; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = env_int("EHYB_DEBUG_SKIP", 0); a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
+        const MainArgs a = main_args(h, h->x, h->y, NULL);
         main_kernel_t k = main_kernel_of(h);
         cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)iters * 2, sizeof(cudaEvent_t));
         if (!ev) return ehyb_fail(EHYB_ERR_NOMEM, "ehyb_time_spmv: out of memory");
@@ -513,7 +539,7 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
             cudaEventRecord(ev[2 * i], h->stream);
             k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, h->stream>>>(a);
             cudaEventRecord(ev[2 * i + 1], h->stream);
-            launch_overflow(h, h->x, h->y, h->stream);
+            launch_overflow(h, h->x, h->y, h->stream, NULL);
         }
         cudaError_t e = cudaStreamSynchronize(h->stream);
         float sum = 0.f;
@@ -527,6 +553,21 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
         if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "kernel timing: %s", cudaGetErrorString(e));
         *kernel_ms = sum;
     }
+    return EHYB_OK;
+}
+
+/* Development aid (EHYB_TRACE=1 when the session was created): the staged kernel's per-CTA
+ * timeline of the last product - 8 words per CTA: globaltimer ns at CTA start, after the wait
+ * for the previous grid, after the halo push, when window + cache are staged, when the last
+ * warp finished; then SM id, partition, unused.  out holds 8 * *ctas words. */
+extern "C" int ehyb_trace_read(ehyb_handle *h, unsigned long long *out, int *ctas)
+{
+    if (!h || !ctas) return ehyb_fail(EHYB_ERR_ARG, "ehyb_trace_read: NULL");
+    *ctas = h->trace ? h->nParts * h->kpp : 0;
+    if (!h->trace || !out) return EHYB_OK;
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(out, h->trace, sizeof(unsigned long long) * 8 * (size_t)*ctas, cudaMemcpyDeviceToHost));
     return EHYB_OK;
 }
 
@@ -626,14 +667,26 @@ static int nccl_load(void)
 
 struct ehyb_mg_session {
     ehyb_handle *h;
-    int rank, nranks;
+    int rank, nranks, exchange;
+    int64_t nSend, nHalo;
+    int32_t *sendIdx_d;
+    int64_t *sendCount, *recvCount; /* host copies */
+    /* NCCL exchange */
     ncclComm_t comm;
     cudaStream_t commStream;
     cudaEvent_t evX, evHalo;
-    int64_t nSend, nHalo;
-    int32_t *sendIdx_d;
     double *sendBuf_d;
-    int64_t *sendCount, *recvCount; /* host copies */
+    /* peer-memory exchange */
+    unsigned char *shared;       /* one allocation mapped by the neighbours: [halo 0 | halo 1 | flags] */
+    size_t sharedBytes, haloStride; /* haloStride: bytes between the two halo buffers */
+    void **peerBase;             /* [nranks] the neighbours' `shared`, mapped here (NULL: not a neighbour) */
+    double **pushDst_d[2];       /* device: [nSend] destination of every send-list entry, per parity */
+    uint32_t **peerFlag_d;       /* device: [nPeers] flags[my rank][0] on every neighbour */
+    int32_t *peerPushCtas_d;     /* device: [nranks] pushing CTAs of every rank (flag words to poll) */
+    uint32_t *status_d;
+    uint32_t epoch, recvMask, nbrMask;
+    int nPeers, pushCtas, connected;
+    unsigned long long timeoutNs;
 };
 
 __global__ void ehyb_pack_kernel(const double *__restrict__ x, const int32_t *__restrict__ idx, double *__restrict__ out, int64_t n)
@@ -656,9 +709,19 @@ extern "C" int ehyb_mg_unique_id(void *id128)
 extern "C" void ehyb_mg_session_free(ehyb_mg_session *s)
 {
     if (!s) return;
-    if (s->h) cudaSetDevice(s->h->device);
+    if (s->h) {
+        cudaSetDevice(s->h->device);
+        if (s->h->stream) cudaStreamSynchronize(s->h->stream);
+    }
     if (s->commStream) cudaStreamSynchronize(s->commStream);
     if (s->comm && g_nccl.dl) g_nccl.CommDestroy(s->comm);
+    if (s->peerBase) {
+        for (int g = 0; g < s->nranks; ++g)
+            if (s->peerBase[g]) cudaIpcCloseMemHandle(s->peerBase[g]);
+        free(s->peerBase);
+    }
+    cudaFree(s->shared); cudaFree(s->pushDst_d[0]); cudaFree(s->pushDst_d[1]); cudaFree(s->peerFlag_d);
+    cudaFree(s->peerPushCtas_d); cudaFree(s->status_d);
     cudaFree(s->sendIdx_d); cudaFree(s->sendBuf_d);
     if (s->evX) cudaEventDestroy(s->evX);
     if (s->evHalo) cudaEventDestroy(s->evHalo);
@@ -668,6 +731,62 @@ extern "C" void ehyb_mg_session_free(ehyb_mg_session *s)
     free(s);
 }
 
+/* what both exchanges share: the uploaded block, the send list and the per-peer counts */
+static int mg_session_base(const ehyb_mg_local *L, int rank, int nranks, int device, int exchange, ehyb_mg_session **out)
+{
+    const ehyb_layout *layout = NULL;
+    const int32_t *sendIdx = NULL;
+    const int64_t *sendCount = NULL, *recvCount = NULL;
+    int64_t nSend = 0, nHalo = 0;
+    int rc = ehyb_mg_local_view(L, NULL, &layout, &nSend, &sendIdx, &sendCount);
+    if (rc) return rc;
+    ehyb_mg_local_halo(L, &nHalo, NULL, &recvCount);
+    ehyb_layout_view v;
+    rc = ehyb_layout_get(layout, &v);
+    if (rc) return rc;
+    if (nHalo > 0 && (v.haloInOverflow != 0) != (exchange == EHYB_MG_NCCL))
+        return ehyb_fail(EHYB_ERR_ARG, "the block was finished for the %s exchange", v.haloInOverflow ? "NCCL" : "peer-memory");
+    ehyb_mg_session *s = (ehyb_mg_session *)calloc(1, sizeof *s);
+    if (!s) return ehyb_fail(EHYB_ERR_NOMEM, "mg session: out of memory");
+    s->rank = rank; s->nranks = nranks; s->nSend = nSend; s->nHalo = nHalo; s->exchange = exchange;
+    ehyb_session_opts o;
+    ehyb_session_opts_default(&o);
+    o.device = device;
+    rc = ehyb_upload(layout, &o, &s->h);
+    if (rc) { free(s); return rc; }
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(device));
+        s->sendCount = (int64_t *)malloc(sizeof(int64_t) * (size_t)nranks);
+        s->recvCount = (int64_t *)malloc(sizeof(int64_t) * (size_t)nranks);
+        if (!s->sendCount || !s->recvCount) return ehyb_fail(EHYB_ERR_NOMEM, "mg session: out of memory");
+        memcpy(s->sendCount, sendCount, sizeof(int64_t) * (size_t)nranks);
+        memcpy(s->recvCount, recvCount, sizeof(int64_t) * (size_t)nranks);
+        CU(cudaMalloc(&s->sendIdx_d, sizeof(int32_t) * (size_t)(nSend ? nSend : 1)));
+        if (nSend) CU(cudaMemcpy(s->sendIdx_d, sendIdx, sizeof(int32_t) * (size_t)nSend, cudaMemcpyHostToDevice));
+        return EHYB_OK;
+    };
+    rc = body();
+    if (rc) {
+        char msg[512];
+        snprintf(msg, sizeof msg, "%s", ehyb_last_error());
+        ehyb_mg_session_free(s);
+        return ehyb_fail(rc, "%s", msg);
+    }
+    *out = s;
+    return EHYB_OK;
+}
+
+#define MG_TRY(s, call)                                            \
+    do {                                                           \
+        int r2__ = (call);                                         \
+        if (r2__) {                                                \
+            char m__[512];                                         \
+            snprintf(m__, sizeof m__, "%s", ehyb_last_error());    \
+            ehyb_mg_session_free(s);                               \
+            return ehyb_fail(r2__, "%s", m__);                     \
+        }                                                          \
+    } while (0)
+
 /* Collective over all ranks (ncclCommInitRank).  id128 comes from rank 0's ehyb_mg_unique_id,
  * distributed by the caller. */
 extern "C" int ehyb_mg_session_create(const ehyb_mg_local *L, int rank, int nranks, int device, const void *id128,
@@ -676,58 +795,266 @@ extern "C" int ehyb_mg_session_create(const ehyb_mg_local *L, int rank, int nran
     if (!L || !id128 || !out || nranks <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_session_create: bad argument");
     int rc = nccl_load();
     if (rc) return rc;
-    const ehyb_layout *layout = NULL;
-    const int32_t *sendIdx = NULL;
-    const int64_t *sendCount = NULL, *recvCount = NULL;
-    int64_t nSend = 0, nHalo = 0;
-    rc = ehyb_mg_local_view(L, NULL, &layout, &nSend, &sendIdx, &sendCount);
+    ehyb_mg_session *s = NULL;
+    rc = mg_session_base(L, rank, nranks, device, EHYB_MG_NCCL, &s);
     if (rc) return rc;
-    ehyb_mg_local_halo(L, &nHalo, NULL, &recvCount);
-    ehyb_mg_session *s = (ehyb_mg_session *)calloc(1, sizeof *s);
-    if (!s) return ehyb_fail(EHYB_ERR_NOMEM, "mg session: out of memory");
-    s->rank = rank; s->nranks = nranks; s->nSend = nSend; s->nHalo = nHalo;
-    ehyb_session_opts o;
-    ehyb_session_opts_default(&o);
-    o.device = device;
-    rc = ehyb_upload(layout, &o, &s->h);
-    if (rc) { free(s); return rc; }
-#define MG(call) do { int r2__ = (call); if (r2__) { char m__[512]; snprintf(m__, sizeof m__, "%s", ehyb_last_error()); ehyb_mg_session_free(s); return ehyb_fail(r2__, "%s", m__); } } while (0)
     auto body = [&]() -> int {
-        CU(cudaSetDevice(device));
-        s->sendCount = (int64_t *)malloc(sizeof(int64_t) * (size_t)nranks);
-        s->recvCount = (int64_t *)malloc(sizeof(int64_t) * (size_t)nranks);
-        if (!s->sendCount || !s->recvCount) return ehyb_fail(EHYB_ERR_NOMEM, "mg session: out of memory");
-        memcpy(s->sendCount, sendCount, sizeof(int64_t) * (size_t)nranks);
-        memcpy(s->recvCount, recvCount, sizeof(int64_t) * (size_t)nranks);
         CU(cudaStreamCreateWithFlags(&s->commStream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&s->evX, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&s->evHalo, cudaEventDisableTiming));
-        CU(cudaMalloc(&s->sendIdx_d, sizeof(int32_t) * (size_t)(nSend ? nSend : 1)));
-        CU(cudaMalloc(&s->sendBuf_d, sizeof(double) * (size_t)(nSend ? nSend : 1)));
-        if (nSend) CU(cudaMemcpy(s->sendIdx_d, sendIdx, sizeof(int32_t) * (size_t)nSend, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&s->sendBuf_d, sizeof(double) * (size_t)(s->nSend ? s->nSend : 1)));
         ncclUniqueId id;
         memcpy(&id, id128, sizeof id);
         NC(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
         return EHYB_OK;
     };
-    MG(body());
-#undef MG
+    MG_TRY(s, body());
     *out = s;
     return EHYB_OK;
 }
 
+/* ---- peer-memory exchange ---------------------------------------------------------------- */
+
+/* what a rank tells the others about its shared allocation (EHYB_MG_P2P_BLOB_BYTES) */
+struct P2PBlob {
+    cudaIpcMemHandle_t handle; /* 64 bytes */
+    int64_t haloStride;        /* bytes from halo buffer 0 to halo buffer 1 */
+    int64_t flagsOffset;       /* bytes from the base to flags[0] */
+    int64_t nHalo;
+    int32_t device, rank;
+    int32_t pushCtas;          /* CTAs of this rank that push = flag words it writes on a neighbour */
+    int32_t pad32;
+    int64_t pad[3];
+};
+static_assert(sizeof(P2PBlob) == EHYB_MG_P2P_BLOB_BYTES, "P2PBlob must match EHYB_MG_P2P_BLOB_BYTES");
+
+extern "C" int ehyb_mg_p2p_supported(int device, int nranks, int *supported)
+{
+    if (!supported || nranks <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_supported: bad argument");
+    *supported = 0;
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (nranks > 32 || nranks > count) return EHYB_OK; /* one rank per GPU of this node, flags masks are 32-bit */
+    for (int g = 0; g < nranks; ++g) {
+        if (g == device) continue;
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, device, g));
+        if (!can) return EHYB_OK;
+    }
+    *supported = 1;
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int nranks, int device, ehyb_mg_session **out)
+{
+    if (!L || !out || nranks <= 0 || nranks > 32) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_session_create_p2p: bad argument (at most 32 ranks)");
+    ehyb_mg_session *s = NULL;
+    int rc = mg_session_base(L, rank, nranks, device, EHYB_MG_P2P, &s);
+    if (rc) return rc;
+    const ehyb_layout *layout = NULL;
+    ehyb_mg_local_view(L, NULL, &layout, NULL, NULL, NULL);
+    auto body = [&]() -> int {
+        /* [halo 0 | halo 1 | flags], every part 256-byte aligned; the allocation is rounded up to
+         * 2 MiB so that the IPC handle covers this block and nothing else */
+        s->haloStride = (((size_t)s->nHalo + 1) * sizeof(double) + 255) & ~(size_t)255;
+        const size_t flagsBytes = (size_t)nranks * kMaxPushCtas * sizeof(uint32_t);
+        s->sharedBytes = (2 * s->haloStride + flagsBytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        CU(cudaMalloc(&s->shared, s->sharedBytes));
+        CU(cudaMemset(s->shared, 0, s->sharedBytes));
+        CU(cudaMalloc(&s->status_d, 256));
+        CU(cudaMemset(s->status_d, 0, 256));
+        CU(cudaDeviceSynchronize());
+        s->timeoutNs = (unsigned long long)env_int("EHYB_P2P_TIMEOUT_MS", 10000) * 1000000ull;
+        /* the CTAs that push (their last warp does) are resident in the first wave of the main
+         * kernel: at most one per SM and no more than the grid; >= 64 entries each */
+        ehyb_handle *h = s->h;
+        int64_t ctas = (s->nSend + 63) / 64;
+        if (env_int("EHYB_P2P_PUSH_CTAS", 0) > 0) ctas = env_int("EHYB_P2P_PUSH_CTAS", 0);
+        const int64_t grid = (int64_t)h->nParts * h->kpp;
+        if (ctas > grid) ctas = grid;
+        if (ctas > h->smCount) ctas = h->smCount;
+        if (ctas > kMaxPushCtas) ctas = kMaxPushCtas;
+        if (ctas < 1) ctas = 1;
+        s->pushCtas = (int)ctas;
+        /* dispatch order (CTAs start in blockIdx order): a first wave of partitions WITHOUT halo
+         * columns in their remainder cache (the lists are ascending, so the last entry tells) -
+         * these CTAs push, nobody in them waits; then the partitions that need halo values, by
+         * which time the neighbours' push of this product has arrived; then the rest, so that
+         * the tail of the kernel is made of ordinary partitions */
+        ehyb_layout_view v;
+        int rc2 = ehyb_layout_get(layout, &v);
+        if (rc2) return rc2;
+        int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)h->nParts);
+        unsigned char *cls = (unsigned char *)malloc((size_t)h->nParts);
+        if (!order || !cls) { free(order); free(cls); return ehyb_fail(EHYB_ERR_NOMEM, "mg session: out of memory"); }
+        const int reorder = env_int("EHYB_P2P_ORDER", 1);
+        int firstWave = h->smCount * h->ctasPerSM / h->kpp;
+        if (firstWave < 1) firstWave = 1;
+        int nPlain = 0;
+        for (int p = 0; p < h->nParts; ++p) {
+            const int cnt = v.parts[p].cacheCount;
+            const int halo = reorder && cnt > 0 && v.cacheCols[v.parts[p].cacheStart + cnt - 1] >= v.n;
+            cls[p] = halo ? 1 : (nPlain++ < firstWave ? 0 : 2);
+        }
+        int k = 0;
+        for (int pass = 0; pass < 3; ++pass)
+            for (int p = 0; p < h->nParts; ++p)
+                if (cls[p] == pass) order[k++] = p;
+        free(cls);
+        cudaError_t e = cudaMalloc(&h->order, sizeof(int32_t) * (size_t)h->nParts);
+        if (e == cudaSuccess) e = cudaMemcpy(h->order, order, sizeof(int32_t) * (size_t)h->nParts, cudaMemcpyHostToDevice);
+        free(order);
+        if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "dispatch order: %s", cudaGetErrorString(e));
+        return EHYB_OK;
+    };
+    MG_TRY(s, body());
+    *out = s;
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_mg_p2p_export(ehyb_mg_session *s, void *blob)
+{
+    if (!s || !blob || s->exchange != EHYB_MG_P2P) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_export: not a peer-memory session");
+    CU(cudaSetDevice(s->h->device));
+    P2PBlob b;
+    memset(&b, 0, sizeof b);
+    CU(cudaIpcGetMemHandle(&b.handle, s->shared));
+    b.haloStride = (int64_t)s->haloStride;
+    b.flagsOffset = (int64_t)(2 * s->haloStride);
+    b.nHalo = s->nHalo;
+    b.device = s->h->device;
+    b.rank = s->rank;
+    b.pushCtas = s->pushCtas;
+    memcpy(blob, &b, sizeof b);
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_mg_p2p_connect(ehyb_mg_session *s, const void *blobs, const int64_t *recvOffsetOnPeer)
+{
+    if (!s || !blobs || !recvOffsetOnPeer || s->exchange != EHYB_MG_P2P) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_connect: bad argument");
+    if (s->connected) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_connect: already connected");
+    CU(cudaSetDevice(s->h->device));
+    const int R = s->nranks;
+    const P2PBlob *B = (const P2PBlob *)blobs;
+    s->peerBase = (void **)calloc((size_t)R, sizeof(void *));
+    double **dst[2] = {(double **)malloc(sizeof(double *) * (size_t)(s->nSend ? s->nSend : 1)),
+                       (double **)malloc(sizeof(double *) * (size_t)(s->nSend ? s->nSend : 1))};
+    uint32_t **flagAddr = (uint32_t **)malloc(sizeof(uint32_t *) * (size_t)R);
+    int rc = EHYB_OK;
+    auto body = [&]() -> int {
+        if (!s->peerBase || !dst[0] || !dst[1] || !flagAddr) return ehyb_fail(EHYB_ERR_NOMEM, "p2p connect: out of memory");
+        s->recvMask = s->nbrMask = 0;
+        s->nPeers = 0;
+        int64_t so = 0;
+        for (int g = 0; g < R; ++g) {
+            const int64_t sc = s->sendCount[g], rcv = s->recvCount[g];
+            if (g == s->rank || (sc == 0 && rcv == 0)) { so += sc; continue; }
+            if (B[g].rank != g) return ehyb_fail(EHYB_ERR_ARG, "p2p connect: blob %d describes rank %d", g, B[g].rank);
+            if (recvOffsetOnPeer[g] < 0 || recvOffsetOnPeer[g] + sc > B[g].nHalo)
+                return ehyb_fail(EHYB_ERR_ARG, "p2p connect: %lld entries at %lld do not fit rank %d's halo of %lld", (long long)sc,
+                                 (long long)recvOffsetOnPeer[g], g, (long long)B[g].nHalo);
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, s->h->device, B[g].device));
+            if (!can) return ehyb_fail(EHYB_ERR_PEER, "GPU %d cannot access GPU %d (rank %d) directly", s->h->device, B[g].device, g);
+            cudaError_t e = cudaIpcOpenMemHandle(&s->peerBase[g], B[g].handle, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                s->peerBase[g] = NULL;
+                return ehyb_fail(EHYB_ERR_PEER, "cudaIpcOpenMemHandle(rank %d): %s", g, cudaGetErrorString(e));
+            }
+            unsigned char *base = (unsigned char *)s->peerBase[g];
+            for (int64_t k = 0; k < sc; ++k)
+                for (int b = 0; b < 2; ++b)
+                    dst[b][so + k] = (double *)(base + (size_t)b * (size_t)B[g].haloStride) + recvOffsetOnPeer[g] + k;
+            flagAddr[s->nPeers++] = (uint32_t *)(base + B[g].flagsOffset) + (size_t)s->rank * kMaxPushCtas;
+            s->nbrMask |= 1u << g;
+            if (rcv > 0) s->recvMask |= 1u << g;
+            so += sc;
+        }
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaMalloc(&s->pushDst_d[b], sizeof(double *) * (size_t)(s->nSend ? s->nSend : 1)));
+            if (s->nSend) CU(cudaMemcpy(s->pushDst_d[b], dst[b], sizeof(double *) * (size_t)s->nSend, cudaMemcpyHostToDevice));
+        }
+        int32_t *ppc = (int32_t *)malloc(sizeof(int32_t) * (size_t)R);
+        if (!ppc) return ehyb_fail(EHYB_ERR_NOMEM, "p2p connect: out of memory");
+        for (int g = 0; g < R; ++g) {
+            ppc[g] = B[g].pushCtas;
+            if (ppc[g] < 1 || ppc[g] > kMaxPushCtas) { free(ppc); return ehyb_fail(EHYB_ERR_ARG, "p2p connect: rank %d announces %d pushing CTAs", g, B[g].pushCtas); }
+        }
+        cudaError_t e2 = cudaMalloc(&s->peerPushCtas_d, sizeof(int32_t) * (size_t)R);
+        if (e2 == cudaSuccess) e2 = cudaMemcpy(s->peerPushCtas_d, ppc, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice);
+        free(ppc);
+        if (e2 != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "p2p connect: %s", cudaGetErrorString(e2));
+        CU(cudaMalloc(&s->peerFlag_d, sizeof(uint32_t *) * (size_t)(s->nPeers ? s->nPeers : 1)));
+        if (s->nPeers) CU(cudaMemcpy(s->peerFlag_d, flagAddr, sizeof(uint32_t *) * (size_t)s->nPeers, cudaMemcpyHostToDevice));
+        CU(cudaDeviceSynchronize());
+        return EHYB_OK;
+    };
+    rc = body();
+    free(dst[0]); free(dst[1]); free(flagAddr);
+    if (rc) return rc;
+    s->connected = 1;
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_mg_status(ehyb_mg_session *s, int *timed_out)
+{
+    if (!s || !timed_out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_status: NULL");
+    *timed_out = 0;
+    if (s->exchange != EHYB_MG_P2P) return EHYB_OK;
+    CU(cudaSetDevice(s->h->device));
+    uint32_t st = 0;
+    CU(cudaStreamSynchronize(s->h->stream));
+    CU(cudaMemcpy(&st, s->status_d, sizeof st, cudaMemcpyDeviceToHost));
+    *timed_out = st != 0;
+    return EHYB_OK;
+}
+
+extern "C" int ehyb_mg_launches_per_spmv(const ehyb_mg_session *s)
+{
+    if (!s) return 0;
+    const int ovf = s->h->nOvf > 0 ? 1 : 0;
+    return s->exchange == EHYB_MG_P2P ? 1 + ovf : 2 + ovf + (s->nSend > 0 ? 1 : 0); /* NCCL: pack + send/recv kernel + main */
+}
+
+/* peer-memory product: ONE launch (plus the overflow kernel if the block has overflow
+ * entries); the exchange happens inside the main kernel (ehyb_kernels.cuh, PeerArgs) */
+static int mg_spmv_p2p(ehyb_mg_session *s, double *x_d, double *y_d)
+{
+    ehyb_handle *h = s->h;
+    if (!s->connected) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv: call ehyb_mg_p2p_connect first");
+    s->epoch += 1;
+    const int b = (int)(s->epoch & 1u);
+    PeerArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.xh = (const double *)(s->shared + (size_t)b * s->haloStride);
+    pa.flags = (const uint32_t *)(s->shared + 2 * s->haloStride);
+    pa.status = s->status_d;
+    pa.pushIdx = s->sendIdx_d;
+    pa.pushDst = s->pushDst_d[b];
+    pa.peerFlag = s->peerFlag_d;
+    pa.peerPushCtas = s->peerPushCtas_d;
+    pa.timeoutNs = s->timeoutNs;
+    pa.epoch = s->epoch;
+    pa.recvMask = s->recvMask;
+    pa.nbrMask = s->nbrMask;
+    pa.nranks = s->nranks;
+    pa.pushCount = (int)s->nSend;
+    pa.pushCtas = s->pushCtas;
+    pa.nPeers = s->nPeers;
+    int rc = launch_main(h, x_d, y_d, h->stream, &pa);
+    return rc ? rc : launch_overflow(h, x_d, y_d, h->stream, &pa);
+}
+
 /*
- * One distributed product.  x_d holds the local x in its first n entries; the halo part
- * x_d[n, n+nHalo) is filled here.  Order of work:
+ * One distributed product, NCCL exchange.  x_d holds the local x in its first n entries; the
+ * halo part x_d[n, n+nHalo) is filled here.  Order of work:
  *   comm stream : pack (gather the x entries peers need) -> grouped ncclSend/ncclRecv
  *   main stream : main kernel (needs only local x: every halo entry lives in the overflow
  *                 list) || exchange ; then the overflow kernel after the halo has arrived.
  */
-extern "C" int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d)
+static int mg_spmv_nccl(ehyb_mg_session *s, double *x_d, double *y_d)
 {
-    if (!s || !x_d || !y_d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv: NULL argument");
     ehyb_handle *h = s->h;
-    CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(s->evX, h->stream)); /* x is ready / previous product done with the halo */
     CU(cudaStreamWaitEvent(s->commStream, s->evX, 0));
     if (s->nSend > 0) {
@@ -744,10 +1071,17 @@ extern "C" int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d)
     }
     NC(g_nccl.GroupEnd());
     CU(cudaEventRecord(s->evHalo, s->commStream));
-    int rc = launch_main(h, x_d, y_d, h->stream);
+    int rc = launch_main(h, x_d, y_d, h->stream, NULL);
     if (rc) return rc;
     CU(cudaStreamWaitEvent(h->stream, s->evHalo, 0));
-    return launch_overflow(h, x_d, y_d, h->stream);
+    return launch_overflow(h, x_d, y_d, h->stream, NULL);
+}
+
+extern "C" int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d)
+{
+    if (!s || !x_d || !y_d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv: NULL argument");
+    CU(cudaSetDevice(s->h->device));
+    return s->exchange == EHYB_MG_P2P ? mg_spmv_p2p(s, x_d, y_d) : mg_spmv_nccl(s, x_d, y_d);
 }
 
 extern "C" int ehyb_mg_session_handle(ehyb_mg_session *s, ehyb_handle **h)
@@ -769,7 +1103,7 @@ extern "C" int ehyb_mg_time_spmv(ehyb_mg_session *s, int warmup, int iters, floa
         if (rc) return rc;
     }
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaStreamSynchronize(s->commStream));
+    if (s->commStream) CU(cudaStreamSynchronize(s->commStream));
     CU(cudaEventRecord(h->ev0, h->stream));
     for (int i = 0; i < iters; ++i) {
         int rc = ehyb_mg_spmv(s, h->x, h->y);
@@ -777,7 +1111,11 @@ extern "C" int ehyb_mg_time_spmv(ehyb_mg_session *s, int warmup, int iters, floa
     }
     CU(cudaEventRecord(h->ev1, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaStreamSynchronize(s->commStream));
+    if (s->commStream) CU(cudaStreamSynchronize(s->commStream));
     CU(cudaEventElapsedTime(ms_total, h->ev0, h->ev1));
+    int timedOut = 0;
+    int rc = ehyb_mg_status(s, &timedOut);
+    if (rc) return rc;
+    if (timedOut) return ehyb_fail(EHYB_ERR_PEER, "a neighbour did not deliver its halo within the time limit");
     return EHYB_OK;
 }

@@ -29,6 +29,38 @@ namespace ehyb {
 
 constexpr int kSmemHeader = 128; /* mbarrier + slice counter in front of the window */
 
+/*
+ * Peer-memory halo exchange (multi-GPU, one process per GPU).  Every GPU
+ * owns two halo buffers (products alternate between them) and kMaxPushCtas flag words per rank,
+ * all in one allocation that the neighbours map through CUDA IPC.  Product number `epoch`:
+ *   push   the last warp of the first pushCtas CTAs of the main kernel stores its share of the
+ *          x entries the neighbours need straight into the neighbours' halo buffers over NVLink
+ *          and then writes `epoch` into ITS OWN flag word on every neighbour with one
+ *          st.release.sys - the only MEMBAR of the protocol (a MEMBAR.SYS drains behind the
+ *          ~120 KB the SM has in flight: several microseconds under load, measured);
+ *   pull   a warp that needs a halo column (remainder-cache fill, overflow kernel) polls, with
+ *          ld.acquire.sys (LDG.STRONG.SYS + CCTL.IVALL, no MEMBAR), until all the flag words of
+ *          the neighbours it receives from show `epoch`.
+ * flags == NULL: no exchange inside the kernels (single GPU, or the NCCL exchange, where the
+ * halo entries live in the overflow list and x_halo = x + n).
+ */
+constexpr int kMaxPushCtas = 256; /* flag words per rank (>= SMs of the device) */
+
+struct PeerArgs {
+    const double *xh;            /* halo values of this product: column c >= n is xh[c - n] */
+    const uint32_t *flags;       /* [nranks][kMaxPushCtas] last epoch delivered by CTA j of rank g */
+    uint32_t *status;            /* set to 1 when a wait ran into the time limit */
+    const int32_t *pushIdx;      /* [pushCount] local x entries the neighbours need */
+    double *const *pushDst;      /* [pushCount] their addresses in the neighbours' halo buffers */
+    uint32_t *const *peerFlag;   /* [nPeers] address of flags[my rank][0] on every neighbour */
+    const int32_t *peerPushCtas; /* [nranks] how many CTAs of rank g push (= flag words to poll) */
+    unsigned long long timeoutNs;
+    uint32_t epoch;
+    uint32_t recvMask;           /* ranks this GPU receives halo values from */
+    uint32_t nbrMask;            /* ranks it exchanges flags with (senders and receivers) */
+    int nranks, pushCount, pushCtas, nPeers;
+};
+
 struct MainArgs {
     const ehyb_part_desc *parts;
     const ehyb_slice_desc *slices;
@@ -41,6 +73,9 @@ struct MainArgs {
     int dbg;   /* development only (EHYB_DEBUG_SKIP): 1 = skip remainder math, 2 = skip ELL math */
     const int32_t *cacheCols; /* per-partition remainder cache lists (permuted columns) */
     int cacheCap;             /* shared-memory cache capacity in elements (>= longest list) */
+    const int32_t *order;     /* CTA slot -> partition (NULL: identity) */
+    unsigned long long *trace; /* development (EHYB_TRACE=1): 8 globaltimer stamps per CTA, else NULL */
+    PeerArgs peer;
 };
 
 struct OverflowArgs {
@@ -50,6 +85,8 @@ struct OverflowArgs {
     const double *x;
     double *y;
     int perWarp; /* consecutive entries per warp, a multiple of 32 */
+    int n;       /* columns >= n are halo columns: peer.xh[c - n] */
+    PeerArgs peer;
 };
 
 /* ---------------------------------------------------------------- PTX helpers ----- */
@@ -72,6 +109,11 @@ __device__ __forceinline__ void fence_mbar_init()
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
@@ -140,6 +182,144 @@ __device__ __forceinline__ double ld_gather_f64(const double *p)
     return v;
 }
 
+/* ---------------------------------------------------------------- peer exchange --- */
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory"); /* clobber: keeps its place between barriers and memory operations */
+    return t;
+}
+
+/* Warp-collective (all 32 lanes, converged): waits until the first `firstOnly ? 1 : pushCtas(g)`
+ * flag words of every rank g in `mask` show `epoch` or later (flags only grow; compared modulo
+ * 2^32).  Bounded: a peer that never shows up sets *status instead of hanging the GPU, and the
+ * host reports it (ehyb_mg_status). */
+__device__ __noinline__ void peer_wait(const uint32_t *flags, uint32_t mask, int nranks, const int32_t *peerPushCtas, bool firstOnly,
+                                       uint32_t epoch, unsigned long long timeoutNs, uint32_t *status)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long t0 = 0;
+    for (int g = 0; g < nranks; ++g) {
+        if (!((mask >> g) & 1u)) continue;
+        const uint32_t *f = flags + g * kMaxPushCtas;
+        const int cnt = firstOnly ? 1 : __ldg(peerPushCtas + g);
+        for (;;) {
+            bool ok = true;
+            for (int i = lane; i < cnt; i += 32) ok = ok && static_cast<int32_t>(ld_acquire_sys_u32(f + i) - epoch) >= 0;
+            if (__all_sync(0xffffffffu, ok)) break;
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            if (__any_sync(0xffffffffu, now - t0 > timeoutNs)) {
+                if (lane == 0) atomicExch(status, 1u);
+                return;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+
+/* halo value of column c >= n: written by a peer over NVLink, L2 is the point of coherence */
+__device__ __forceinline__ double ld_halo_f64(const PeerArgs &pa, int n, int c) { return __ldcg(pa.xh + (c - n)); }
+
+/* Fills the shared-memory remainder cache of a partition from its column list (ascending, so
+ * halo columns are its tail).  Own columns are gathered right away; if the exchange runs inside
+ * this kernel (pa.flags) and the list has halo columns, warp 0 waits once for the neighbours'
+ * push of this product, a CTA barrier orders everybody behind it, and the tail is read from the
+ * halo buffer.  Called by all threads of the CTA (direct kernel, unaligned-x path). */
+__device__ __forceinline__ void fill_remainder_cache(double *cache, const int32_t *cols, int count, const double *x, int n,
+                                                     const PeerArgs &pa, int tid, int nthreads)
+{
+    bool skipped = false;
+    for (int i = tid; i < count; i += nthreads) {
+        const int c = __ldg(cols + i);
+        if (c < n) cache[i] = ld_gather_f64(x + c);
+        else if (pa.flags == nullptr) cache[i] = ld_halo_f64(pa, n, c); /* halo already in place (x tail) */
+        else skipped = true;
+    }
+    if (pa.flags != nullptr && __syncthreads_or(skipped)) {
+        if (tid < 32) peer_wait(pa.flags, pa.recvMask, pa.nranks, pa.peerPushCtas, false, pa.epoch, pa.timeoutNs, pa.status);
+        __syncthreads();
+        for (int i = tid; i < count; i += nthreads) {
+            const int c = __ldg(cols + i);
+            if (c >= n) cache[i] = ld_halo_f64(pa, n, c);
+        }
+    }
+}
+
+/* The push half, executed by ONE warp (the last one: under the static deal of slices it is a
+ * warp with the fewest slices) of every CTA blockIdx.x < pushCtas.  Two steps:
+ *   prepare (before griddepcontrol.wait, i.e. hidden when the grid was launched early): check
+ *           that the neighbours are done with the halo buffer of this parity, and fetch the
+ *           first 128 (index, address) pairs of this CTA's share into registers;
+ *   send    (x is final): gather, store to the neighbours, one st.release.sys per neighbour.
+ * No thread of a pushing warp waits for this product's flags before it has signalled: two GPUs
+ * doing that would deadlock. */
+struct PushRegs {
+    int idx[4];
+    unsigned long long dst[4];
+    int i0, i1;
+};
+
+__device__ __forceinline__ void peer_push_prepare(const PeerArgs &pa, int lane, PushRegs &pr)
+{
+    /* the neighbours' halo buffer of this parity was last read by their product epoch-2, which
+     * is complete once any of their CTAs has signalled epoch-1 (it passed its dependency wait) */
+    peer_wait(pa.flags, pa.nbrMask, pa.nranks, pa.peerPushCtas, true, pa.epoch - 1u, pa.timeoutNs, pa.status);
+    const int chunk = (pa.pushCount + pa.pushCtas - 1) / pa.pushCtas;
+    pr.i0 = static_cast<int>(blockIdx.x) * chunk;
+    pr.i1 = min(pr.i0 + chunk, pa.pushCount);
+    const unsigned long long *dstTab = reinterpret_cast<const unsigned long long *>(pa.pushDst);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = pr.i0 + u * 32 + lane;
+        pr.idx[u] = i < pr.i1 ? __ldg(pa.pushIdx + i) : 0;
+        pr.dst[u] = i < pr.i1 ? __ldg(dstTab + i) : 0ull;
+    }
+}
+
+__device__ __forceinline__ void peer_push_send(const PeerArgs &pa, const double *x, int lane, const PushRegs &pr)
+{
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld_gather_f64(x + pr.idx[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (pr.dst[u]) *reinterpret_cast<double *>(pr.dst[u]) = v[u];
+    /* shares beyond 128 entries: same pattern, loads not hoisted above the dependency wait */
+    const unsigned long long *dstTab = reinterpret_cast<const unsigned long long *>(pa.pushDst);
+    for (int base = pr.i0 + 128; base < pr.i1; base += 128) {
+        int idx[4];
+        unsigned long long dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * 32 + lane;
+            idx[u] = i < pr.i1 ? __ldg(pa.pushIdx + i) : 0;
+            dst[u] = i < pr.i1 ? __ldg(dstTab + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_gather_f64(x + idx[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (dst[u]) *reinterpret_cast<double *>(dst[u]) = v[u];
+    }
+    __syncwarp(); /* every lane's stores are ordered before lane j's release below */
+    if (lane < pa.nPeers) st_release_sys_u32(pa.peerFlag[lane] + blockIdx.x, pa.epoch);
+    for (int j = 32 + lane; j < pa.nPeers; j += 32) st_release_sys_u32(pa.peerFlag[j] + blockIdx.x, pa.epoch);
+}
+
 /* one ELL group: 4 columns x 2 rows per lane */
 struct Group {
     uint4 c;
@@ -184,14 +364,20 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(cons
     double *win = reinterpret_cast<double *>(smem + kSmemHeader);
 
     const int kpp = a.kpp;
-    const int p = blockIdx.x / kpp;
-    const int sub = blockIdx.x - p * kpp;
+    const int slot = blockIdx.x / kpp;
+    const int sub = blockIdx.x - slot * kpp;
+    const int p = a.order ? __ldg(a.order + slot) : slot;
     const int4 part = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p);
     const int4 part2 = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p + 1); /* cacheStart, cacheCount */
     const int ps = part.x, pe = part.y;
-    if (pe <= ps) return; /* empty partition (uniform over the CTA) */
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    /* multi-GPU: the last warp of the first pushCtas CTAs sends this CTA's share of the halo */
+    if (a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas && warp == nwarps - 1) {
+        PushRegs pr;
+        peer_push_prepare(a.peer, lane, pr);
+        peer_push_send(a.peer, a.x, lane, pr);
+    }
+    if (pe <= ps) return; /* empty partition (uniform over the CTA) */
     double *cache = win + ((a.W + 2 + 15) & ~15); /* remainder cache behind the window */
 
     /* ---- stage the x window: x[g0, winEnd) -> win[0, len), g0 = ps rounded down to even so
@@ -224,8 +410,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(cons
     } else {
         for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
     }
-    /* remainder cache: x at the partition's most referenced columns outside the window */
-    for (int i = tid; i < part2.y; i += blockDim.x) cache[i] = ld_gather_f64(a.x + __ldg(a.cacheCols + part2.x + i));
+    /* remainder cache: x at the partition's most referenced columns outside the window (halo
+     * columns included when the exchange runs inside this kernel) */
+    fill_remainder_cache(cache, a.cacheCols + part2.x, part2.y, a.x, a.n, a.peer, tid, blockDim.x);
 
     /* ---- slices of this CTA: local index t = sub + kpp*q, q handed out dynamically ---- */
     const int nsl = part.w - part.z;
@@ -329,6 +516,28 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) ehyb_main_kernel(cons
         if (r + 32 < pe) a.y[r + 32] = acc1;
         q = qn;
         d = dn;
+    }
+}
+
+/* Warp-level variant for the staged kernel: warp `fw` of `nFill` filling warps takes every
+ * nFill-th group of 32 list entries; a warp that meets halo columns waits for the neighbours'
+ * push itself (one poll per warp).  No CTA barrier: the caller arrives on an mbarrier. */
+__device__ __forceinline__ void fill_remainder_cache_warp(double *cache, const int32_t *cols, int count, const double *x, int n,
+                                                          const PeerArgs &pa, int fw, int nFill, int lane)
+{
+    bool skipped = false;
+    for (int i = fw * 32 + lane; i < count; i += nFill * 32) {
+        const int c = __ldg(cols + i);
+        if (c < n) cache[i] = ld_gather_f64(x + c);
+        else if (pa.flags == nullptr) cache[i] = ld_halo_f64(pa, n, c);
+        else skipped = true;
+    }
+    if (pa.flags != nullptr && __any_sync(0xffffffffu, skipped)) {
+        peer_wait(pa.flags, pa.recvMask, pa.nranks, pa.peerPushCtas, false, pa.epoch, pa.timeoutNs, pa.status);
+        for (int i = fw * 32 + lane; i < count; i += nFill * 32) {
+            const int c = __ldg(cols + i);
+            if (c >= n) cache[i] = ld_halo_f64(pa, n, c);
+        }
     }
 }
 
@@ -484,35 +693,61 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     constexpr uint32_t kSlotBytes = static_cast<uint32_t>(slot_bytes(KCE));
     constexpr uint32_t kSlotValBytes = static_cast<uint32_t>(slot_val_bytes(KCE));
     const int kpp = a.kpp;
-    const int p = blockIdx.x / kpp;
-    const int sub = blockIdx.x - p * kpp;
+    const int slot_ = blockIdx.x / kpp;
+    const int sub = blockIdx.x - slot_ * kpp;
+    /* CTAs are dispatched in blockIdx order; `order` lets the session run the partitions that
+     * depend on halo values last, when the neighbours have long delivered them */
+    const int p = a.order ? __ldg(a.order + slot_) : slot_;
     const int4 part = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p);
     const int4 part2 = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p + 1); /* cacheStart, cacheCount */
     const int ps = part.x, pe = part.y;
-    if (pe <= ps) return;
-
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = blockDim.x >> 5;
+    const bool pusher = a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas && warp == nw - 1;
+    unsigned long long *tr = a.trace ? a.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+    if (tr && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[0] = global_timer_ns(); /* CTA start */
+        tr[5] = smid;
+        tr[6] = static_cast<unsigned long long>(p);
+        tr[4] = 0;
+        tr[2] = 0;
+    }
+    PushRegs pr;
+    if (pe <= ps) { /* empty partition: only its share of the halo push */
+        if (pusher) {
+            peer_push_prepare(a.peer, lane, pr);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            peer_push_send(a.peer, a.x, lane, pr);
+        }
+        return;
+    }
     const int g0 = ps & ~1;
     const int winEnd = min(ps + a.W, a.n);
     const int len = winEnd - g0;
     double *win = reinterpret_cast<double *>(smem + kStageHeader);
     const uint32_t winBytes = (static_cast<uint32_t>(a.W + 2) * 8u + 127u) & ~127u;
     const uint32_t xsAddr = smem_u32(win) + static_cast<uint32_t>(ps - g0) * 8u;
-    const uint32_t winBar = smem_u32(smem);
+    const uint32_t winBar = smem_u32(smem);       /* x window staged (TMA bytes + the odd tail element) */
+    const uint32_t cacheBar = smem_u32(smem + 8); /* remainder cache staged (one arrival per filling warp) */
     const uint32_t slotBar0 = smem_u32(smem + 16) + static_cast<uint32_t>(warp * kSlotsPerWarp) * 8u;
     const uint32_t cacheBytes = (static_cast<uint32_t>(a.cacheCap) * 8u + 127u) & ~127u;
     double *cache = reinterpret_cast<double *>(smem + kStageHeader + winBytes);
     const uint32_t cacheAddr = smem_u32(cache);
     const uint32_t slot0 = cacheAddr + cacheBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
     const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    /* in a CTA that pushes halo values the last warp does only that; the others fill the cache */
+    const bool pushCta = a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas;
+    const int nFill = pushCta && nw > 1 ? nw - 1 : nw;
 
     /* Programmatic dependent launch: let the next grid in the stream start as soon as SMs free
      * up.  Its matrix stream (constant data) then overlaps this grid's tail; everything that
      * touches x or y comes after its own griddepcontrol.wait below. */
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
-        mbar_init(winBar, 1);
+        mbar_init(winBar, 2);
+        mbar_init(cacheBar, static_cast<uint32_t>(nFill));
         for (int i = 0; i < nw * kSlotsPerWarp; ++i) mbar_init(smem_u32(smem + 16) + i * 8u, 1);
         fence_mbar_init();
     }
@@ -526,29 +761,52 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     meta[1] = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane);
     uint32_t phases = 0; /* bit s = parity to wait for on slot s */
 
+    /* multi-GPU, pushing warp: everything of the halo push that does not need x */
+    if (pusher) peer_push_prepare(a.peer, lane, pr);
+
     /* x (and later y) belong to the stream's previous work: wait for it here (every thread
      * reads x below: the window tail / fallback copy and the remainder cache) */
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tr && tid == 0) tr[1] = global_timer_ns(); /* previous grid complete */
+    /* The prologue has no CTA-wide barrier: a warp starts on its ELL chunks as soon as the
+     * window has landed (winBar) and needs the remainder cache (cacheBar) only at its first
+     * remainder chunk; nobody waits for the warp that pushes halo values. */
+    bool cacheReady = false;
     if (tma_ok) {
         if (tid == 0) {
             const uint32_t bulkBytes = static_cast<uint32_t>(len & ~1) * 8u;
-            mbar_expect_tx(winBar, bulkBytes);
+            mbar_expect_tx(winBar, bulkBytes); /* arrival 1 of 2 */
             const char *src = reinterpret_cast<const char *>(a.x + g0);
             const uint32_t dst = smem_u32(win);
             for (uint32_t off = 0; off < bulkBytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, min(32768u, bulkBytes - off), winBar);
-        } else if (tid == blockDim.x - 1 && (len & 1)) {
-            win[len - 1] = a.x[g0 + len - 1]; /* odd tail element */
+        } else if (tid == blockDim.x - 1) {
+            if (len & 1) win[len - 1] = a.x[g0 + len - 1]; /* odd tail element */
+            mbar_arrive(winBar);                           /* arrival 2 of 2 (releases the store) */
         }
-    } else {
-        for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
-    }
-    /* remainder cache: x at the partition's most referenced columns outside the window,
-     * gathered once per CTA (the list is ascending: neighbouring lanes mostly share sectors) */
-    for (int i = tid; i < part2.y; i += blockDim.x) cache[i] = ld_gather_f64(a.x + __ldg(a.cacheCols + part2.x + i));
-    if (tma_ok) {
+        /* multi-GPU: this CTA's share of the x entries the neighbours need goes out over NVLink
+         * (last warp only; it joins the product when it is done) */
+        if (pusher) {
+            peer_push_send(a.peer, a.x, lane, pr);
+            if (tr && lane == 0) tr[2] = global_timer_ns(); /* this CTA's share pushed and signalled */
+        }
+        /* remainder cache: x at the partition's most referenced columns outside the window,
+         * gathered once per CTA (ascending list: neighbouring lanes mostly share sectors; halo
+         * columns, >= n, are its tail and wait for the neighbours' push) */
+        if (!pusher || nFill == nw) {
+            fill_remainder_cache_warp(cache, a.cacheCols + part2.x, part2.y, a.x, a.n, a.peer, warp, nFill, lane);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cacheBar);
+        }
         while (!mbar_try_wait(winBar, 0)) { }
+    } else {
+        /* x not 16-byte aligned: plain copies and a CTA barrier */
+        for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
+        if (pusher) peer_push_send(a.peer, a.x, lane, pr);
+        fill_remainder_cache(cache, a.cacheCols + part2.x, part2.y, a.x, a.n, a.peer, tid, blockDim.x);
+        __syncthreads();
+        cacheReady = true;
     }
-    __syncthreads(); /* odd tail element / fallback copy / remainder cache visible */
+    if (tr && tid == 0) tr[3] = global_timer_ns(); /* x window in shared memory */
 
     double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
     int s = 0; /* slot in use: chunks alternate between the two slots of the warp */
@@ -561,6 +819,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
         if (m.kc) {
             while (!mbar_try_wait(bar, (phases >> s) & 1u)) { }
             phases ^= 1u << s;
+            if ((m.flags & 1) && !cacheReady) { /* first remainder chunk of this warp */
+                while (!mbar_try_wait(cacheBar, 0)) { }
+                cacheReady = true;
+                if (tr && tid == 0) tr[7] = global_timer_ns(); /* remainder cache in shared memory */
+            }
             const uint32_t vAddr = slot + static_cast<uint32_t>(lane) * 16u;
             if (!(a.dbg & ((m.flags & 1) ? 1 : 2))) { /* (dbg: timing experiments skip the arithmetic) */
                 /* ELL chunk: indices into the x window, accumulators acc0/acc1; remainder
@@ -618,6 +881,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
         if (s) meta[1] = mn; else meta[0] = mn;
         s ^= 1;
     }
+    if (tr && lane == 0) atomicMax(tr + 4, global_timer_ns()); /* last warp of the CTA done */
 }
 
 /* ---------------------------------------------------------------- overflow kernel -- */
@@ -647,15 +911,23 @@ __global__ void __launch_bounds__(256) ehyb_overflow_kernel(const OverflowArgs a
     const int64_t end = min(begin + a.perWarp, a.count);
     int carryRow = -1;
     double carry = 0.0;
+    bool haloReady = false;
     for (int64_t base = begin; base < end; base += 32) {
         const int64_t i = base + lane;
         const bool live = i < end;
         int r = -2 - lane; /* dead lanes: unique rows, never merged, never written */
         double prod = 0.0;
+        int c = 0;
         if (live) {
             r = __ldg(a.row + i);
-            prod = __ldg(a.val + i) * __ldg(a.x + __ldg(a.col + i));
+            c = __ldg(a.col + i);
         }
+        if (a.peer.flags != nullptr && !haloReady && __any_sync(0xffffffffu, c >= a.n)) {
+            /* first halo column of this warp: wait (once) for the neighbours' push */
+            peer_wait(a.peer.flags, a.peer.recvMask, a.peer.nranks, a.peer.peerPushCtas, false, a.peer.epoch, a.peer.timeoutNs, a.peer.status);
+            haloReady = true;
+        }
+        if (live) prod = __ldg(a.val + i) * (c < a.n ? ld_gather_f64(a.x + c) : ld_halo_f64(a.peer, a.n, c));
         if (lane == 0 && r == carryRow) prod += carry; /* continue the carried segment */
         const int flushRow = (lane == 0 && carryRow >= 0 && r != carryRow) ? carryRow : -1;
         if (flushRow >= 0) atomicAdd(a.y + flushRow, carry);

@@ -407,6 +407,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     v->parts = L->parts; v->slices = L->slices; v->blob = L->blob; v->blobBytes = blobBytes;
     v->nOverflow = nOvf; v->ovfRow = L->ovfRow; v->ovfCol = L->ovfCol; v->ovfVal = L->ovfVal;
     v->cacheCols = L->cacheCols; v->cacheTotal = cacheTotal; v->cacheMax = cacheMax;
+    v->haloInOverflow = haloOvf;
     v->nnzEll = nnzEll; v->nnzRemInSlice = nnzRemIn; v->nnzOverflow = nnzOvf;
     v->padEll = padEll; v->padRem = padRem; v->nLongRows = nLong;
     v->algBytes = 8 * v->nnz + 2 * nnzEll + 4 * (v->nnz - nnzEll) + 8 * ncols + 8 * (int64_t)n;

@@ -10,10 +10,12 @@
  *     (local column index n_local + position in the list);
  *   - the local operator: columns renumbered [own | halo], rows/own columns permuted by the
  *     level-2 (per-GPU) partition exactly like the single-GPU path (ehyb_reorder_core), and
- *     built into the tuned layout with every halo entry in the overflow list, so that the main
- *     kernel never depends on the exchange;
+ *     built into the tuned layout - for the NCCL exchange with every halo entry in the overflow
+ *     list, so that the main kernel never depends on the exchange; for the peer-memory
+ *     exchange with halo columns in the partitions' remainder caches;
  *   - the send list: permuted local indices of the x entries each peer asked for.
- * The per-product data path (pack kernel, NCCL send/recv, launches) is cuda/ehyb_mg.cu.
+ * The per-product data path (peer-memory push / NCCL send/recv, launches) is the "multi-GPU"
+ * part of cuda/ehyb_device.cu.
  * Who needs what is exchanged between the ranks by the caller (any transport: the Python
  * front end uses torch.distributed, gloo on CPU and nccl on GPU), which keeps this file free
  * of communication and testable without GPUs.
@@ -169,9 +171,11 @@ int ehyb_mg_local_set_send(ehyb_mg_local *L, const int64_t *sendCount, const int
 
 /* Level-2: partition the own-column block (symmetrised pattern handled by the caller's choice
  * of partVec; NULL = contiguous blocks), permute, build the layout. */
-int ehyb_mg_local_finish(ehyb_mg_local *L, int nParts, int W, int ctasPerPart, const uint32_t *partVec, double er_fill)
+int ehyb_mg_local_finish(ehyb_mg_local *L, int nParts, int W, int ctasPerPart, const uint32_t *partVec, double er_fill,
+                         int exchange)
 {
-    if (!L || nParts <= 0 || W <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_local_finish: bad argument");
+    if (!L || nParts <= 0 || W <= 0 || (exchange != EHYB_MG_NCCL && exchange != EHYB_MG_P2P))
+        return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_local_finish: bad argument");
     if (L->finished) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_local_finish: already finished");
     const int n = (int)L->n;
     const int64_t nnz = L->nnz;
@@ -228,7 +232,11 @@ int ehyb_mg_local_finish(ehyb_mg_local *L, int nParts, int W, int ctasPerPart, c
     ehyb_layout_opts o;
     memset(&o, 0, sizeof o);
     o.W = W; o.ctasPerPart = ctasPerPart > 0 ? ctasPerPart : 1; o.er_fill = er_fill;
-    o.ncols = n + L->nHalo; o.halo_in_overflow = 1;
+    o.ncols = n + L->nHalo;
+    /* NCCL exchange: the halo arrives on another stream while the main kernel runs, so no halo
+     * entry may sit in a slice; peer-memory exchange: halo columns are served from the
+     * remainder cache like any other column outside the window */
+    o.halo_in_overflow = exchange == EHYB_MG_NCCL;
     return ehyb_layout_build(m, &o, &L->layout);
 }
 

@@ -1,10 +1,16 @@
 """Multi-GPU front end: one process per GPU (torchrun), rows distributed in contiguous blocks.
 
 torch.distributed is plumbing only: it carries the set-up exchanges (who needs which x entries,
-the NCCL unique id) and the barrier / max-over-ranks around timed regions.  The per-product data
-path - pack kernel, grouped ncclSend/ncclRecv of the x halo overlapped with the main kernel,
-overflow kernel on the received halo - is C/CUDA inside libehyb.so (csrc/cuda/ehyb_device.cu,
-"multi-GPU"), reached through include/ehyb.h ehyb_mg_*.
+the CUDA IPC handles of the halo buffers or the NCCL unique id) and the barrier / max-over-ranks
+around timed regions.  The per-product data path is C/CUDA inside libehyb.so
+(csrc/cuda/ehyb_device.cu "multi-GPU", csrc/cuda/ehyb_kernels.cuh PeerArgs), reached through
+include/ehyb.h ehyb_mg_*:
+
+  exchange "p2p"  (default) the main kernel stores the x entries its neighbours need into their
+                  halo buffers over NVLink and reads its own halo columns through the
+                  shared-memory remainder cache: one launch per product, no collective call;
+  exchange "nccl" (baseline) pack kernel + grouped ncclSend/ncclRecv overlapped with the main
+                  kernel, halo entries in the overflow list (a second launch).
 """
 from __future__ import annotations
 
@@ -83,12 +89,13 @@ class DistributedBlock:
         self.lib.ehyb_free_host(xadj); self.lib.ehyb_free_host(adj)
         return xa, ad
 
-    def finish(self, nParts, W, kpp=1, partVec=None, er_fill=-1.0):
+    def finish(self, nParts, W, kpp=1, partVec=None, er_fill=-1.0, exchange="p2p"):
         pv = None
         if partVec is not None:
             pv = np.ascontiguousarray(partVec, np.uint32)
+        self.exchange = exchange
         check(self.lib, self.lib.ehyb_mg_local_finish(self.h, nParts, W, kpp, pv.ctypes.data_as(L.c_u32_p) if pv is not None else None,
-                                                      C.c_double(er_fill)), "ehyb_mg_local_finish")
+                                                      C.c_double(er_fill), EXCHANGES[exchange]), "ehyb_mg_local_finish")
         coo = C.POINTER(MatrixCOO)(); lay = C.c_void_p(); ns = C.c_int64(); si = C.POINTER(C.c_int32)(); sc = L.c_i64_p()
         check(self.lib, self.lib.ehyb_mg_local_view(self.h, C.byref(coo), C.byref(lay), C.byref(ns), C.byref(si), C.byref(sc)),
               "ehyb_mg_local_view")
@@ -101,16 +108,48 @@ class DistributedBlock:
         v = api.LayoutView()
         check(self.lib, self.lib.ehyb_layout_get(lay, C.byref(v)), "ehyb_layout_get")
         self.stats = {k: getattr(v, k) for k in ("n", "ncols", "nnz", "nParts", "W", "nSlices", "nOverflow", "nnzEll",
-                                                 "nnzRemInSlice", "nnzOverflow", "algBytes", "formatBytes")}
+                                                 "nnzRemInSlice", "nnzOverflow", "algBytes", "formatBytes", "cacheMax",
+                                                 "haloInOverflow")}
+        self.layout = lay
+
+    def recv_offsets_on_peers(self, all_recv_counts):
+        """all_recv_counts[g] = rank g's recvCount array.  Entry g of the result: where this rank's
+        entries start in rank g's halo list (the list is grouped by owner in rank order)."""
+        return np.array([int(np.sum(np.asarray(all_recv_counts[g])[:self.rank])) for g in range(self.world)], np.int64)
 
     # ---- device ------------------------------------------------------------------------
     def create_session(self, device, unique_id: bytes):
+        """NCCL exchange (collective: joins the communicator)."""
         self.session = C.c_void_p()
         buf = C.create_string_buffer(unique_id, 128)
         check(self.lib, self.lib.ehyb_mg_session_create(self.h, self.rank, self.world, device, buf, C.byref(self.session)),
               "ehyb_mg_session_create")
         self.handle = C.c_void_p()
         check(self.lib, self.lib.ehyb_mg_session_handle(self.session, C.byref(self.handle)), "ehyb_mg_session_handle")
+
+    def create_session_p2p(self, device, dist):
+        """Peer-memory exchange (collective over `dist`: IPC handles and halo offsets are gathered)."""
+        self.session = C.c_void_p()
+        check(self.lib, self.lib.ehyb_mg_session_create_p2p(self.h, self.rank, self.world, device, C.byref(self.session)),
+              "ehyb_mg_session_create_p2p")
+        self.handle = C.c_void_p()
+        check(self.lib, self.lib.ehyb_mg_session_handle(self.session, C.byref(self.handle)), "ehyb_mg_session_handle")
+        blob = C.create_string_buffer(P2P_BLOB_BYTES)
+        check(self.lib, self.lib.ehyb_mg_p2p_export(self.session, blob), "ehyb_mg_p2p_export")
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, (blob.raw, [int(c) for c in self.recvCount]))
+        blobs = C.create_string_buffer(b"".join(g[0] for g in gathered), P2P_BLOB_BYTES * self.world)
+        off = self.recv_offsets_on_peers([g[1] for g in gathered])
+        check(self.lib, self.lib.ehyb_mg_p2p_connect(self.session, blobs, off.ctypes.data_as(L.c_i64_p)), "ehyb_mg_p2p_connect")
+        dist.barrier()  # every rank has mapped its neighbours before anybody pushes
+
+    def launches_per_spmv(self):
+        return int(self.lib.ehyb_mg_launches_per_spmv(self.session))
+
+    def timed_out(self):
+        t = C.c_int()
+        check(self.lib, self.lib.ehyb_mg_status(self.session, C.byref(t)), "ehyb_mg_status")
+        return bool(t.value)
 
     def set_x(self, x_local_perm):
         xe = np.zeros(self.n + self.nHalo, np.float64)
@@ -142,6 +181,17 @@ class DistributedBlock:
             self.h = C.c_void_p()
 
 
+EXCHANGES = {"nccl": 0, "p2p": 1}  # EHYB_MG_NCCL, EHYB_MG_P2P
+P2P_BLOB_BYTES = 128               # EHYB_MG_P2P_BLOB_BYTES
+
+
+def p2p_supported(device, world) -> bool:
+    lib = L.load()
+    ok = C.c_int()
+    check(lib, lib.ehyb_mg_p2p_supported(device, world, C.byref(ok)), "ehyb_mg_p2p_supported")
+    return bool(ok.value)
+
+
 def unique_id() -> bytes:
     lib = L.load()
     buf = C.create_string_buffer(128)
@@ -161,7 +211,7 @@ def x_of_global(idx):
     return ((z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53)) - 0.5) * 0.2
 
 
-def setup_slab(rank, world, grid, dist, partition="metis"):
+def setup_slab(rank, world, grid, dist, partition="metis", exchange="p2p"):
     """Rank's z-slab of the 27-point stencil on nx x ny x (nz*world)."""
     nx, ny, nzl = grid
     plane = nx * ny
@@ -182,8 +232,16 @@ def setup_slab(rank, world, grid, dist, partition="metis"):
         check(blk.lib, blk.lib.ehyb_partition_graph(C.c_uint32(blk.n), xa.ctypes.data_as(L.c_u32_p), ad.ctypes.data_as(L.c_u32_p),
                                                     C.c_uint32(pl.nParts), C.c_uint32(1), pv.ctypes.data_as(L.c_u32_p)),
               "ehyb_partition_graph")
-    blk.finish(pl.nParts, pl.W, pl.ctasPerPart, pv)
+    blk.finish(pl.nParts, pl.W, pl.ctasPerPart, pv, exchange=exchange)
     return blk, rowStarts
+
+
+EXCHANGE_TEXT = {
+    "p2p": "inside the main kernel: x entries stored into the neighbours' halo buffers over NVLink (CUDA IPC peer "
+           "memory, epoch flags), halo columns served from the shared-memory remainder cache; one launch per product",
+    "nccl": "pack kernel + grouped ncclSend/ncclRecv per product, overlapped with the main kernel; halo entries in the "
+            "overflow kernel",
+}
 
 
 def bench(args, rank, world, local, grid, workload):
@@ -193,11 +251,21 @@ def bench(args, rank, world, local, grid, workload):
     from bench import ClockSampler, measured_peaks, stdout_to_stderr
 
     t0 = time.time()
+    exchange = os.environ.get("EHYB_MG_EXCHANGE", "p2p")
+    if exchange == "p2p":
+        # every rank must be able to map its neighbours' memory, else all fall back to NCCL
+        ok = torch.tensor([1 if p2p_supported(local, world) else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            raise SystemExit("bench.py: the GPUs of this box have no peer access; set EHYB_MG_EXCHANGE=nccl")
     with stdout_to_stderr():
-        blk, rowStarts = setup_slab(rank, world, grid, dist, os.environ.get("EHYB_MG_PARTITION", "metis"))
-        ids = [unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        blk.create_session(local, ids[0])
+        blk, rowStarts = setup_slab(rank, world, grid, dist, os.environ.get("EHYB_MG_PARTITION", "metis"), exchange)
+        if exchange == "p2p":
+            blk.create_session_p2p(local, dist)
+        else:
+            ids = [unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            blk.create_session(local, ids[0])
     t_prep = time.time() - t0
     r0 = int(rowStarts[rank])
     x_nat = x_of_global(np.arange(r0, r0 + blk.n))
@@ -208,6 +276,8 @@ def bench(args, rank, world, local, grid, workload):
     # parity of one distributed product: CPU CSR of the permuted local block on [x_local | halo]
     blk.spmv()
     y = blk.get_y()
+    if blk.timed_out():
+        raise SystemExit("bench.py: rank %d: a neighbour did not deliver its halo" % rank)
     from oracle import oracle as O
     orc = O.Oracle()
     x_ext = np.concatenate([x_perm, x_of_global(blk.haloGlobal)])
@@ -259,15 +329,19 @@ def bench(args, rank, world, local, grid, workload):
                        "decomposition": "z-slabs, one per GPU; level-2 partition per GPU: " + os.environ.get("EHYB_MG_PARTITION", "metis"),
                        "n_per_gpu": blk.n, "nnz_total": int(nnz_all), "halo_x_entries_total": int(halo_all),
                        "partitions_per_gpu": blk.stats["nParts"], "window": blk.stats["W"],
-                       "exchange": "pack kernel + grouped ncclSend/ncclRecv per product, overlapped with the main kernel",
+                       "exchange": EXCHANGE_TEXT[exchange], "nnz_overflow_rank0": blk.stats["nOverflow"],
+                       "remainder_cache_max": blk.stats["cacheMax"],
                        "l2": "matrix data per GPU larger than L2, no flush", "host_prep_s": round(t_prep, 1)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                         "note": "rank 0 algorithmic bytes / whole-step time (main kernel + exchange + overflow)"},
+                         "kernel": "ehyb_staged_kernel",
+                         "note": "rank 0 algorithmic bytes / whole-step time (the step is the main kernel with the "
+                                 "exchange inside it)" if exchange == "p2p" else
+                                 "rank 0 algorithmic bytes / whole-step time (main kernel + exchange + overflow)"},
             "e2e": {"value": round(2.0 * nnz_all * args.steps / te / 1e9, 2), "unit": "GFLOP/s",
                     "h2d_bytes_per_step": 8 * (blk.n + blk.nHalo), "d2h_bytes_per_step": 8 * blk.n,
                     "api": "ehyb_set_x + ehyb_mg_spmv + ehyb_get_y per step, per rank"},
-            "gpu_launches": args.steps * (2 + (1 if blk.stats["nOverflow"] else 0)),
+            "gpu_launches": args.steps * blk.launches_per_spmv(),
             "clocks": clocks,
             "parity": {"rows_outside_1e-12_gate_all_ranks": int(gate_all)},
         }

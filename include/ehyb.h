@@ -36,7 +36,8 @@ typedef enum ehyb_status {
     EHYB_ERR_PARTITION = -4, /* the partitioner failed or is not available */
     EHYB_ERR_IO = -5,        /* file problem */
     EHYB_ERR_LIMIT = -6,     /* a format limit was exceeded (e.g. window larger than 65536) */
-    EHYB_ERR_NCCL = -7       /* an NCCL call failed */
+    EHYB_ERR_NCCL = -7,      /* an NCCL call failed */
+    EHYB_ERR_PEER = -8       /* peer-memory exchange: no P2P access, or a neighbour never delivered */
 } ehyb_status;
 
 const char *ehyb_last_error(void);
@@ -162,7 +163,7 @@ typedef struct ehyb_layout_view {
     const int32_t *cacheCols;      /* [cacheTotal] per-partition remainder cache lists */
     int64_t cacheTotal;
     int32_t cacheMax;              /* longest list: sizes the shared-memory cache */
-    int32_t reserved;
+    int32_t haloInOverflow;        /* built with halo_in_overflow (no halo column in a cache list) */
     /* statistics */
     int64_t nnzEll, nnzRemInSlice, nnzOverflow, padEll, padRem, nLongRows;
     int64_t algBytes;              /* 8 nnz + 2 nnzEll + 4 (nnz - nnzEll) + 16 n, BASELINE.md sec. 3 */
@@ -231,6 +232,11 @@ int ehyb_sync(ehyb_handle *h);
 void *ehyb_stream(ehyb_handle *h); /* cudaStream_t */
 void ehyb_free(ehyb_handle *h);
 
+/* Development aid: with EHYB_TRACE=1 in the environment when the session is created, the main
+ * kernel records a per-CTA timeline of the last product (8 words per CTA, see
+ * ehyb_device.cu); *ctas = 0 when tracing is off.  out may be NULL to query the size. */
+int ehyb_trace_read(ehyb_handle *h, unsigned long long *out, int *ctas);
+
 /* Device-side description in the reference's struct (for matrixVectorEHYB callers): fills
  * `d` with dimension/nParts/... and d->b200 = h.  No arrays in the reference layout exist
  * on the device. */
@@ -238,11 +244,19 @@ int ehyb_describe(ehyb_handle *h, matrixEHYB *d);
 
 /* ------------------------------------------------------------------------------------ */
 /* multi-GPU: one process per GPU, rows distributed in contiguous blocks, x halo exchanged    */
-/* with NCCL send/recv every product (no reference counterpart)        */
+/* every product (no reference counterpart).  Two exchanges:             */
+/*   EHYB_MG_P2P   (product) the main kernel itself stores the x entries its neighbours need   */
+/*                 into their memory over NVLink (CUDA IPC mappings + epoch flags) and serves  */
+/*                 halo columns from the shared-memory remainder cache: one launch per product */
+/*   EHYB_MG_NCCL  (baseline) pack kernel + grouped ncclSend/ncclRecv on a second stream,      */
+/*                 overlapped with the main kernel; halo entries live in the overflow list     */
 /* ------------------------------------------------------------------------------------ */
 
 typedef struct ehyb_mg_local ehyb_mg_local;     /* host: a rank's block, halo and send lists */
-typedef struct ehyb_mg_session ehyb_mg_session; /* device: the block on its GPU + NCCL communicator */
+typedef struct ehyb_mg_session ehyb_mg_session; /* device: the block on its GPU + its exchange state */
+
+#define EHYB_MG_NCCL 0
+#define EHYB_MG_P2P 1
 
 /* rowStarts[nranks+1]: global row range of every rank.  rowPtr/colGlobal/val: the rank's rows
  * (CSR, global column indices).  Computes the halo (sorted external columns, grouped by owner). */
@@ -256,24 +270,43 @@ int ehyb_mg_local_halo(const ehyb_mg_local *L, int64_t *nHalo, const int64_t **h
 int ehyb_mg_local_set_send(ehyb_mg_local *L, const int64_t *sendCount, const int64_t *sendGlobal);
 /* Graph of the block's own columns for the level-2 partitioner (malloc'd, ehyb_free_host). */
 int ehyb_mg_local_graph(const ehyb_mg_local *L, uint32_t **xadj, uint32_t **adjncy);
-/* Level-2 partition (partVec[n_local], NULL = contiguous blocks), permutation, tuned layout
- * with every halo entry in the overflow list. */
+/* Level-2 partition (partVec[n_local], NULL = contiguous blocks), permutation, tuned layout.
+ * exchange = EHYB_MG_NCCL: every halo entry in the overflow list (the main kernel must not
+ * depend on the exchange); EHYB_MG_P2P: halo columns are ordinary remainder columns. */
 int ehyb_mg_local_finish(ehyb_mg_local *L, int nParts, int W, int ctasPerPart, const uint32_t *partVec,
-                         double er_fill);
+                         double er_fill, int exchange);
 int ehyb_mg_local_view(const ehyb_mg_local *L, const matrixCOO **coo, const ehyb_layout **layout,
                        int64_t *nSend, const int32_t **sendIdx, const int64_t **sendCount);
 void ehyb_mg_local_free(ehyb_mg_local *L);
 
 /* 128-byte NCCL unique id (rank 0 creates it, the caller distributes it). */
 int ehyb_mg_unique_id(void *id128);
-/* Collective: uploads the block and joins the communicator. */
+/* NCCL exchange.  Collective: uploads the block and joins the communicator. */
 int ehyb_mg_session_create(const ehyb_mg_local *L, int rank, int nranks, int device, const void *id128,
                            ehyb_mg_session **out);
+/* Peer-memory exchange, three steps (the caller moves the blobs between the ranks, any
+ * transport):  create_p2p (uploads the block, allocates halo buffers + flags)  ->  p2p_export
+ * (EHYB_MG_P2P_BLOB_BYTES describing this rank's buffers)  ->  p2p_connect with the blobs of
+ * ALL ranks (rank-major) and recvOffsetOnPeer[g] = position of this rank's first entry in rank
+ * g's halo list (= sum of g's recvCount[0..rank)).  Needs P2P access between the GPUs
+ * (NVLink/NVSwitch) and nranks <= 32. */
+#define EHYB_MG_P2P_BLOB_BYTES 128
+int ehyb_mg_p2p_supported(int device, int nranks, int *supported);
+int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int nranks, int device, ehyb_mg_session **out);
+int ehyb_mg_p2p_export(ehyb_mg_session *s, void *blob);
+int ehyb_mg_p2p_connect(ehyb_mg_session *s, const void *blobs, const int64_t *recvOffsetOnPeer);
+/* Set when a wait on a neighbour ran into the time limit ($EHYB_P2P_TIMEOUT_MS, default 10 s)
+ * since the session was created: the products since then are not valid. */
+int ehyb_mg_status(ehyb_mg_session *s, int *timed_out);
 int ehyb_mg_session_handle(ehyb_mg_session *s, ehyb_handle **h);
-/* y_local = A_block [x_local | halo]: pack + grouped ncclSend/ncclRecv on a second stream,
- * overlapped with the main kernel; the overflow kernel (all halo entries) follows. */
+/* y_local = A_block [x_local | halo].  x_d: the n local entries (NCCL exchange: n + nHalo, the
+ * halo part is filled here).  Collective in the sense that every rank has to call it the same
+ * number of times; asynchronous on the session stream. */
 int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d);
 int ehyb_mg_time_spmv(ehyb_mg_session *s, int warmup, int iters, float *ms_total);
+/* Kernel launches one distributed product issues. */
+int ehyb_mg_launches_per_spmv(const ehyb_mg_session *s);
+/* Every rank must have finished its products before any rank frees its session (barrier). */
 void ehyb_mg_session_free(ehyb_mg_session *s);
 /* Rows of z-planes [z0, z1) of the 27-point stencil on nx x ny x nz (full rows, global
  * columns ascending): a rank's slab of BASELINE.json config 5, generated in place. */

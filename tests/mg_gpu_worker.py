@@ -1,0 +1,79 @@
+"""Worker of tests/test_gpu_multi.py: one rank (one GPU) of a multi-GPU job.
+
+Runs distributed products through the C ABI (ehyb_mg_*) with a DIFFERENT x every product - a
+halo value read too early, too late or from the wrong buffer parity cannot pass - and checks
+every y against the oracle's CSR product of the rank's block on [x_local | halo]."""
+import ctypes as C
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("EHYB_MTMETIS_BIN", str(ROOT / "bin" / "ehyb_mtmetis"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from ehyb_spmv_gpu_b200 import _lib as L
+    from ehyb_spmv_gpu_b200 import multigpu as mg
+    from oracle import oracle as O
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    exchange, partition = sys.argv[1], sys.argv[2]
+    grid = tuple(int(v) for v in sys.argv[3].split("x"))
+    products = int(sys.argv[4]) if len(sys.argv) > 4 else 7
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    if exchange == "p2p":
+        assert mg.p2p_supported(rank, world), "no peer access between the GPUs of this box"
+    blk, rowStarts = mg.setup_slab(rank, world, grid, dist, partition, exchange)
+    if exchange == "p2p":
+        blk.create_session_p2p(rank, dist)
+        assert blk.launches_per_spmv() == 1 + (1 if blk.stats["nOverflow"] else 0)
+    else:
+        ids = [mg.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        blk.create_session(rank, ids[0])
+    orc = O.Oracle()
+    r0 = int(rowStarts[rank])
+    gl = np.arange(r0, r0 + blk.n)
+    worst = 0.0
+    for k in range(products):
+        # x_k(global i) = base(i) * (k + 1) + 0.01 k: every product has its own halo values
+        x_nat = mg.x_of_global(gl) * (k + 1) + 0.01 * k
+        x_perm = np.empty(blk.n)
+        x_perm[blk.coo["reorderList"]] = x_nat
+        blk.set_x(x_perm)
+        blk.spmv()
+        y = blk.get_y()
+        halo = mg.x_of_global(blk.haloGlobal) * (k + 1) + 0.01 * k
+        x_ext = np.concatenate([x_perm, halo])
+        y_ref = orc.csr_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_ext)
+        absAx = orc.csr_abs_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_ext)
+        bad = np.flatnonzero(~(np.abs(y - y_ref) <= 1e-12 * absAx))
+        assert bad.size == 0, "rank %d product %d: %d rows outside the gate, first %s" % (rank, k, bad.size, bad[:5])
+        worst = max(worst, float(np.abs(y - y_ref).max()))
+    assert not blk.timed_out(), "a neighbour did not deliver its halo in time"
+    # back-to-back products without host synchronisation in between (the timed loop)
+    ms = blk.time_spmv(3, 50)
+    assert ms > 0
+    y2 = blk.get_y()
+    if blk.stats["nOverflow"] == 0:
+        # every row is summed by one lane in a fixed order: bit-reproducible
+        assert np.array_equal(y2, y), "back-to-back products of the same x changed y"
+    else:
+        # overflow entries are added with atomics (order varies): inside the gate of the last x
+        assert np.all(np.abs(y2 - y_ref) <= 1e-12 * absAx), "back-to-back products left the gate"
+    dist.barrier()
+    blk.free()
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank %d ok (max abs err %.3g, %.1f us/product)" % (rank, worst, ms / 50 * 1e3))
+
+
+if __name__ == "__main__":
+    main()

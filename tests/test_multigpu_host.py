@@ -17,8 +17,9 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,partition", [(2, "blocks"), (3, "blocks"), (2, "metis")])
-def test_distributed_product_gloo(world, partition):
+@pytest.mark.parametrize("world,partition,exchange", [(2, "blocks", "nccl"), (3, "blocks", "p2p"), (2, "metis", "p2p"),
+                                                      (2, "metis", "nccl")])
+def test_distributed_product_gloo(world, partition, exchange):
     if partition == "metis" and not (ROOT / "bin" / "ehyb_mtmetis").exists():
         pytest.skip("bin/ehyb_mtmetis not built")
     port = _free_port()
@@ -26,7 +27,7 @@ def test_distributed_product_gloo(world, partition):
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                    OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "mg_worker.py"), partition], env=env,
+        procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "mg_worker.py"), partition, exchange], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
     for p in procs:

@@ -57,3 +57,38 @@ def assert_within_gate(y, y_ref, absAx, tol=1e-12):
     """BASELINE.json accuracy gate: |y - y_ref| <= tol * (|A||x|) per row."""
     bad = np.flatnonzero(~(np.abs(y - y_ref) <= tol * absAx))
     assert bad.size == 0, f"{bad.size} rows outside the gate, first {bad[:5]}, err {np.abs(y - y_ref)[bad[:5]]}, bound {tol * absAx[bad[:5]]}"
+
+
+def layout_spmv(raw, x_ext):
+    """y = A x evaluated from the device-facing arrays of a tuned layout (Layout.raw()) with the
+    index formulas of DESIGN.md section 3, written in numpy independently of layout.c and of the
+    kernels.  x_ext has ncols entries ([own | halo] for a distributed block)."""
+    parts, sl, blob = raw["parts"], raw["slices"], raw["blob"]
+    n = int(parts[-1][1])
+    y = np.zeros(n)
+    for p in range(len(parts)):
+        rs, re_, s0, s1, cs, cc = (int(v) for v in parts[p][:6])
+        cache = raw["cacheCols"][cs:cs + cc]
+        for s in range(s0, s1):
+            off = int(sl["off256"][s]) * 256
+            w, wr = int(sl["w"][s]), int(sl["wr"][s])
+            w4, wr4 = (w + 3) // 4, (wr + 3) // 4
+            ev = blob[off:off + w * 512].view(np.float64).reshape(w, 32, 2)
+            ec = blob[off + w * 512:off + w * 512 + w4 * 512].view(np.uint16).reshape(w4, 32, 2, 4)
+            ro = off + w * 512 + w4 * 512
+            rv = blob[ro:ro + wr * 512].view(np.float64).reshape(wr, 32, 2)
+            rc = blob[ro + wr * 512:ro + wr * 512 + wr4 * 512].view(np.uint16).reshape(wr4, 32, 2, 4)
+            acc = np.zeros((32, 2))
+            if w:
+                cols = ec.transpose(0, 3, 1, 2).reshape(w4 * 4, 32, 2)[:w].astype(np.int64) + rs
+                acc += (ev * x_ext[np.minimum(cols, len(x_ext) - 1)]).sum(axis=0)
+            if wr:
+                idx = rc.transpose(0, 3, 1, 2).reshape(wr4 * 4, 32, 2)[:wr].astype(np.int64)
+                acc += (rv * x_ext[cache[idx]]).sum(axis=0)
+            r0 = rs + (s - s0) * 64
+            for h in range(2):
+                lo = r0 + 32 * h
+                cnt = max(0, min(32, re_ - lo))
+                y[lo:lo + cnt] = acc[:cnt, h]
+    np.add.at(y, raw["ovfRow"], raw["ovfVal"] * x_ext[raw["ovfCol"]])
+    return y
