@@ -51,7 +51,7 @@ struct ehyb_handle {
     double *x, *y;       /* session vectors */
     double *xb[2], *yb[2]; /* double buffers of the pipelined host path (lazy) */
     cudaEvent_t evX[2], evK[2], evY[2], ev0, ev1;
-    int use_graph, l2_persist, pdl, dbgSkip, haloInOverflow;
+    int use_graph, l2_persist, pdl, dbgSkip, haloInOverflow, l2hint, winPiece;
     cudaGraphExec_t gexec;
     const double *gx;
     double *gy;
@@ -249,6 +249,9 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     h->pdl = env_int("EHYB_PDL", 1);
     h->dbgSkip = env_int("EHYB_DEBUG_SKIP", 0); /* development: timing experiments without the arithmetic */
     h->haloInOverflow = v->haloInOverflow;
+    h->l2hint = env_int("EHYB_L2_HINT", 1);
+    h->winPiece = env_int("EHYB_WIN_PIECE", 32768) & ~15;
+    if (h->winPiece < 16) h->winPiece = 32768;
     if (env_int("EHYB_TRACE", 0)) {
         CU(cudaMalloc(&h->trace, sizeof(unsigned long long) * 8 * (size_t)h->nParts * (size_t)h->kpp));
         CU(cudaMemset(h->trace, 0, sizeof(unsigned long long) * 8 * (size_t)h->nParts * (size_t)h->kpp));
@@ -320,6 +323,8 @@ static MainArgs main_args(const ehyb_handle *h, const double *x_d, double *y_d, 
     a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
     a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = h->dbgSkip; a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
     a.order = h->order;
+    a.l2hint = h->l2hint;
+    a.winPiece = (uint32_t)h->winPiece;
     a.trace = h->trace;
     a.peer = pa ? *pa : no_peer(h, x_d);
     return a;

@@ -74,6 +74,8 @@ struct MainArgs {
     const int32_t *cacheCols; /* per-partition remainder cache lists (permuted columns) */
     int cacheCap;             /* shared-memory cache capacity in elements (>= longest list) */
     const int32_t *order;     /* CTA slot -> partition (NULL: identity) */
+    int l2hint;               /* staged kernel: L2 eviction hints on the TMA copies (stream evict-first, x evict-last) */
+    uint32_t winPiece;        /* staged kernel: bytes per bulk copy of the x window (multiple of 16) */
     unsigned long long *trace; /* development (EHYB_TRACE=1): 8 globaltimer stamps per CTA, else NULL */
     PeerArgs peer;
 };
@@ -137,6 +139,22 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
+}
+
+/* the same with an L2 eviction-priority hint (createpolicy): evict-first for the matrix stream,
+ * which is read once per product, evict-last for x, which every product reads again */
+__device__ __forceinline__ void tma_bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_evict_last_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
 
 /* streaming 128-bit loads: read-only path, no L1 allocation, evict-first in L2 */
@@ -640,7 +658,7 @@ struct ChunkMeta {
 
 /* Describes the next chunk, advances the walker and (lane 0) starts its TMA copies. */
 template <int KCE>
-__device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE> &wk, uint32_t slotAddr, uint32_t barAddr, int lane)
+__device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE> &wk, uint32_t slotAddr, uint32_t barAddr, int lane, uint64_t streamPolicy)
 {
     constexpr uint32_t kValBytes = static_cast<uint32_t>(slot_val_bytes(KCE));
     ChunkMeta m;
@@ -668,8 +686,13 @@ __device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE> &wk, uint32_t 
     }
     if (lane == 0 && b0) {
         mbar_expect_tx(barAddr, b0 + b1);
-        tma_bulk_g2s(slotAddr, src0, b0, barAddr);
-        tma_bulk_g2s(slotAddr + kValBytes, src1, b1, barAddr);
+        if (streamPolicy) {
+            tma_bulk_g2s_hint(slotAddr, src0, b0, barAddr, streamPolicy);
+            tma_bulk_g2s_hint(slotAddr + kValBytes, src1, b1, barAddr, streamPolicy);
+        } else {
+            tma_bulk_g2s(slotAddr, src0, b0, barAddr);
+            tma_bulk_g2s(slotAddr + kValBytes, src1, b1, barAddr);
+        }
     }
     if (++wk.ci == wk.nc) { /* last chunk of the slice: move on */
         m.flags |= 2;
@@ -757,8 +780,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     ChunkWalker<KCE> wk;
     wk.start(reinterpret_cast<const uint2 *>(a.slices) + part.z, a.blob, sub, kpp, warp, nw, part.w - part.z);
     ChunkMeta meta[2];
-    meta[0] = issue_chunk(wk, slot0, slotBar0, lane);
-    meta[1] = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane);
+    /* L2 priorities (a.l2hint): the matrix is read once per product -> evict-first; x is read
+     * again by every product -> evict-last, so that 600 MB of stream do not push it out */
+    const uint64_t streamPolicy = a.l2hint ? make_evict_first_policy() : 0ull;
+    meta[0] = issue_chunk(wk, slot0, slotBar0, lane, streamPolicy);
+    meta[1] = issue_chunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane, streamPolicy);
     uint32_t phases = 0; /* bit s = parity to wait for on slot s */
 
     /* multi-GPU, pushing warp: everything of the halo push that does not need x */
@@ -778,7 +804,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
             mbar_expect_tx(winBar, bulkBytes); /* arrival 1 of 2 */
             const char *src = reinterpret_cast<const char *>(a.x + g0);
             const uint32_t dst = smem_u32(win);
-            for (uint32_t off = 0; off < bulkBytes; off += 32768u) tma_bulk_g2s(dst + off, src + off, min(32768u, bulkBytes - off), winBar);
+            const uint32_t piece = a.winPiece;
+            if (a.l2hint) {
+                const uint64_t keep = make_evict_last_policy();
+                for (uint32_t off = 0; off < bulkBytes; off += piece) tma_bulk_g2s_hint(dst + off, src + off, min(piece, bulkBytes - off), winBar, keep);
+            } else {
+                for (uint32_t off = 0; off < bulkBytes; off += piece) tma_bulk_g2s(dst + off, src + off, min(piece, bulkBytes - off), winBar);
+            }
         } else if (tid == blockDim.x - 1) {
             if (len & 1) win[len - 1] = a.x[g0 + len - 1]; /* odd tail element */
             mbar_arrive(winBar);                           /* arrival 2 of 2 (releases the store) */
@@ -877,7 +909,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
             acc0 = acc1 = r0 = r1 = 0.0;
         }
         __syncwarp(); /* every lane is done with the slot before it is refilled */
-        const ChunkMeta mn = issue_chunk(wk, slot, bar, lane);
+        const ChunkMeta mn = issue_chunk(wk, slot, bar, lane, streamPolicy);
         if (s) meta[1] = mn; else meta[0] = mn;
         s ^= 1;
     }
