@@ -133,6 +133,35 @@ def build_matrix(grid, x=None):
     return m, lay, x, pl, time.time() - t0
 
 
+def gpu_comparisons(m, xr, y_ref, absAx):
+    """Other GPU implementations of the same product on the same device, outside the timed region
+    (reported rows): cuSPARSE generic-API CSR SpMV through spmvGeneric's library
+    (libehyb_cusparse.so, the reference's comparison path made to work).  Empty if not built."""
+    out = {}
+    path = ROOT / "ehyb_spmv_gpu_b200" / "lib" / "libehyb_cusparse.so"
+    if not path.exists():
+        return out
+    try:
+        lib = C.CDLL(str(path))
+        lib.ehyb_cusparse_last_error.restype = C.c_char_p
+        nnz = m.nnz
+        for alg in (1, 2):
+            us = C.c_float()
+            y = np.empty(m.n)
+            rc = lib.ehyb_cusparse_spmv(C.byref(m.c), xr.ctypes.data_as(C.POINTER(C.c_double)),
+                                        y.ctypes.data_as(C.POINTER(C.c_double)), 5, 50, alg, C.byref(us))
+            if rc != 0:
+                out["cusparse_csr_alg%d" % alg] = {"error": lib.ehyb_cusparse_last_error().decode()}
+                continue
+            out["cusparse_csr_alg%d" % alg] = {
+                "us_per_product": round(us.value, 2), "GFLOP/s": round(2.0 * nnz / (us.value * 1e3), 1),
+                "rows_outside_1e-12_gate": int(np.count_nonzero(~(np.abs(y - y_ref) <= 1e-12 * absAx))),
+                "what": "cusparseSpMV CSR fp64 (CUSPARSE_SPMV_CSR_ALG%d, preprocessed) on the same permuted matrix, same GPU" % alg}
+    except Exception as e:  # a comparison row must never take the bench down
+        out["error"] = repr(e)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -208,6 +237,8 @@ def run_ours(args):
     absAx = orc.csr_abs_spmv(a["rowIdx"], a["J"], a["V"], xr)
     gate_fail = int(np.count_nonzero(~(np.abs(s.get_y() - y_cpu) <= 1e-12 * absAx)))
 
+    comparisons = gpu_comparisons(m, xr, y_cpu, absAx)
+
     peaks, peak_src = measured_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # One product = `launches` kernels.  With a single launch per product the kernel's average
@@ -247,6 +278,7 @@ def run_ours(args):
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "parity": {"max_abs_err_vs_golden": err, "rows_outside_1e-12_gate": gate_fail},
+        "comparisons": comparisons,
     }
     for p in pin:
         lib.ehyb_host_free_pinned(p)

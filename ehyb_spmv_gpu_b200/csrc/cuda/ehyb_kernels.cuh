@@ -74,6 +74,7 @@ struct MainArgs {
     const int32_t *cacheCols; /* per-partition remainder cache lists (permuted columns) */
     int cacheCap;             /* shared-memory cache capacity in elements (>= longest list) */
     const int32_t *order;     /* CTA slot -> partition (NULL: identity) */
+    int dynamicDeal;          /* staged kernel: slices beyond the first nw are taken on demand (shared-memory counter) */
     int l2hint;               /* staged kernel: L2 eviction hints on the TMA copies (stream evict-first, x evict-last) */
     uint32_t winPiece;        /* staged kernel: bytes per bulk copy of the x window (multiple of 16) */
     unsigned long long *trace; /* development (EHYB_TRACE=1): 8 globaltimer stamps per CTA, else NULL */
@@ -575,7 +576,7 @@ __device__ __forceinline__ void fill_remainder_cache_warp(double *cache, const i
  * smem  = kStageHeader + align128((W+2)*8) + NW * kSlotsPerWarp * kSlotBytes
  * Slices are dealt statically: warp i of CTA `sub` takes local slices sub + kpp*(i + NW*j).
  */
-constexpr int kStageHeader = 512;  /* window mbarrier + 2*24 slot mbarriers */
+constexpr int kStageHeader = 512;  /* window + cache mbarriers, 2*24 slot mbarriers, slice counter (last 8 bytes) */
 constexpr int kSlotsPerWarp = 2;
 constexpr int kMaxStageWarps = 24;
 /* a slot holds one chunk: kc columns of one slice, ELL or remainder alike (kc*512 B of values
@@ -614,11 +615,12 @@ __device__ __forceinline__ int2 lds_s32x2(uint32_t addr)
  * bookkeeping, integer divisions included, rather than on the matrix entries). */
 template <int KCE>
 struct ChunkWalker {
-    const uint2 *descs;        /* descriptors of this warp's slices: descs[j * stride] */
+    const uint2 *descs;        /* descriptors of this CTA's slices: descs[q * kpp], q = 0..nq-1 */
     const unsigned char *blob;
     const unsigned char *base; /* current slice */
-    int stride;                /* kpp * NW: distance between consecutive slices of this warp */
-    int left;                  /* slices still to start after the current one */
+    int *counter;              /* shared-memory counter dealing the slices q >= nw (NULL: static deal) */
+    int kpp, sub, nq, nw;
+    int q, qnext;              /* current and next slice of this warp (index among the CTA's slices) */
     int t;                     /* current slice (local index in the partition) */
     int w, wr, nE, nc, ci;     /* current slice: widths, ELL chunks, all chunks, next chunk */
     uint2 dnext;               /* prefetched descriptor of the next slice */
@@ -634,18 +636,47 @@ struct ChunkWalker {
         ci = 0;
     }
 
-    __device__ __forceinline__ void start(const uint2 *partDescs, const unsigned char *blob_, int sub, int kpp, int warp, int nw, int nsl)
+    /* the slice after `cur` for this warp: the next one nobody has taken (dynamic: the rows of a
+     * partition are sorted by length, so slices come widest first and the deal is longest-job-
+     * first), or cur + nw (static) */
+    __device__ __forceinline__ int take_next(int cur, int lane)
+    {
+        if (counter == nullptr) return cur + nw;
+        int v = 0;
+        if (lane == 0) v = atomicAdd(counter, 1);
+        return __shfl_sync(0xffffffffu, v, 0);
+    }
+
+    __device__ __forceinline__ void start(const uint2 *partDescs, const unsigned char *blob_, int sub_, int kpp_, int warp, int nw_, int nsl,
+                                          int *counter_, int lane)
     {
         blob = blob_;
-        stride = kpp * nw;
-        t = sub + kpp * warp;
-        live = t < nsl;
-        descs = partDescs + t;
-        left = live ? (nsl - 1 - t) / stride : 0;
+        counter = counter_;
+        kpp = kpp_; sub = sub_; nw = nw_;
+        nq = nsl > sub ? (nsl - sub + kpp - 1) / kpp : 0;
+        descs = partDescs + sub;
+        q = warp; /* the first nw slices are dealt statically */
+        live = q < nq;
+        t = sub + kpp * q;
+        qnext = nq;
         dnext = make_uint2(0u, 0u);
         if (live) {
-            load_slice(__ldg(descs));
-            if (left > 0) dnext = __ldg(descs + stride);
+            load_slice(__ldg(descs + kpp * q));
+            qnext = take_next(q, lane);
+            if (qnext < nq) dnext = __ldg(descs + kpp * qnext);
+        }
+    }
+
+    __device__ __forceinline__ void advance(int lane)
+    {
+        if (qnext < nq) {
+            q = qnext;
+            t = sub + kpp * q;
+            load_slice(dnext);
+            qnext = take_next(q, lane);
+            if (qnext < nq) dnext = __ldg(descs + kpp * qnext);
+        } else {
+            live = false;
         }
     }
 };
@@ -696,15 +727,7 @@ __device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE> &wk, uint32_t 
     }
     if (++wk.ci == wk.nc) { /* last chunk of the slice: move on */
         m.flags |= 2;
-        if (wk.left > 0) {
-            wk.left -= 1;
-            wk.t += wk.stride;
-            wk.descs += wk.stride;
-            wk.load_slice(wk.dnext);
-            if (wk.left > 0) wk.dnext = __ldg(wk.descs + wk.stride);
-        } else {
-            wk.live = false;
-        }
+        wk.advance(lane);
     }
     return m;
 }
@@ -768,7 +791,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
      * up.  Its matrix stream (constant data) then overlaps this grid's tail; everything that
      * touches x or y comes after its own griddepcontrol.wait below. */
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    int *sliceCounter = reinterpret_cast<int *>(smem + kStageHeader - 8);
     if (tid == 0) {
+        *sliceCounter = nw; /* slices 0..nw-1 go to the warps statically, the rest on demand */
         mbar_init(winBar, 2);
         mbar_init(cacheBar, static_cast<uint32_t>(nFill));
         for (int i = 0; i < nw * kSlotsPerWarp; ++i) mbar_init(smem_u32(smem + 16) + i * 8u, 1);
@@ -778,7 +803,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
 
     /* the matrix stream does not depend on x, y or the previous grid: start it right away */
     ChunkWalker<KCE> wk;
-    wk.start(reinterpret_cast<const uint2 *>(a.slices) + part.z, a.blob, sub, kpp, warp, nw, part.w - part.z);
+    wk.start(reinterpret_cast<const uint2 *>(a.slices) + part.z, a.blob, sub, kpp, warp, nw, part.w - part.z,
+             a.dynamicDeal ? sliceCounter : nullptr, lane);
     ChunkMeta meta[2];
     /* L2 priorities (a.l2hint): the matrix is read once per product -> evict-first; x is read
      * again by every product -> evict-last, so that 600 MB of stream do not push it out */

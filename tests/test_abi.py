@@ -8,9 +8,14 @@ from ehyb_spmv_gpu_b200 import _lib
 INC = Path(__file__).resolve().parent.parent / "include"
 
 
-def declared_functions():
+CUSPARSE_HEADER = "ehyb_cusparse.h"  # its symbols live in libehyb_cusparse.so
+
+
+def declared_functions(only=None):
     names = set()
     for h in INC.glob("*.h"):
+        if (h.name == CUSPARSE_HEADER) != (only == CUSPARSE_HEADER):
+            continue
         text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
         text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
         text = re.sub(r"static inline[^{]*\{.*?\n\}", "", text, flags=re.S)
@@ -30,6 +35,17 @@ def test_every_declared_symbol_is_exported(lib):
     missing = sorted(s for s in decl if not hasattr(lib, s))
     assert not missing, missing
     assert set(_lib.EXPORTS) <= decl
+
+
+def test_comparison_library_exports_its_header():
+    """libehyb_cusparse.so (spmvGeneric, the reference's cuSPARSE comparison) loads on a box
+    without a GPU and exports what include/ehyb_cusparse.h declares."""
+    path = _lib.PKG / "lib" / "libehyb_cusparse.so"
+    assert path.exists(), "build it with __graft_entry__.build()"
+    lib = C.CDLL(str(path))
+    decl = declared_functions(only=CUSPARSE_HEADER)
+    assert {"spmvGeneric", "ehyb_cusparse_spmv"} <= decl
+    assert not [s for s in decl if not hasattr(lib, s)]
 
 
 def test_struct_layouts_match_the_reference(ref):
