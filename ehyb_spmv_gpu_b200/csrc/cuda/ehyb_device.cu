@@ -51,7 +51,7 @@ struct ehyb_handle {
     double *x, *y;       /* session vectors */
     double *xb[2], *yb[2]; /* double buffers of the pipelined host path (lazy) */
     cudaEvent_t evX[2], evK[2], evY[2], ev0, ev1;
-    int use_graph, l2_persist, pdl, dbgSkip, haloInOverflow, l2hint, winPiece, dynamicDeal;
+    int use_graph, l2_persist, pdl, dbgSkip, haloInOverflow, l2hint, winPiece, dynamicDeal, ovfUnroll, ovfLateTrigger, pdlOvf;
     cudaGraphExec_t gexec;
     const double *gx;
     double *gy;
@@ -255,6 +255,9 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     h->l2hint = env_int("EHYB_L2_HINT", -1);
     if (h->l2hint < 0) h->l2hint = (double)v->blobBytes + 16.0 * (double)v->n > 0.75 * (double)prop.l2CacheSize;
     h->dynamicDeal = env_int("EHYB_DYNAMIC_DEAL", 1);
+    h->ovfUnroll = env_int("EHYB_OVF_UNROLL", 4);
+    h->ovfLateTrigger = env_int("EHYB_OVF_LATE_TRIGGER", 1);
+    h->pdlOvf = env_int("EHYB_PDL_OVF", 1); /* launch the overflow kernel programmatically behind the main kernel */
     h->winPiece = env_int("EHYB_WIN_PIECE", 32768) & ~15;
     if (h->winPiece < 16) h->winPiece = 32768;
     if (env_int("EHYB_TRACE", 0)) {
@@ -381,10 +384,14 @@ static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaS
     o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = x_d; o.y = y_d;
     o.perWarp = overflow_per_warp(h);
     o.n = (int)h->n;
+    o.lateTrigger = h->ovfLateTrigger;
     o.peer = pa ? *pa : no_peer(h, x_d);
     const int64_t warps = (h->nOvf + o.perWarp - 1) / o.perWarp;
     const unsigned blocks = (unsigned)((warps + 7) / 8);
-    if (h->pdl) {
+    /* Programmatic launch behind the main kernel pays for short lists (halo-sized: the launch gap
+     * disappears), but with a grid of thousands of CTAs it costs 65 us per product (R-MAT scale
+     * 20: 211 us vs 144, profiles/r1_notes.md): only for grids of at most 8 CTAs per SM. */
+    if (h->pdl && h->pdlOvf && blocks <= 8u * (unsigned)h->smCount) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(blocks);
         cfg.blockDim = dim3(256);
@@ -394,9 +401,11 @@ static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaS
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, ehyb_overflow_kernel, o));
+        if (h->ovfUnroll == 1) CU(cudaLaunchKernelEx(&cfg, ehyb_overflow_kernel<1>, o));
+        else CU(cudaLaunchKernelEx(&cfg, ehyb_overflow_kernel<4>, o));
     } else {
-        ehyb_overflow_kernel<<<blocks, 256, 0, s>>>(o);
+        if (h->ovfUnroll == 1) ehyb_overflow_kernel<1><<<blocks, 256, 0, s>>>(o);
+        else ehyb_overflow_kernel<4><<<blocks, 256, 0, s>>>(o);
         CU(cudaGetLastError());
     }
     return EHYB_OK;

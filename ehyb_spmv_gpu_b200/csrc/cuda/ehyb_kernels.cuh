@@ -89,6 +89,7 @@ struct OverflowArgs {
     double *y;
     int perWarp; /* consecutive entries per warp, a multiple of 32 */
     int n;       /* columns >= n are halo columns: peer.xh[c - n] */
+    int lateTrigger; /* release the dependent grid at the end of the CTA instead of the top */
     PeerArgs peer;
 };
 
@@ -954,56 +955,74 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
  * group of 32 is carried in registers instead of being flushed.
  */
 constexpr int kOvfPerWarp = 32 * 8;
-
+/* kOvfUnroll = groups of 32 entries whose loads and gathers are in flight together */
+template <int kOvfUnroll>
 __global__ void __launch_bounds__(256) ehyb_overflow_kernel(const OverflowArgs a)
 {
-    /* let the next product's main kernel start its matrix stream while this one runs (it waits
-     * for this grid's completion before it touches x or y); this grid itself is launched
-     * programmatically behind the main kernel and waits here for its y */
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    /* This grid is launched programmatically behind the main kernel and waits here for its y.
+     * The next product's main kernel is released only when this CTA is done (trigger at the end,
+     * a.lateTrigger): released at the top, its 768-thread CTAs take over the SMs while most of
+     * this grid's CTAs have not been scheduled yet and then sit waiting for them (measured:
+     * 211 us per product instead of 144 on R-MAT scale 20). */
+    if (!a.lateTrigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int64_t warpId = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t begin = warpId * a.perWarp;
-    if (begin >= a.count) return;
+    if (begin >= a.count) return; /* (an exited CTA counts as triggered) */
     const int64_t end = min(begin + a.perWarp, a.count);
     int carryRow = -1;
     double carry = 0.0;
     bool haloReady = false;
-    for (int64_t base = begin; base < end; base += 32) {
-        const int64_t i = base + lane;
-        const bool live = i < end;
-        int r = -2 - lane; /* dead lanes: unique rows, never merged, never written */
-        double prod = 0.0;
-        int c = 0;
-        if (live) {
-            r = __ldg(a.row + i);
-            c = __ldg(a.col + i);
+    for (int64_t base = begin; base < end; base += 32 * kOvfUnroll) {
+        /* all the streaming loads of kOvfUnroll groups first, then all the x gathers: a warp keeps
+         * 4 x 32 independent gathers in flight instead of 32 (the list is L2-latency bound) */
+        int r[kOvfUnroll], c[kOvfUnroll];
+        double v[kOvfUnroll], xv[kOvfUnroll];
+        bool anyHalo = false;
+#pragma unroll
+        for (int u = 0; u < kOvfUnroll; ++u) {
+            const int64_t i = base + 32 * u + lane;
+            const bool live = i < end;
+            r[u] = live ? __ldg(a.row + i) : -2 - lane; /* dead lanes: unique rows, never merged, never written */
+            c[u] = live ? __ldg(a.col + i) : 0;
+            v[u] = live ? __ldg(a.val + i) : 0.0;
+            anyHalo = anyHalo || c[u] >= a.n;
         }
-        if (a.peer.flags != nullptr && !haloReady && __any_sync(0xffffffffu, c >= a.n)) {
+        if (a.peer.flags != nullptr && !haloReady && __any_sync(0xffffffffu, anyHalo)) {
             /* first halo column of this warp: wait (once) for the neighbours' push */
             peer_wait(a.peer.flags, a.peer.recvMask, a.peer.nranks, a.peer.peerPushCtas, false, a.peer.epoch, a.peer.timeoutNs, a.peer.status);
             haloReady = true;
         }
-        if (live) prod = __ldg(a.val + i) * (c < a.n ? ld_gather_f64(a.x + c) : ld_halo_f64(a.peer, a.n, c));
-        if (lane == 0 && r == carryRow) prod += carry; /* continue the carried segment */
-        const int flushRow = (lane == 0 && carryRow >= 0 && r != carryRow) ? carryRow : -1;
-        if (flushRow >= 0) atomicAdd(a.y + flushRow, carry);
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, prod, off);
-            const int rr = __shfl_up_sync(0xffffffffu, r, off);
-            if (lane >= off && rr == r) prod += t;
+        for (int u = 0; u < kOvfUnroll; ++u) xv[u] = c[u] < a.n ? ld_gather_f64(a.x + c[u]) : ld_halo_f64(a.peer, a.n, c[u]);
+#pragma unroll
+        for (int u = 0; u < kOvfUnroll; ++u) {
+            const int64_t gbase = base + 32 * u;
+            if (gbase >= end) break; /* warp-uniform */
+            const bool live = gbase + lane < end;
+            const int row = r[u];
+            double prod = v[u] * xv[u];
+            if (lane == 0 && row == carryRow) prod += carry; /* continue the carried segment */
+            const int flushRow = (lane == 0 && carryRow >= 0 && row != carryRow) ? carryRow : -1;
+            if (flushRow >= 0) atomicAdd(a.y + flushRow, carry);
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, prod, off);
+                const int rr = __shfl_up_sync(0xffffffffu, row, off);
+                if (lane >= off && rr == row) prod += t;
+            }
+            const int rnext = __shfl_down_sync(0xffffffffu, row, 1);
+            const bool tailOfSeg = live && (lane == 31 || rnext != row);
+            /* the segment ending in lane 31 may continue in the next group: carry it */
+            const bool carries = lane == 31 && live && gbase + 32 < end;
+            if (tailOfSeg && !carries) atomicAdd(a.y + row, prod);
+            carryRow = __shfl_sync(0xffffffffu, carries ? row : -1, 31);
+            carry = __shfl_sync(0xffffffffu, prod, 31);
         }
-        const int rnext = __shfl_down_sync(0xffffffffu, r, 1);
-        const bool tailOfSeg = live && (lane == 31 || rnext != r);
-        /* the segment ending in lane 31 may continue in the next group: carry it */
-        const bool carries = lane == 31 && live && base + 32 < end;
-        if (tailOfSeg && !carries) atomicAdd(a.y + r, prod);
-        carryRow = __shfl_sync(0xffffffffu, carries ? r : -1, 31);
-        carry = __shfl_sync(0xffffffffu, prod, 31);
     }
     if (lane == 0 && carryRow >= 0) atomicAdd(a.y + carryRow, carry);
+    if (a.lateTrigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 } /* namespace ehyb */

@@ -44,6 +44,7 @@
 #include "kernel.h"
 
 #define SR EHYB_SLICE_ROWS
+#define EHYB_BALANCE_WARPS 24 /* warps of a staged-kernel CTA (kMaxStageWarps) */
 
 struct ehyb_layout {
     ehyb_layout_view v;
@@ -144,12 +145,13 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     int rc = EHYB_OK;
     int64_t *sliceOff = NULL;
     int32_t **cacheList = (int32_t **)calloc((size_t)P, sizeof(int32_t *)); /* per partition, ascending */
+    int32_t *wrCap = (int32_t *)malloc((size_t)P * sizeof(int32_t));          /* per partition: widest in-slice remainder */
     L->parts = (ehyb_part_desc *)calloc((size_t)P, sizeof(ehyb_part_desc));
     L->rowEll = (int32_t *)calloc((size_t)n, sizeof(int32_t));
     L->rowRemIn = (int32_t *)calloc((size_t)n, sizeof(int32_t));
     L->rowCached = (int32_t *)calloc((size_t)n, sizeof(int32_t));
     L->ovfPtr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
-    if (!cacheList || !L->parts || !L->rowEll || !L->rowRemIn || !L->rowCached || !L->ovfPtr) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
+    if (!cacheList || !wrCap || !L->parts || !L->rowEll || !L->rowRemIn || !L->rowCached || !L->ovfPtr) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
     /* distributed blocks: an entry whose column is in the halo [n, ncols) arrives with the
      * exchange, after the main kernel has started: it is never cached, always overflow */
     const int haloOvf = opts->halo_in_overflow && ncols > n;
@@ -177,6 +179,28 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
         const int64_t winEnd = (int64_t)ps + W < n ? (int64_t)ps + W : n;
         int firstReg = ps, scanning = 1;
         int64_t nExt = 0;
+        /* Long-row limit of this partition.  The reference's rule is a constant (512 in-window
+         * entries, kernel.h:26); a slice is walked by ONE warp, chunk after chunk, so a slice much
+         * wider than a warp's fair share of the partition serialises the CTA (R-MAT: 106 us for
+         * 2 M entries).  The limit is therefore also bounded by twice the columns a warp would
+         * own if the partition's in-window entries were spread evenly over EHYB_BALANCE_WARPS
+         * warps (never below 32).  Regular matrices are unaffected: a 27-point stencil partition
+         * holds ~110 columns per warp and no row has more than 27 entries. */
+        int partThr = longThr;
+        int64_t fairCols = -1;
+        wrCap[p] = 65535;
+        if (opts->long_row_threshold <= 0) {
+            int64_t inWin = 0;
+            for (int r = ps; r < pe; ++r) {
+                if (r - ps >= W) break;
+                for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) inWin += (col[e] >= ps && col[e] < winEnd);
+            }
+            const int64_t fair = inWin / SR / EHYB_BALANCE_WARPS; /* columns per warp, evenly spread */
+            int64_t lim = 2 * fair;
+            if (lim < 32) lim = 32;
+            if (lim < partThr) partThr = (int)lim;
+            fairCols = fair;
+        }
         for (int r = ps; r < pe; ++r) {
             int ell = 0;
             const int inWindowRow = r - ps < W; /* rows beyond the window are remainder as a whole (convert.c:128-134) */
@@ -185,7 +209,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                 if (c < 0 || c >= ncols) bad = 1;
                 ell += (inWindowRow && c >= ps && c < winEnd);
             }
-            if (scanning && ell > longThr) { /* long rows sit at the head of the partition */
+            if (scanning && ell > partThr) { /* long rows sit at the head of the partition */
                 firstReg = r + 1;
                 L->rowEll[r] = -1;
                 continue;
@@ -250,6 +274,15 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
             }
             L->rowCached[r] = cached;
         }
+        /* the same balance rule for the in-slice remainder width: at most twice a warp's fair
+         * share of all the partition's columns (ELL + cached remainder), never below 32 */
+        if (fairCols >= 0) {
+            int64_t sumCached = 0;
+            for (int r = firstReg; r < pe; ++r) sumCached += L->rowCached[r];
+            int64_t lim = 2 * (fairCols + sumCached / SR / EHYB_BALANCE_WARPS);
+            if (lim < 32) lim = 32;
+            if (lim < wrCap[p]) wrCap[p] = (int32_t)lim;
+        }
     }
     if (bad) { rc = bad == 2 ? ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory") : ehyb_fail(EHYB_ERR_ARG, "layout: a column index is outside [0, ncols)"); goto fail; }
     int64_t cacheTotal = 0;
@@ -286,11 +319,15 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                     ovfAlways += len - L->rowEll[r] - L->rowCached[r];
                 }
                 qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
-                const int wrA = m >= 1 ? rem[0] : 0, wrB = m >= SR / 2 ? rem[SR / 2 - 1] : 0;
+                int wrA = m >= 1 ? rem[0] : 0, wrB = m >= SR / 2 ? rem[SR / 2 - 1] : 0;
+                if (wrA > wrCap[p]) wrA = wrCap[p];
+                if (wrB > wrCap[p]) wrB = wrCap[p];
                 cost[0] += 640.0 * wrA;
                 cost[1] += 640.0 * wrB;
-                for (int i = 0; i < m; ++i)
+                for (int i = 0; i < m; ++i) {
+                    if (rem[i] > wrA) cost[0] += 16.0 * (rem[i] - wrA);
                     if (rem[i] > wrB) { cost[1] += 16.0 * (rem[i] - wrB); ovfB += rem[i] - wrB; }
+                }
             }
         }
         if (ovfB > 0 && ovfAlways == 0) cost[1] += 30e6; /* the overflow launch would exist only because of this choice */
@@ -311,7 +348,8 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                 rem[m++] = L->rowCached[r] > 65535 ? 65535 : L->rowCached[r];
             }
             qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
-            const int wr = m >= need ? rem[need - 1] : 0;
+            int wr = m >= need ? rem[need - 1] : 0;
+            if (wr > wrCap[p]) wr = wrCap[p];
             if (w > 65535) bad = 1;
             L->slices[s].w = (uint16_t)w;
             L->slices[s].wr = (uint16_t)wr;
@@ -416,6 +454,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     if (nnzEll + nnzRemIn + nnzOvf != v->nnz) { rc = ehyb_fail(EHYB_ERR_ARG, "layout: entry count mismatch"); goto fail; }
     for (int p = 0; p < P; ++p) free(cacheList[p]);
     free(cacheList);
+    free(wrCap);
     free(sliceOff);
     *out = L;
     return EHYB_OK;
@@ -423,6 +462,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
 fail:
     if (cacheList) for (int p = 0; p < P; ++p) free(cacheList[p]);
     free(cacheList);
+    free(wrCap);
     free(sliceOff);
     ehyb_layout_free(L);
     return rc;

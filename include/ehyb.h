@@ -124,7 +124,9 @@ typedef struct ehyb_layout_opts {
                                0 = keep every remainder entry in its slice; < 0 = choose between 0
                                and 0.5 by stored bytes (the default of spmvGPuEHYB) */
     int long_row_threshold; /* rows at a partition head with more in-window entries than this go
-                               whole to the overflow list; 0 = 512 (reference threadLongVec) */
+                               whole to the overflow list; 0 = min(512 (reference threadLongVec),
+                               max(32, twice a warp's fair share of the partition's columns)): a
+                               slice is walked by one warp, see layout.c */
     int64_t ncols;          /* columns of the local operator (n + halo); 0 = n */
     int halo_in_overflow;   /* entries with a halo column (>= n) always go to the overflow list,
                                which the multi-GPU product runs after the halo exchange */

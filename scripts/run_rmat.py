@@ -15,6 +15,7 @@ ap.add_argument("--scale", type=int, default=20)
 ap.add_argument("--edge-factor", type=int, default=16)
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--blocks", action="store_true", help="contiguous-block partition instead of mt-metis")
+ap.add_argument("--no-graph", action="store_true")
 a = ap.parse_args()
 t = time.time()
 n, fi, fj, fv = api.gen_rmat(a.scale, a.edge_factor, seed=1, add_diagonal=False)
@@ -33,7 +34,7 @@ t = time.time()
 lay = api.Layout(m)
 st = lay.stats()
 print(f"layout {time.time()-t:.1f}s", {k: st[k] for k in ("nSlices", "nnzEll", "nnzRemInSlice", "nnzOverflow", "padEll", "padRem", "nLongRows", "cacheMax", "algBytes", "formatBytes")}, flush=True)
-s = api.Session(lay)
+s = api.Session(lay, use_graph=not a.no_graph)
 xr = m.vector_reorder(x)
 y = m.vector_recover(s.spmv_host(xr))
 orc = O.Oracle()
@@ -43,8 +44,19 @@ absAx = m.vector_recover(orc.csr_abs_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
 bad = int(np.count_nonzero(~(np.abs(y - y_ref) <= 1e-12 * absAx)))
 print("rows outside the 1e-12 gate:", bad, " max abs err", float(np.abs(y - y_ref).max()), " vs golden", float(np.abs(y - m.y_golden).max()))
 s.set_x(xr)
-ms = s.time_spmv(5, a.iters)
+ms, kms = s.time_spmv(5, a.iters, kernel_only=True)
 per = ms / a.iters
+print(f"main kernel alone {kms/a.iters*1e3:.1f} us (isolated launches)")
 print(f"{per*1e3:.1f} us per product, {2*st['nnz']/(per*1e6):.1f} GFLOP/s, {st['algBytes']/(per*1e6):.1f} GB/s algorithmic, launches/product {s.launches_per_spmv()}")
+# cuSPARSE CSR on the same permuted matrix, same GPU (comparison row)
+import ctypes as C
+cus = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ehyb_spmv_gpu_b200", "lib", "libehyb_cusparse.so")
+if os.path.exists(cus):
+    lib = C.CDLL(cus)
+    for alg in (1, 2):
+        us = C.c_float(); yc = np.empty(n)
+        rc = lib.ehyb_cusparse_spmv(C.byref(m.c), xr.ctypes.data_as(C.POINTER(C.c_double)), yc.ctypes.data_as(C.POINTER(C.c_double)), 3, 20, alg, C.byref(us))
+        if rc == 0:
+            print(f"cuSPARSE CSR ALG{alg}: {us.value:.1f} us per product, {2*st['nnz']/(us.value*1e3):.1f} GFLOP/s")
 sec, _ = orc.csr_spmv_timed(arr["rowIdx"], arr["J"], arr["V"], xr, 1, 5)
 print(f"CPU CSR ({orc.num_threads()} threads): {2*st['nnz']*5/sec/1e9:.2f} GFLOP/s")
