@@ -63,7 +63,8 @@ class Plan(C.Structure):
 
 class LayoutOpts(C.Structure):
     _fields_ = [("W", C.c_int), ("ctasPerPart", C.c_int), ("er_fill", C.c_double),
-                ("long_row_threshold", C.c_int), ("ncols", C.c_int64), ("halo_in_overflow", C.c_int), ("cache_cap", C.c_int)]
+                ("long_row_threshold", C.c_int), ("ncols", C.c_int64), ("halo_in_overflow", C.c_int), ("cache_cap", C.c_int),
+                ("min_coverage", C.c_double)]
 
 
 class SliceDesc(C.Structure):

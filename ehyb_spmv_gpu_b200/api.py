@@ -250,10 +250,11 @@ class Layout:
     """ehyb_layout: the Blackwell-tuned layout on the host."""
 
     def __init__(self, m: CooMatrix, W: int = 0, ctasPerPart: int = 0, er_fill: float = -1.0,
-                 long_row_threshold: int = 0, ncols: int = 0, halo_in_overflow: bool = False, cache_cap: int = 0):
+                 long_row_threshold: int = 0, ncols: int = 0, halo_in_overflow: bool = False, cache_cap: int = 0,
+                 min_coverage: float = 0.0):
         self.lib = L.load()
         self.h = C.c_void_p()
-        o = LayoutOpts(W, ctasPerPart, er_fill, long_row_threshold, ncols, int(halo_in_overflow), cache_cap)
+        o = LayoutOpts(W, ctasPerPart, er_fill, long_row_threshold, ncols, int(halo_in_overflow), cache_cap, min_coverage)
         check(self.lib, self.lib.ehyb_layout_build(C.byref(m.c), C.byref(o), C.byref(self.h)), "ehyb_layout_build")
         self.v = LayoutView()
         check(self.lib, self.lib.ehyb_layout_get(self.h, C.byref(self.v)), "ehyb_layout_get")

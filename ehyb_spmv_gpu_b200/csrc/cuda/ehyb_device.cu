@@ -51,7 +51,7 @@ struct ehyb_handle {
     double *x, *y;       /* session vectors */
     double *xb[2], *yb[2]; /* double buffers of the pipelined host path (lazy) */
     cudaEvent_t evX[2], evK[2], evY[2], ev0, ev1;
-    int use_graph, l2_persist, pdl, dbgSkip, haloInOverflow, l2hint, winPiece, dynamicDeal, ovfUnroll, ovfLateTrigger, pdlOvf;
+    int use_graph, l2_persist, pdl, dbgSkip, haloInOverflow, l2hint, winPiece, dynamicDeal, ovfUnroll, ovfLateTrigger, pdlOvf, skipMain;
     cudaGraphExec_t gexec;
     const double *gx;
     double *gy;
@@ -249,6 +249,9 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     h->pdl = env_int("EHYB_PDL", 1);
     h->dbgSkip = env_int("EHYB_DEBUG_SKIP", 0); /* development: timing experiments without the arithmetic */
     h->haloInOverflow = v->haloInOverflow;
+    /* nothing lives in slices (layout.c: coverage below min_coverage, everything in the COO list):
+     * the product is a memset of y + the overflow kernel */
+    h->skipMain = v->nnz > 0 && v->nnzEll + v->nnzRemInSlice == 0 && env_int("EHYB_SKIP_EMPTY_MAIN", 1);
     /* L2 eviction hints on the TMA copies: evict-first for the matrix stream and evict-last for x
      * when the matrix is larger than L2 (it would push x out every product: 100.8 -> 95.7 us at
      * config 2); none when matrix + vectors fit L2 and simply stay there (config 1: 60 MB) */
@@ -342,6 +345,10 @@ static MainArgs main_args(const ehyb_handle *h, const double *x_d, double *y_d, 
 /* the launches of one product, on `s` */
 static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s, const PeerArgs *pa)
 {
+    if (h->skipMain && pa == NULL) { /* (a peer-memory product needs the kernel: it carries the halo push) */
+        CU(cudaMemsetAsync(y_d, 0, sizeof(double) * (size_t)h->n, s));
+        return EHYB_OK;
+    }
     const MainArgs a = main_args(h, x_d, y_d, pa);
     main_kernel_t k = main_kernel_of(h);
     if (h->kernel == EHYB_KERNEL_STAGED && h->pdl) {
@@ -417,7 +424,7 @@ static int launch_product(ehyb_handle *h, const double *x_d, double *y_d, cudaSt
     return rc ? rc : launch_overflow(h, x_d, y_d, s, NULL);
 }
 
-extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h) { return h ? (h->nOvf > 0 ? 2 : 1) : 0; }
+extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h) { return h ? (h->nOvf > 0 ? 2 : 1) - (h->skipMain ? 1 : 0) : 0; }
 
 extern "C" int ehyb_spmv(ehyb_handle *h, const double *x_d, double *y_d)
 {
@@ -557,7 +564,8 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
         for (int i = 0; i < 2 * iters; ++i) cudaEventCreate(&ev[i]);
         for (int i = 0; i < iters; ++i) {
             cudaEventRecord(ev[2 * i], h->stream);
-            k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, h->stream>>>(a);
+            if (h->skipMain) cudaMemsetAsync(h->y, 0, sizeof(double) * (size_t)h->n, h->stream);
+            else k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, h->stream>>>(a);
             cudaEventRecord(ev[2 * i + 1], h->stream);
             launch_overflow(h, h->x, h->y, h->stream, NULL);
         }

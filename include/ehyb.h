@@ -134,9 +134,13 @@ typedef struct ehyb_layout_opts {
                                cached per partition (0 = what fits a B200 CTA next to the window
                                and ~100 KB of staging, at least 4096; < 0 = none: all remainder
                                entries go to the overflow list) */
+    double min_coverage;    /* if fewer than this fraction of the entries would live in slices
+                               (window + remainder cache), every entry goes to the overflow list
+                               and the product is memset + overflow kernel; 0 = 0.2, < 0 = never */
 } ehyb_layout_opts;
 
 #define EHYB_DEFAULT_CACHE_CAP 4096
+#define EHYB_DEFAULT_MIN_COVERAGE 0.2
 
 typedef struct ehyb_slice_desc {
     uint32_t off256; /* byte offset of the slice in the blob / 256 */

@@ -109,3 +109,41 @@ def test_timed_loop_and_batch(orc):
     assert np.array_equal(ys[0], y1)
     assert s.launches_per_spmv() in (1, 2)
     s.free(); lay.free(); m.free()
+
+
+@pytest.mark.parametrize("min_coverage,partition", [(0.9, "blocks"), (-1.0, "blocks"), (-1.0, "metis")])
+def test_power_law_matrix_general_path(orc, min_coverage, partition):
+    """BASELINE.json config 4 in small: R-MAT through the general (unsymmetric) path.  The
+    reference cannot run this input at all; the bar is the accuracy gate
+    against the CPU CSR product.  Coverage below min_coverage (default 20 %, which scale >= 20
+    falls under; 90 % here to force it on a small matrix) -> every entry in the COO list, memset +
+    overflow kernel; min_coverage < 0 keeps the slices (long rows by the work-based limit,
+    remainder cache, overflow for the rest)."""
+    n, fi, fj, fv = api.gen_rmat(13, 16, seed=3, add_diagonal=False)
+    x = util.x_random(n, 7)
+    m = api.CooMatrix.from_general(n, fi, fj, fv, x)
+    pl = api.plan(n)
+    m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
+    if partition == "metis":
+        m.reorder()
+    else:
+        m.reorder_with_partition((np.arange(n, dtype=np.int64) * pl.nParts // n).astype(np.uint32))
+    lay = api.Layout(m, min_coverage=min_coverage)
+    st = lay.stats()
+    if min_coverage > 0:
+        assert st["nnzOverflow"] == st["nnz"] and st["blobBytes"] == 0
+    else:
+        assert st["nnzEll"] + st["nnzRemInSlice"] > 0 and st["nLongRows"] > 0
+    s = api.Session(lay)
+    assert s.launches_per_spmv() == (1 if min_coverage > 0 else 2)
+    a = m.arrays()
+    for seed in (7, 8):
+        xs = util.x_random(n, seed)
+        xr = m.vector_reorder(xs)
+        y = s.spmv_host(xr)
+        util.assert_within_gate(y, orc.csr_spmv(a["rowIdx"], a["J"], a["V"], xr), orc.csr_abs_spmv(a["rowIdx"], a["J"], a["V"], xr))
+    s.set_x(m.vector_reorder(x))
+    ms, kms = s.time_spmv(2, 5, kernel_only=True)
+    assert ms > 0
+    util.assert_within_gate(m.vector_recover(s.get_y()), m.y_golden, m.vector_recover(orc.csr_abs_spmv(a["rowIdx"], a["J"], a["V"], m.vector_reorder(x))))
+    s.free(); lay.free(); m.free()

@@ -127,9 +127,23 @@ def test_long_rows_and_empty_rows(orc):
     a = m.arrays()
     e = m.coo2ehyb()
     assert e["nLongVec"] >= 1
-    lay = api.Layout(m)
+    # the reference's constant rule (512 in-window entries, kernel.h:26), pinned explicitly ...
+    lay = api.Layout(m, long_row_threshold=512, min_coverage=-1)
     st = lay.stats()
     assert st["nLongRows"] == e["nLongVec"] and st["nnzEll"] + st["nnzRemInSlice"] + st["nnzOverflow"] == st["nnz"]
+    # ... and the default: the limit also follows a warp's fair share of the partition (a slice is
+    # walked by one warp), so at least the same rows are long and the slices are narrower
+    lay_d = api.Layout(m, min_coverage=-1)
+    st_d = lay_d.stats()
+    assert st_d["nLongRows"] >= st["nLongRows"] and st_d["nnzEll"] + st_d["nnzRemInSlice"] + st_d["nnzOverflow"] == st["nnz"]
+    assert int(lay_d.raw()["slices"]["w"].max(initial=0)) <= int(lay.raw()["slices"]["w"].max(initial=0))
+    assert np.allclose(util.layout_spmv(lay_d.raw(), m.vector_reorder(x)), orc.csr_spmv(a["rowIdx"], a["J"], a["V"], m.vector_reorder(x)), rtol=0, atol=1e-12)
+    # coverage rule: an R-MAT-like matrix keeps almost nothing in slices -> everything in the COO list
+    lay_c = api.Layout(m, min_coverage=0.99)
+    st_c = lay_c.stats()
+    assert st_c["nnzOverflow"] == st["nnz"] and st_c["nnzEll"] == 0 and st_c["blobBytes"] == 0
+    assert np.allclose(util.layout_spmv(lay_c.raw(), m.vector_reorder(x)), orc.csr_spmv(a["rowIdx"], a["J"], a["V"], m.vector_reorder(x)), rtol=0, atol=1e-12)
+    lay_d.free(); lay_c.free()
     # CPU check of the reference-layout arrays through the oracle's emulation (long rows included)
     r = dict(rowIdx=a["rowIdx"], J=a["J"], V=a["V"])
     xr = m.vector_reorder(x)
