@@ -74,6 +74,7 @@ struct MainArgs {
     const int32_t *cacheCols; /* per-partition remainder cache lists (permuted columns) */
     int cacheCap;             /* shared-memory cache capacity in elements (>= longest list) */
     const int32_t *order;     /* CTA slot -> partition (NULL: identity) */
+    int prologueBarrier;      /* staged kernel, experiments: CTA barrier after window + cache staging */
     int dynamicDeal;          /* staged kernel: slices beyond the first nw are taken on demand (shared-memory counter) */
     int l2hint;               /* staged kernel: L2 eviction hints on the TMA copies (stream evict-first, x evict-last) */
     uint32_t winPiece;        /* staged kernel: bytes per bulk copy of the x window (multiple of 16) */
@@ -857,6 +858,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
             if (lane == 0) mbar_arrive(cacheBar);
         }
         while (!mbar_try_wait(winBar, 0)) { }
+        if (a.prologueBarrier) { /* (experiment switch: the classic CTA barrier behind the staging) */
+            __syncthreads();
+            cacheReady = true;
+        }
     } else {
         /* x not 16-byte aligned: plain copies and a CTA barrier */
         for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
