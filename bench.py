@@ -35,6 +35,14 @@ os.environ.setdefault("EHYB_MTMETIS_BIN", str(ROOT / "bin" / "ehyb_mtmetis"))
 
 GRID = (128, 128, 128)  # BASELINE.json configs[1]
 WORKLOAD = "3D 27-point stencil 128^3 (n 2097152, nnz 55742968) fp64, EHYB, per GPU"
+# Other shapes (not the driver's default): EHYB_BENCH_GRID=NXxNYxNZ sets the grid; with
+# EHYB_BENCH_SCALING=strong that grid is the GLOBAL one and rank r owns z-slab r of NZ/N planes
+# (BASELINE.json configs[4], the sharded big stencil), else it is the per-GPU grid (weak).
+if os.environ.get("EHYB_BENCH_GRID"):
+    GRID = tuple(int(v) for v in os.environ["EHYB_BENCH_GRID"].lower().split("x"))
+    WORKLOAD = "3D 27-point stencil %dx%dx%d fp64, EHYB, %s" % (
+        GRID + ("global grid (strong scaling)" if os.environ.get("EHYB_BENCH_SCALING") == "strong" else "per GPU",))
+STRONG = os.environ.get("EHYB_BENCH_SCALING") == "strong"
 
 
 def measured_peaks():
@@ -182,7 +190,12 @@ def run_ours(args):
 
     if world > 1:
         from ehyb_spmv_gpu_b200 import multigpu
-        return multigpu.bench(args, rank, world, local, GRID, WORKLOAD)
+        grid = GRID
+        if STRONG:
+            if GRID[2] % world:
+                raise SystemExit("bench.py: strong scaling needs NZ divisible by the number of GPUs")
+            grid = (GRID[0], GRID[1], GRID[2] // world)
+        return multigpu.bench(args, rank, world, local, grid, WORKLOAD, "strong" if STRONG else "weak")
 
     with stdout_to_stderr():
         m, lay, x, pl, t_prep = build_matrix(GRID)
@@ -257,7 +270,7 @@ def run_ours(args):
     out = {
         "metric": "fp64 SpMV GFLOP/s (2*nnz/t), EHYB format", "value": round(gflops, 2), "unit": "GFLOP/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 6),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if STRONG else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "grid": list(GRID), "n": n, "nnz": st["nnz"],
                    "partitions": st["nParts"], "window": st["W"], "ctas_per_partition": st["ctasPerPart"],
                    "slices": st["nSlices"], "nnz_ell": st["nnzEll"], "nnz_remainder_in_slice": st["nnzRemInSlice"],

@@ -99,7 +99,7 @@ class SessionOpts(C.Structure):
 # the header text)
 EXPORTS = [
     # spmv.h / kernel.h / convert.h / reordering.h (the reference's entry points)
-    "spmvGPuEHYB", "matrixVectorEHYB", "matrixVectorEHYB_small", "COO2EHYB", "EHYBfreeHost",
+    "spmvGPuEHYB", "spmvGPuEHYB_layout", "matrixVectorEHYB", "matrixVectorEHYB_small", "COO2EHYB", "EHYBfreeHost",
     "matrixReorder", "matrixReorder_unsym", "vectorReorder", "vectorRecover",
     # mmio.h
     "mm_read_banner", "mm_read_mtx_crd_size", "mm_read_mtx_array_size", "mm_write_banner",
@@ -110,7 +110,8 @@ EXPORTS = [
     "ehyb_plan", "ehyb_plan_reference", "ehyb_build_graph", "ehyb_set_partitioner", "ehyb_partition_graph",
     "ehyb_reorder_with_partition", "ehyb_reorder", "ehyb_partition_blocks", "ehyb_free_host",
     "ehyb_layout_build", "ehyb_layout_build_csr", "ehyb_layout_get", "ehyb_layout_to_reference",
-    "ehyb_layout_free", "ehyb_session_opts_default", "ehyb_upload", "ehyb_spmv", "ehyb_spmv_host",
+    "ehyb_layout_free", "ehyb_layout_save", "ehyb_layout_load", "ehyb_cache_save", "ehyb_cache_load",
+    "ehyb_session_opts_default", "ehyb_upload", "ehyb_spmv", "ehyb_spmv_host",
     "ehyb_spmv_host_batch", "ehyb_session_vectors", "ehyb_set_x", "ehyb_get_y", "ehyb_time_spmv",
     "ehyb_launches_per_spmv", "ehyb_trace_read", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
     "ehyb_gen_lower", "ehyb_coo_from_lower", "ehyb_coo_from_general", "ehyb_gen_rmat", "ehyb_x_reference",

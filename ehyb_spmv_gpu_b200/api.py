@@ -259,6 +259,50 @@ class Layout:
         self.v = LayoutView()
         check(self.lib, self.lib.ehyb_layout_get(self.h, C.byref(self.v)), "ehyb_layout_get")
 
+    @classmethod
+    def _adopt(cls, handle):
+        self = cls.__new__(cls)
+        self.lib = L.load()
+        self.h = handle
+        self.v = LayoutView()
+        check(self.lib, self.lib.ehyb_layout_get(self.h, C.byref(self.v)), "ehyb_layout_get")
+        return self
+
+    def save(self, path):
+        """ehyb_layout_save: the layout alone as a binary file."""
+        check(self.lib, self.lib.ehyb_layout_save(self.h, str(path).encode()), "ehyb_layout_save")
+
+    @classmethod
+    def load(cls, path):
+        lib = L.load()
+        h = C.c_void_p()
+        check(lib, lib.ehyb_layout_load(str(path).encode(), C.byref(h)), "ehyb_layout_load")
+        return cls._adopt(h)
+
+    def cache_save(self, path, source_path, symmetric, reorderList, x, y_golden, absAx):
+        """ehyb_cache_save: the finished pipeline of `source_path` (layout + permutation + vectors)."""
+        rl = np.ascontiguousarray(reorderList, np.int32)
+        vs = [np.ascontiguousarray(a, np.float64) for a in (x, y_golden, absAx)]
+        check(self.lib, self.lib.ehyb_cache_save(str(path).encode(), str(source_path).encode() if source_path else None, self.h,
+                                                 int(symmetric), rl.ctypes.data_as(L.c_int_p), *[a.ctypes.data_as(L.c_dbl_p) for a in vs]),
+              "ehyb_cache_save")
+
+    @classmethod
+    def cache_load(cls, path, source_path=None, plan=None):
+        """ehyb_cache_load -> (Layout, dict(n, symmetric, reorderList, x, y_golden, absAx))."""
+        lib = L.load()
+        h = C.c_void_p(); n = C.c_int(); sym = C.c_int()
+        rl = L.c_int_p(); x = L.c_dbl_p(); y = L.c_dbl_p(); a = L.c_dbl_p()
+        check(lib, lib.ehyb_cache_load(str(path).encode(), str(source_path).encode() if source_path else None,
+                                       C.byref(plan) if plan is not None else None, C.byref(h), C.byref(n), C.byref(sym),
+                                       C.byref(rl), C.byref(x), C.byref(y), C.byref(a)), "ehyb_cache_load")
+        out = dict(n=n.value, symmetric=bool(sym.value))
+        for k, ptr, dt in (("reorderList", rl, np.int32), ("x", x, np.float64), ("y_golden", y, np.float64), ("absAx", a, np.float64)):
+            out[k] = _np(ptr, n.value, dt) if ptr else None
+            if ptr:
+                lib.ehyb_free_host(ptr)
+        return cls._adopt(h), out
+
     def stats(self):
         v = self.v
         return {k: getattr(v, k) for k in ("n", "ncols", "nnz", "nParts", "W", "ctasPerPart", "nSlices", "blobBytes",

@@ -599,3 +599,56 @@ done:
     free(c.rowIdx); free(c.numInRow); free(c.numInRow2); free(c.I); free(c.J); free(c.V); free(c.partBoundary);
     return rc;
 }
+
+/* ---------------------------------------------------------------------------------- */
+/* serialisation hooks (cache.c)                                                       */
+/* ---------------------------------------------------------------------------------- */
+
+/* every array of a layout, in the order ehyb_layout_import expects them */
+int ehyb_layout_export_arrays(const ehyb_layout *L, const void **arrays, int64_t *bytes, int max)
+{
+    const ehyb_layout_view *v = &L->v;
+    const void *a[] = {L->parts, L->slices, L->blob, L->ovfRow, L->ovfCol, L->ovfVal, L->cacheCols,
+                       L->rowEll, L->rowRemIn, L->rowCached, L->ovfPtr};
+    const int64_t b[] = {(int64_t)sizeof(ehyb_part_desc) * v->nParts, (int64_t)sizeof(ehyb_slice_desc) * v->nSlices, v->blobBytes,
+                         4 * v->nOverflow, 4 * v->nOverflow, 8 * v->nOverflow, 4 * v->cacheTotal,
+                         4 * v->n, 4 * v->n, 4 * v->n, 8 * (v->n + 1)};
+    const int na = (int)(sizeof a / sizeof a[0]);
+    if (max < na) return 0;
+    for (int i = 0; i < na; ++i) { arrays[i] = a[i]; bytes[i] = b[i]; }
+    return na;
+}
+
+/* builds a layout around malloc'd arrays (ownership passes to the layout) after checking that
+ * they are consistent with the scalars: a corrupt cache must not reach the device */
+int ehyb_layout_import(const ehyb_layout_view *sc, void *const *arrays, ehyb_layout **out)
+{
+    ehyb_layout *L = (ehyb_layout *)calloc(1, sizeof *L);
+    if (!L) return ehyb_fail(EHYB_ERR_NOMEM, "layout import: out of memory");
+    const ehyb_part_desc *parts = (const ehyb_part_desc *)arrays[0];
+    const ehyb_slice_desc *slices = (const ehyb_slice_desc *)arrays[1];
+    const int32_t *cacheCols = (const int32_t *)arrays[6];
+    int bad = sc->W <= 0 || sc->W > 65536 || sc->ncols < sc->n;
+    for (int p = 0; p < sc->nParts && !bad; ++p) {
+        const ehyb_part_desc *d = &parts[p];
+        bad = d->rowStart < 0 || d->rowEnd < d->rowStart || d->rowEnd > sc->n || d->sliceStart < 0 || d->sliceEnd < d->sliceStart ||
+              d->sliceEnd > sc->nSlices || d->cacheStart < 0 || d->cacheCount < 0 || (int64_t)d->cacheStart + d->cacheCount > sc->cacheTotal ||
+              d->cacheCount > sc->cacheMax || (p > 0 && d->rowStart != parts[p - 1].rowEnd);
+    }
+    for (int s = 0; s < sc->nSlices && !bad; ++s)
+        bad = (int64_t)slices[s].off256 * 256 + slice_bytes(slices[s].w, slices[s].wr) > sc->blobBytes;
+    for (int64_t i = 0; i < sc->cacheTotal && !bad; ++i) bad = cacheCols[i] < 0 || cacheCols[i] >= sc->ncols;
+    const int32_t *ovfRow = (const int32_t *)arrays[3], *ovfCol = (const int32_t *)arrays[4];
+    for (int64_t i = 0; i < sc->nOverflow && !bad; ++i)
+        bad = ovfRow[i] < 0 || ovfRow[i] >= sc->n || ovfCol[i] < 0 || ovfCol[i] >= sc->ncols || (i > 0 && ovfRow[i] < ovfRow[i - 1]);
+    if (bad) { free(L); return ehyb_fail(EHYB_ERR_IO, "layout import: arrays are inconsistent with the header"); }
+    L->parts = (ehyb_part_desc *)arrays[0]; L->slices = (ehyb_slice_desc *)arrays[1]; L->blob = (unsigned char *)arrays[2];
+    L->ovfRow = (int32_t *)arrays[3]; L->ovfCol = (int32_t *)arrays[4]; L->ovfVal = (double *)arrays[5];
+    L->cacheCols = (int32_t *)arrays[6]; L->rowEll = (int32_t *)arrays[7]; L->rowRemIn = (int32_t *)arrays[8];
+    L->rowCached = (int32_t *)arrays[9]; L->ovfPtr = (int64_t *)arrays[10];
+    L->v = *sc;
+    L->v.parts = L->parts; L->v.slices = L->slices; L->v.blob = L->blob;
+    L->v.ovfRow = L->ovfRow; L->v.ovfCol = L->ovfCol; L->v.ovfVal = L->ovfVal; L->v.cacheCols = L->cacheCols;
+    *out = L;
+    return EHYB_OK;
+}

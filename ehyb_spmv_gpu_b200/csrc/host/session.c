@@ -27,23 +27,42 @@ static double measured_hbm_gbs(void)
     return s && s[0] ? atof(s) : 0.0;
 }
 
+static void session_on_layout(const ehyb_layout *L, const double *vectorIn, double *vectorOut, const int MAXIter, int *realIter);
+
 void spmvGPuEHYB(matrixCOO *localMatrix, const double *vectorIn, double *vectorOut, const int MAXIter, int *realIter)
 {
     if (!localMatrix || !vectorIn || !vectorOut) {
         ehyb_fail(EHYB_ERR_ARG, "NULL argument");
         ehyb_die("spmvGPuEHYB");
     }
-    const int totalNum = localMatrix->totalNum;
     ehyb_layout *L = NULL;
-    ehyb_handle *h = NULL;
     ehyb_layout_opts lo;
     memset(&lo, 0, sizeof lo);
     lo.er_fill = -1.0; /* automatic */
     const char *fillEnv = getenv("EHYB_ER_FILL");
     if (fillEnv && fillEnv[0]) lo.er_fill = atof(fillEnv);
     if (ehyb_layout_build(localMatrix, &lo, &L)) ehyb_die("spmvGPuEHYB: format build");
+    session_on_layout(L, vectorIn, vectorOut, MAXIter, realIter);
+    ehyb_layout_free(L);
+}
+
+/* The same session on a layout that already exists (built by the caller, or loaded from the
+ * binary cache, cache.c): everything of spmvGPuEHYB after the format build. */
+void spmvGPuEHYB_layout(const ehyb_layout *L, const double *vectorIn, double *vectorOut, const int MAXIter, int *realIter)
+{
+    if (!L || !vectorIn || !vectorOut) {
+        ehyb_fail(EHYB_ERR_ARG, "NULL argument");
+        ehyb_die("spmvGPuEHYB_layout");
+    }
+    session_on_layout(L, vectorIn, vectorOut, MAXIter, realIter);
+}
+
+static void session_on_layout(const ehyb_layout *L, const double *vectorIn, double *vectorOut, const int MAXIter, int *realIter)
+{
+    ehyb_handle *h = NULL;
     ehyb_layout_view v;
     ehyb_layout_get(L, &v);
+    const int64_t totalNum = v.nnz;
     /* the reference's converter lines (convert.c:140, :310; spmv.cu:82), same meaning */
     printf("toER is %lld, kernel calculation is %lld\n", (long long)(v.nnz - v.nnzEll), (long long)v.nnzEll);
     printf("wasteElement is %lld\n", (long long)v.padEll);
@@ -95,7 +114,6 @@ void spmvGPuEHYB(matrixCOO *localMatrix, const double *vectorIn, double *vectorO
            (long long)(12LL * v.nnz + 4 * (v.n + 1) + 16 * v.n), (long long)v.formatBytes);
     if (realIter) *realIter = iter;
     ehyb_free(h);
-    ehyb_layout_free(L);
 }
 
 static ehyb_handle *session_of(matrixEHYB *m, const char *who)

@@ -9,12 +9,16 @@
  * instead of compile-time constants (-R keeps the reference's heuristic), -M takes a path
  * instead of a name under ./read, -g generates one of the BASELINE.json matrices in memory,
  * the comparison is against the accuracy gate |y - y_ref| <= 1e-12 (|A||x|) and decides the
- * exit code, and y is calloc'd (B-10).
+ * exit code, and y is calloc'd (B-10).  Binary cache: the finished pipeline of
+ * a .mtx file (permutation, x, golden y, tuned layout) is written to <file>.ehyb and loaded by
+ * the next run with the same file and partition parameters, which then skips the reader,
+ * mt-metis, the reorder and the format build; -C disables it, the stage times are printed.
  */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/time.h>
 #include <unistd.h>
 #include "ehyb.h"
 #include "kernel.h"
@@ -57,19 +61,41 @@ static int compare(const double *yResult, const double *y, const double *absAx, 
     return gate;
 }
 
+static double now_s(void)
+{
+    struct timeval t;
+    gettimeofday(&t, NULL);
+    return (double)t.tv_sec + 1e-6 * (double)t.tv_usec;
+}
+
+/* recover y, print the reference's sample lines, compare (solver_test.c:383-389) */
+static int finish(int n, const double *yReorder, const int *reorderList, const double *y, const double *absAx)
+{
+    double *yResult = (double *)calloc((size_t)n, sizeof(double));
+    vectorRecover(n, yReorder, yResult, reorderList);
+    for (int i = 0; i < 10; i++) { /* solver_test.c:385-388, without the out-of-bounds read (B-18) */
+        int r = n > 30010 ? i + 30000 : i % n;
+        printf("at %d yResult is %f y is  %f\n", r, yResult[r], y[r]);
+    }
+    int failed = compare(yResult, y, absAx, 0.01, n);
+    free(yResult);
+    return failed;
+}
+
 static void usage(void)
 {
     printf("usage: spmv.out -i <iterations> (-m <name> | -M <file.mtx> | -g lap2d:NX:NY | -g st27:NX:NY:NZ | -g elas:NX:NY:NZ)\n"
-           "       [-R] reference partition heuristic   [-P <parts> -W <window> -K <ctas per partition>] override\n");
+           "       [-R] reference partition heuristic   [-P <parts> -W <window> -K <ctas per partition>] override\n"
+           "       [-C] do not read or write the binary cache <file>.ehyb\n");
 }
 
 int main(int argc, char *argv[])
 {
-    int MAXIter = 0, oc, useRefPlan = 0, oP = 0, oW = 0, oK = 0;
+    int MAXIter = 0, oc, useRefPlan = 0, oP = 0, oW = 0, oK = 0, useCache = 1;
     char fileName[1024] = "", gen[256] = "";
     cb_s cb;
     init_cb(&cb);
-    while ((oc = getopt(argc, argv, "m:M:g:i:r:t:f:p:RP:W:K:")) != -1) {
+    while ((oc = getopt(argc, argv, "m:M:g:i:r:t:f:p:RP:W:K:C")) != -1) {
         switch (oc) {
         case 'm':
             snprintf(fileName, sizeof fileName, "./read/%s.mtx", optarg); /* solver_test.c:284 */
@@ -85,6 +111,7 @@ int main(int argc, char *argv[])
         case 'P': oP = atoi(optarg); break;
         case 'W': oW = atoi(optarg); break;
         case 'K': oK = atoi(optarg); break;
+        case 'C': useCache = 0; break;
         case '?': printf("unrecongnized option\n"); break;
         default: printf("option/arguments error!\n"); return 0;
         }
@@ -99,11 +126,65 @@ int main(int argc, char *argv[])
         return 0;
     }
     ehyb_set_partitioner(mtmetis_direct, NULL);
+    if (getenv("EHYB_NO_CACHE")) useCache = 0;
+    ehyb_device_info dev;
+    int haveDev = ehyb_device_query(0, &dev) == EHYB_OK;
+    if (!haveDev) ehyb_device_info_b200(&dev);
+
+    /* ------------------------------- binary cache of a previous run ------------------------------- */
+    char cachePath[1100] = "";
+    if (fileName[0]) snprintf(cachePath, sizeof cachePath, "%s.ehyb", fileName);
+    if (useCache && cachePath[0] && access(cachePath, R_OK) == 0) {
+        const double t0 = now_s();
+        ehyb_layout *L = NULL;
+        int n = 0, sym = 1, *perm = NULL;
+        double *cx = NULL, *cy = NULL, *cabs = NULL;
+        int rc = ehyb_cache_load(cachePath, fileName, NULL, &L, &n, &sym, &perm, &cx, &cy, &cabs);
+        if (rc == EHYB_OK && perm && cx) {
+            /* the cache must have been built for the parameters this run would choose */
+            ehyb_layout_view v;
+            ehyb_layout_get(L, &v);
+            ehyb_plan_t want;
+            if (useRefPlan) ehyb_plan_reference(n, sym, &want);
+            else ehyb_plan(n, &dev, &want);
+            if (oP > 0) want.nParts = oP;
+            if (oW > 0) want.W = oW;
+            if (oK > 0) want.ctasPerPart = oK;
+            if (want.nParts != v.nParts || want.W != v.W || (want.ctasPerPart > 0 ? want.ctasPerPart : 1) != v.ctasPerPart) {
+                printf("cache %s holds P=%d W=%d K=%d, this run wants P=%d W=%d K=%d: rebuilding\n", cachePath, v.nParts, v.W, v.ctasPerPart,
+                       want.nParts, want.W, want.ctasPerPart);
+                rc = EHYB_ERR_IO;
+            }
+        } else if (rc == EHYB_OK) {
+            rc = EHYB_ERR_IO;
+        } else {
+            printf("cache not used: %s\n", ehyb_last_error());
+        }
+        if (rc == EHYB_OK) {
+            ehyb_layout_view v;
+            ehyb_layout_get(L, &v);
+            printf("cache: loaded %s in %.2f s (reader, partitioner, reorder and format build skipped)\n", cachePath, now_s() - t0);
+            printf("parts is %d with cachSize %d\n", v.nParts, v.W);
+            printf("device: %s, %d SMs, %d B shared memory per CTA\n", dev.name, dev.sm_count, dev.smem_optin_bytes);
+            double *xReorder = (double *)calloc((size_t)n, sizeof(double));
+            double *yReorder = (double *)calloc((size_t)n, sizeof(double));
+            vectorReorder(n, cx, xReorder, perm);
+            int realIter = 0;
+            spmvGPuEHYB_layout(L, xReorder, yReorder, MAXIter, &realIter);
+            int failed = finish(n, yReorder, perm, cy, cabs);
+            ehyb_layout_free(L);
+            free(xReorder); free(yReorder); ehyb_free_host(perm); ehyb_free_host(cx); ehyb_free_host(cy); ehyb_free_host(cabs);
+            return failed ? 3 : 0;
+        }
+        ehyb_layout_free(L);
+        ehyb_free_host(perm); ehyb_free_host(cx); ehyb_free_host(cy); ehyb_free_host(cabs);
+    }
 
     /* ------------------------------- read / generate the matrix ------------------------------- */
     matrixCOO A;
     double *x = NULL, *y = NULL;
     int symmetric = 1;
+    const double tRead0 = now_s();
     if (gen[0]) {
         char kind[32] = "";
         int nx = 0, ny = 0, nz = 1;
@@ -138,11 +219,10 @@ int main(int argc, char *argv[])
         if (ehyb_read_mtx(fileName, &A, &symmetric, &x, &y)) { printf("%s\n", ehyb_last_error()); return 1; }
     }
 
+    const double tRead = now_s() - tRead0;
+
     /* ------------------------------- partition parameters ------------------------------- */
     ehyb_plan_t plan;
-    ehyb_device_info dev;
-    int haveDev = ehyb_device_query(0, &dev) == EHYB_OK;
-    if (!haveDev) ehyb_device_info_b200(&dev);
     if (useRefPlan) ehyb_plan_reference(A.dimension, symmetric, &plan);
     else ehyb_plan(A.dimension, &dev, &plan);
     if (oP > 0) plan.nParts = oP;
@@ -162,25 +242,40 @@ int main(int argc, char *argv[])
 
     /* ------------------------------- reorder, SpMV, recover, compare ------------------------------- */
     const int n = A.dimension;
-    double *yResult = (double *)calloc((size_t)n, sizeof(double));
     double *xReorder = (double *)calloc((size_t)n, sizeof(double));
     double *yReorder = (double *)calloc((size_t)n, sizeof(double));
+    const double tReorder0 = now_s();
     if (symmetric) {
         matrixReorder(&A);
     } else {
         printf("unsymmetric reordering\n");
         matrixReorder_unsym(&A);
     }
+    const double tReorder = now_s() - tReorder0;
     vectorReorder(n, x, xReorder, A.reorderList);
     int realIter = 0;
-    spmvGPuEHYB(&A, xReorder, yReorder, MAXIter, &realIter);
-    vectorRecover(n, yReorder, yResult, A.reorderList);
-    for (int i = 0; i < 10; i++) { /* solver_test.c:385-388, without the out-of-bounds read (B-18) */
-        int r = n > 30010 ? i + 30000 : i % n;
-        printf("at %d yResult is %f y is  %f\n", r, yResult[r], y[r]);
+    /* the reference calls spmvGPuEHYB(&A, ...) here (solver_test.c:382), which converts inside; the
+     * driver builds the layout itself so that it can also write it to the cache */
+    const double tBuild0 = now_s();
+    ehyb_layout *L = NULL;
+    ehyb_layout_opts lo;
+    memset(&lo, 0, sizeof lo);
+    lo.er_fill = -1.0;
+    const char *fillEnv = getenv("EHYB_ER_FILL");
+    if (fillEnv && fillEnv[0]) lo.er_fill = atof(fillEnv);
+    if (ehyb_layout_build(&A, &lo, &L)) { printf("format build: %s\n", ehyb_last_error()); return 1; }
+    const double tBuild = now_s() - tBuild0;
+    double tSave = 0.0;
+    if (useCache && cachePath[0]) {
+        const double t0 = now_s();
+        if (ehyb_cache_save(cachePath, fileName, L, symmetric, A.reorderList, x, y, absAx)) printf("cache not written: %s\n", ehyb_last_error());
+        else { tSave = now_s() - t0; printf("cache: wrote %s\n", cachePath); }
     }
-    int failed = compare(yResult, y, absAx, 0.01, n);
+    printf("host stages: read/generate %.2f s, partition + reorder %.2f s, format build %.2f s, cache write %.2f s\n", tRead, tReorder, tBuild, tSave);
+    spmvGPuEHYB_layout(L, xReorder, yReorder, MAXIter, &realIter);
+    ehyb_layout_free(L);
+    int failed = finish(n, yReorder, A.reorderList, y, absAx);
     ehyb_coo_free(&A);
-    free(yResult); free(xReorder); free(yReorder); free(x); free(y); free(absAx);
+    free(xReorder); free(yReorder); free(x); free(y); free(absAx);
     return failed ? 3 : 0;
 }

@@ -244,7 +244,7 @@ EXCHANGE_TEXT = {
 }
 
 
-def bench(args, rank, world, local, grid, workload):
+def bench(args, rank, world, local, grid, workload, scaling="weak"):
     """bench.py at N > 1 (called under torchrun, process group already initialised)."""
     import torch
     import torch.distributed as dist
@@ -323,7 +323,7 @@ def bench(args, rank, world, local, grid, workload):
         out = {
             "metric": "fp64 SpMV GFLOP/s (2*nnz/t), EHYB format", "value": round(2.0 * nnz_all / (ms_per_step * 1e6), 2),
             "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_per_step, 6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": round(ms_per_step, 6), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "global_grid": [grid[0], grid[1], grid[2] * world],
                        "decomposition": "z-slabs, one per GPU; level-2 partition per GPU: " + os.environ.get("EHYB_MG_PARTITION", "metis"),

@@ -191,6 +191,21 @@ int ehyb_layout_get(const ehyb_layout *L, ehyb_layout_view *view);
 int ehyb_layout_to_reference(const ehyb_layout *L, matrixEHYB *out, int *sizeBlockELL, int *sizeER);
 void ehyb_layout_free(ehyb_layout *L);
 
+/* Binary cache (the reference re-runs reader, mt-metis, reorder and COO2EHYB on
+ * every invocation).  ehyb_layout_save/load move a layout alone.  ehyb_cache_save/load move the
+ * whole result of the pipeline for a source file: the layout plus - all optional together - the
+ * permutation reorderList[n], x[n], the golden product y_golden[n] and absAx[n] = |A||x| (for
+ * the accuracy gate).  The cache records size + mtime of source_path and the partition
+ * parameters; ehyb_cache_load fails with EHYB_ERR_IO when the file is absent, truncated, fails
+ * its checksum, was built from another version of the source, or - with plan != NULL - for
+ * other parameters.  Output arrays are malloc'd (ehyb_free_host). */
+int ehyb_layout_save(const ehyb_layout *L, const char *path);
+int ehyb_layout_load(const char *path, ehyb_layout **out);
+int ehyb_cache_save(const char *path, const char *source_path, const ehyb_layout *L, int symmetric, const int *reorderList,
+                    const double *x, const double *y_golden, const double *absAx);
+int ehyb_cache_load(const char *path, const char *source_path, const ehyb_plan_t *plan, ehyb_layout **L, int *n,
+                    int *symmetric, int **reorderList, double **x, double **y_golden, double **absAx);
+
 /* ------------------------------------------------------------------------------------ */
 /* device session                                                                         */
 /* ------------------------------------------------------------------------------------ */

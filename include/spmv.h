@@ -102,6 +102,12 @@ static inline void init_cb(cb_s *in_s)
  */
 void spmvGPuEHYB(matrixCOO *localMatrix, const double *vectorIn, double *vectorOut,
                  const int MAXIter, int *realIter);
+/* The same session on an existing tuned layout (struct ehyb_layout of ehyb.h: built by the
+ * caller or loaded from the binary cache): everything of spmvGPuEHYB after COO2EHYB. */
+struct ehyb_layout;
+void spmvGPuEHYB_layout(const struct ehyb_layout *layout, const double *vectorIn, double *vectorOut,
+                        const int MAXIter, int *realIter);
+
 
 #ifdef __cplusplus
 }
