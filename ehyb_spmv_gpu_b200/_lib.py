@@ -90,6 +90,15 @@ class LayoutView(C.Structure):
     ]
 
 
+class PcgOpts(C.Structure):
+    _fields_ = [("max_iters", C.c_int), ("rtol", C.c_double), ("check_every", C.c_int)]
+
+
+class PcgResult(C.Structure):
+    _fields_ = [("iters", C.c_int), ("converged", C.c_int), ("rel_residual", C.c_double), ("true_rel_residual", C.c_double),
+                ("ms", C.c_float)]
+
+
 class SessionOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("threads", C.c_int), ("use_graph", C.c_int),
                 ("l2_persist_x", C.c_int), ("halo_cols", C.c_int64), ("kernel", C.c_int)]
@@ -113,7 +122,7 @@ EXPORTS = [
     "ehyb_layout_free", "ehyb_layout_save", "ehyb_layout_load", "ehyb_cache_save", "ehyb_cache_load",
     "ehyb_session_opts_default", "ehyb_upload", "ehyb_spmv", "ehyb_spmv_host",
     "ehyb_spmv_host_batch", "ehyb_session_vectors", "ehyb_set_x", "ehyb_get_y", "ehyb_time_spmv",
-    "ehyb_launches_per_spmv", "ehyb_trace_read", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
+    "ehyb_launches_per_spmv", "ehyb_pcg_opts_default", "ehyb_pcg_solve", "ehyb_session_size", "ehyb_trace_read", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
     "ehyb_gen_lower", "ehyb_coo_from_lower", "ehyb_coo_from_general", "ehyb_gen_rmat", "ehyb_x_reference",
     "ehyb_read_mtx", "ehyb_write_mtx", "ehyb_coo_free",
     "ehyb_mg_local_build", "ehyb_mg_local_halo", "ehyb_mg_local_set_send", "ehyb_mg_local_graph",

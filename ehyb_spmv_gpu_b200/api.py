@@ -392,6 +392,20 @@ class Session:
               "ehyb_time_spmv")
         return (ms.value, kms.value) if kernel_only else ms.value
 
+    def pcg_solve(self, b, diag=None, max_iters=1000, rtol=1e-10, check_every=8):
+        """ehyb_pcg_solve: A x = b (permuted numbering), Jacobi-preconditioned when diag is given.
+        Returns (x, dict(iters, converged, rel_residual, true_rel_residual, ms))."""
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.empty_like(b)
+        d = np.ascontiguousarray(diag, np.float64) if diag is not None else None
+        o = L.PcgOpts(int(max_iters), float(rtol), int(check_every))
+        r = L.PcgResult()
+        check(self.lib, self.lib.ehyb_pcg_solve(self.h, d.ctypes.data_as(L.c_dbl_p) if d is not None else None,
+                                                b.ctypes.data_as(L.c_dbl_p), x.ctypes.data_as(L.c_dbl_p), C.byref(o), C.byref(r)),
+              "ehyb_pcg_solve")
+        return x, dict(iters=r.iters, converged=bool(r.converged), rel_residual=r.rel_residual,
+                       true_rel_residual=r.true_rel_residual, ms=r.ms)
+
     def launches_per_spmv(self) -> int:
         return int(self.lib.ehyb_launches_per_spmv(self.h))
 

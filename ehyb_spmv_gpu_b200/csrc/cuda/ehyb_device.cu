@@ -604,6 +604,14 @@ extern "C" int ehyb_trace_read(ehyb_handle *h, unsigned long long *out, int *cta
     return EHYB_OK;
 }
 
+extern "C" int ehyb_session_size(const ehyb_handle *h, int64_t *n, int64_t *ncols)
+{
+    if (!h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_session_size: NULL");
+    if (n) *n = h->n;
+    if (ncols) *ncols = h->ncols;
+    return EHYB_OK;
+}
+
 extern "C" int ehyb_describe(ehyb_handle *h, matrixEHYB *d)
 {
     if (!h || !d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_describe: NULL");

@@ -264,6 +264,36 @@ int ehyb_trace_read(ehyb_handle *h, unsigned long long *out, int *ctas);
 int ehyb_describe(ehyb_handle *h, matrixEHYB *d);
 
 /* ------------------------------------------------------------------------------------ */
+/* solver shell on top of the product: Jacobi-preconditioned CG,   */
+/* the loop the reference's unused helpers outline (kernel.cu:13-42, :288-321; cb_s.PRECOND; */
+/* matrixCOO.diag; the never-written realIter of spmvGPuEHYB)                                */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct ehyb_pcg_opts {
+    int max_iters;   /* default 1000 */
+    double rtol;     /* stop when |r| <= rtol |b| (recurrence residual), default 1e-10 */
+    int check_every; /* iterations between two looks at the residual from the host, default 8:
+                        the scalars of the iteration live on the device */
+} ehyb_pcg_opts;
+
+typedef struct ehyb_pcg_result {
+    int iters;                /* products performed (a multiple of check_every unless max_iters stopped it) */
+    int converged;
+    double rel_residual;      /* |r| / |b| of the recurrence at the last check */
+    double true_rel_residual; /* |b - A x| / |b|, one extra product at the end */
+    float ms;                 /* CUDA-event time of the iterations on the session stream */
+} ehyb_pcg_result;
+
+void ehyb_pcg_opts_default(ehyb_pcg_opts *o);
+/* Solves A x = b for the symmetric positive definite matrix of session h.  Host vectors in the
+ * session's (permuted) numbering, n entries; x starts from zero.  diag_h = the matrix diagonal
+ * in the same numbering for Jacobi preconditioning, or NULL for plain CG. */
+int ehyb_pcg_solve(ehyb_handle *h, const double *diag_h, const double *b_h, double *x_h, const ehyb_pcg_opts *opts,
+                   ehyb_pcg_result *res);
+/* rows and columns of the session's operator */
+int ehyb_session_size(const ehyb_handle *h, int64_t *n, int64_t *ncols);
+
+/* ------------------------------------------------------------------------------------ */
 /* multi-GPU: one process per GPU, rows distributed in contiguous blocks, x halo exchanged    */
 /* every product (no reference counterpart).  Two exchanges:             */
 /*   EHYB_MG_P2P   (product) the main kernel itself stores the x entries its neighbours need   */
