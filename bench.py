@@ -200,6 +200,8 @@ def run_ours(args):
     with stdout_to_stderr():
         m, lay, x, pl, t_prep = build_matrix(GRID)
     st = lay.stats()
+    print("layout: P=%d W=%d slices=%d nnz_ell=%d in-slice remainder=%d overflow=%d" % (st["nParts"], st["W"], st["nSlices"], st["nnzEll"],
+                                                                                      st["nnzRemInSlice"], st["nnzOverflow"]), file=sys.stderr, flush=True)
     s = api.Session(lay, device=local)
     xr = m.vector_reorder(x)
     s.set_x(xr)
@@ -238,7 +240,13 @@ def run_ours(args):
     s.spmv_host_batch([xs[i % nbuf] for i in range(args.steps)], [ys[i % nbuf] for i in range(args.steps)])
     t_e2e = time.perf_counter() - t0
     e2e_gflops = 2.0 * st["nnz"] * args.steps / t_e2e / 1e9
-    assert np.array_equal(np.asarray(ys[0]), s.spmv_host(np.asarray(xs[0])))
+    y_again = s.spmv_host(np.asarray(xs[0]))
+    if st["nnzOverflow"] == 0:
+        # every row is summed by one lane in a fixed order: the pipelined path must reproduce it bit for bit
+        assert np.array_equal(np.asarray(ys[0]), y_again)
+    else:
+        # overflow entries are added with atomics: equal up to summation order
+        assert np.allclose(np.asarray(ys[0]), y_again, rtol=0, atol=1e-12 * float(np.abs(y_again).max() + 1.0))
 
     # ---- CPU baseline: the oracle's CSR product on the host cores (bounded sample) ----
     from oracle import oracle as O

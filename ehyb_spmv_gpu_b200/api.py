@@ -15,7 +15,7 @@ from ._lib import (DeviceInfo, EhybError, LayoutOpts, LayoutView, MatrixCOO, Mat
                    SessionOpts, check)
 
 GEN_LAPLACE2D, GEN_STENCIL27, GEN_ELASTICITY = 1, 2, 3
-KERNEL_DIRECT, KERNEL_STAGED = 1, 2
+KERNEL_DIRECT, KERNEL_STAGED, KERNEL_PERSISTENT = 1, 2, 3
 
 
 def _np(ptr, count, dtype):

@@ -36,7 +36,7 @@ struct ehyb_handle {
     int device;
     cudaStream_t stream, h2d, d2h;
     int64_t n, ncols, nnz, nOvf, blobBytes, algBytes;
-    int nParts, W, kpp, nSlices, threads, ctasPerSM, kernel, kcEll, kcRem;
+    int nParts, W, kpp, nSlices, threads, ctasPerSM, kernel, kcEll, kcRem, grid;
     size_t smemBytes;
     ehyb_part_desc *parts;
     ehyb_slice_desc *slices;
@@ -117,6 +117,9 @@ static const StagedVariant kStaged[] = {
     {8, ehyb_staged_kernel<512, 8>, ehyb_staged_kernel<768, 8>},
     {16, ehyb_staged_kernel<512, 16>, ehyb_staged_kernel<768, 16>},
 };
+/* persistent, double-buffered variant (ehyb_persistent_kernel): 4-column chunks only */
+static main_kernel_t persistent_kernel(int threads) { return threads <= 512 ? ehyb_persistent_kernel<512, 4> : ehyb_persistent_kernel<768, 4>; }
+
 static const StagedVariant *staged_variant(int kc)
 {
     for (size_t i = 0; i < sizeof kStaged / sizeof kStaged[0]; ++i)
@@ -172,6 +175,26 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     const size_t winBytes = (((size_t)v->W + 2) * sizeof(double) + 127) & ~(size_t)127;
     h->cacheCap = (v->cacheMax + 15) & ~15;
     const size_t cacheBytes = ((size_t)h->cacheCap * sizeof(double) + 127) & ~(size_t)127;
+    if (kernel == EHYB_KERNEL_PERSISTENT) {
+        /* one CTA per SM over several partitions, {window, cache} double-buffered: needs one CTA
+         * per partition, at most kMaxPartsPerCta partitions per CTA and room for >= 8 warps of
+         * staging next to the two buffers; otherwise the staged kernel */
+        const int grid = h->nParts < prop.multiProcessorCount ? h->nParts : prop.multiProcessorCount;
+        const size_t fixed = (size_t)kPersistHeader + 2 * (winBytes + cacheBytes);
+        const size_t perWarp = (size_t)kSlotsPerWarp * slot_bytes(4);
+        int nw = fixed + perWarp <= prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - fixed) / perWarp) : 0;
+        if (nw > kMaxStageWarps) nw = kMaxStageWarps;
+        if (threads > 0 && threads / 32 < nw) nw = threads / 32 > 0 ? threads / 32 : 1;
+        if (h->kpp != 1 || (h->nParts + grid - 1) / grid > kMaxPartsPerCta || nw < 8) {
+            kernel = EHYB_KERNEL_STAGED;
+        } else {
+            h->kcEll = h->kcRem = 4;
+            h->threads = nw * 32;
+            h->smemBytes = fixed + (size_t)nw * perWarp;
+            h->ctasPerSM = 1;
+            h->grid = grid;
+        }
+    }
     if (kernel == EHYB_KERNEL_STAGED) {
         /* warps = staging capacity: 2 slots each, as many as fit next to the window */
         const StagedVariant *sv = staged_variant(env_int("EHYB_CHUNK", 4));
@@ -191,7 +214,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
             if (h->ctasPerSM < 1) h->ctasPerSM = 1;
         }
     }
-    if (kernel != EHYB_KERNEL_STAGED) {
+    if (kernel != EHYB_KERNEL_STAGED && kernel != EHYB_KERNEL_PERSISTENT) {
         kernel = EHYB_KERNEL_DIRECT;
         h->smemBytes = (size_t)kSmemHeader + (size_t)((v->W + 2 + 15) & ~15) * sizeof(double) + cacheBytes;
         if (h->smemBytes > prop.sharedMemPerBlockOptin)
@@ -208,6 +231,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
         while (h->ctasPerSM > 1 && h->ctasPerSM * threads > 1024) h->ctasPerSM--;
     }
     h->kernel = kernel;
+    if (kernel != EHYB_KERNEL_PERSISTENT) h->grid = h->nParts * h->kpp;
 
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&h->ev0));
@@ -238,6 +262,10 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (int t = 512; t <= 768; t += 256) {
+        CU(cudaFuncSetAttribute(persistent_kernel(t), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        CU(cudaFuncSetAttribute(persistent_kernel(t), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     for (size_t i = 0; i < sizeof kStaged / sizeof kStaged[0]; ++i) {
         CU(cudaFuncSetAttribute(kStaged[i].k512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
         CU(cudaFuncSetAttribute(kStaged[i].k768, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
@@ -316,6 +344,7 @@ extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, 
 
 static main_kernel_t main_kernel_of(const ehyb_handle *h)
 {
+    if (h->kernel == EHYB_KERNEL_PERSISTENT) return persistent_kernel(h->threads);
     if (h->kernel == EHYB_KERNEL_STAGED) {
         const StagedVariant *sv = staged_variant(h->kcEll);
         return h->threads <= 512 ? sv->k512 : sv->k768;
@@ -338,6 +367,7 @@ static MainArgs main_args(const ehyb_handle *h, const double *x_d, double *y_d, 
     a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
     a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = h->dbgSkip; a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
     a.order = h->order;
+    a.nPartsTotal = h->nParts;
     a.l2hint = h->l2hint;
     a.dynamicDeal = h->dynamicDeal;
     a.prologueBarrier = pa ? 0 : h->prologueBarrier;
@@ -356,11 +386,13 @@ static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStrea
     }
     const MainArgs a = main_args(h, x_d, y_d, pa);
     main_kernel_t k = main_kernel_of(h);
-    if (h->kernel == EHYB_KERNEL_STAGED && h->pdl) {
+    if (h->kernel == EHYB_KERNEL_PERSISTENT && pa != NULL)
+        return ehyb_fail(EHYB_ERR_ARG, "the persistent kernel does not carry the peer-memory exchange (multi-GPU sessions use the staged kernel)");
+    if ((h->kernel == EHYB_KERNEL_STAGED || h->kernel == EHYB_KERNEL_PERSISTENT) && h->pdl) {
         /* programmatic dependent launch: this grid may start while the previous kernel of the
          * stream drains; it orders itself with griddepcontrol.wait before touching x or y */
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(h->nParts * h->kpp));
+        cfg.gridDim = dim3((unsigned)h->grid);
         cfg.blockDim = dim3((unsigned)h->threads);
         cfg.dynamicSmemBytes = h->smemBytes;
         cfg.stream = s;
@@ -371,7 +403,7 @@ static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStrea
         cfg.numAttrs = 1;
         CU(cudaLaunchKernelEx(&cfg, k, a));
     } else {
-        k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, s>>>(a);
+        k<<<(unsigned)h->grid, h->threads, h->smemBytes, s>>>(a);
         CU(cudaGetLastError());
     }
     return EHYB_OK;
@@ -570,7 +602,7 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
         for (int i = 0; i < iters; ++i) {
             cudaEventRecord(ev[2 * i], h->stream);
             if (h->skipMain) cudaMemsetAsync(h->y, 0, sizeof(double) * (size_t)h->n, h->stream);
-            else k<<<(unsigned)(h->nParts * h->kpp), h->threads, h->smemBytes, h->stream>>>(a);
+            else k<<<(unsigned)h->grid, h->threads, h->smemBytes, h->stream>>>(a);
             cudaEventRecord(ev[2 * i + 1], h->stream);
             launch_overflow(h, h->x, h->y, h->stream, NULL);
         }
@@ -629,7 +661,7 @@ extern "C" int ehyb_session_info(const ehyb_handle *h, int *threads, int *ctasPe
     if (!h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_session_info: NULL");
     if (threads) *threads = h->threads;
     if (ctasPerSM) *ctasPerSM = h->ctasPerSM;
-    if (grid) *grid = h->nParts * h->kpp;
+    if (grid) *grid = h->grid;
     if (smemBytes) *smemBytes = (int64_t)h->smemBytes;
     if (l2_persist) *l2_persist = h->l2_persist;
     return EHYB_OK;
@@ -793,6 +825,7 @@ static int mg_session_base(const ehyb_mg_local *L, int rank, int nranks, int dev
     ehyb_session_opts o;
     ehyb_session_opts_default(&o);
     o.device = device;
+    o.kernel = EHYB_KERNEL_STAGED; /* the halo push and pull live in the staged kernel */
     rc = ehyb_upload(layout, &o, &s->h);
     if (rc) { free(s); return rc; }
     auto body = [&]() -> int {

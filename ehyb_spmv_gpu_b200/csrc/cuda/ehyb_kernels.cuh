@@ -70,6 +70,7 @@ struct MainArgs {
     int n;    /* local rows == end of the windowable x range */
     int W;    /* window length in elements */
     int kpp;  /* CTAs per partition */
+    int nPartsTotal; /* persistent kernel: partitions of the matrix (its grid is smaller) */
     int dbg;   /* development only (EHYB_DEBUG_SKIP): 1 = skip remainder math, 2 = skip ELL math */
     const int32_t *cacheCols; /* per-partition remainder cache lists (permuted columns) */
     int cacheCap;             /* shared-memory cache capacity in elements (>= longest list) */
@@ -946,6 +947,420 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
         s ^= 1;
     }
     if (tr && lane == 0) atomicMax(tr + 4, global_timer_ns()); /* last warp of the CTA done */
+}
+
+/* ---------------------------------------------------------------- persistent kernel --- */
+
+/*
+ * The staged kernel stops the matrix stream of an SM for ~6 us at every partition boundary (CTA
+ * exit + start, descriptor chain, window + cache staging: per-CTA timeline in
+ * profiles/r1_notes.md), while HBM delivers ~7.5 TB/s in the steady phase.  This variant keeps
+ * ONE CTA per SM alive over several (smaller) partitions and double-buffers the explicit cache:
+ *
+ *   - shared memory holds two {x window, remainder cache} buffers; while the warps consume
+ *     partition j from buffer j&1, partition j+1 is staged into the other one: the window by a
+ *     TMA bulk copy (warp 0), the cache by every warp's share of the gathers, both right after a
+ *     warp's first slice of partition j ("duty"), behind the `empty` mbarrier that tells that
+ *     every warp has left partition j-1;
+ *   - a warp's chunk stream does not know partition boundaries: when its walker runs out of
+ *     slices in partition j it goes on issuing chunks of partition j+1 (slices are dealt from one
+ *     shared-memory counter per partition), with a "switch" marker in the two-slot pipeline
+ *     where the consumer has to change buffers;
+ *   - no CTA-wide barrier after the start-up; warps are at most one partition apart.
+ *
+ * grid = min(#SMs, nParts), block = NW*32, one CTA per SM; CTA c takes the partitions
+ * order[c + grid*j].  smem = 1664 B header (mbarriers, slice counters, partition table) +
+ * 2 * (align128((W+2)*8) + align128(cacheCap*8)) + NW * 2 * slot.  Requires ctasPerPart == 1
+ * and at most kMaxPartsPerCta partitions per CTA.  Single-GPU sessions only (the peer-memory
+ * exchange lives in the staged kernel).
+ */
+/* mbarrier wait with a time limit: a protocol error between the warps must abort the kernel
+ * (trap: the launch fails with an error), never leave the GPU spinning */
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 1023u) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
+    }
+}
+
+/* asynchronous 8-byte copy global -> shared (LDGSTS) and "arrive on the mbarrier when all my
+ * earlier cp.async have landed" (counts as one of the barrier's expected arrivals) */
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+constexpr int kPersistHeader = 1664;
+constexpr int kMaxPartsPerCta = 32;
+
+struct PMeta {
+    int kc;    /* columns in the chunk */
+    int flags; /* 1 remainder chunk, 2 last chunk of its slice, 4 valid, 8 switch to the next partition (no data) */
+    int t;     /* slice (local index in its partition) */
+};
+
+/* issue side of a warp: walks the slices it is dealt, partition after partition */
+template <int KCE>
+struct PWalker {
+    const int *partTab;        /* shared: 8 ints per partition of this CTA {ps, pe, sliceStart, sliceEnd, cacheStart, cacheCount, -, -} */
+    int *counters;             /* shared: next undealt slice of every partition of this CTA */
+    const uint2 *slices;       /* global slice descriptors */
+    const unsigned char *blob;
+    const unsigned char *base; /* current slice */
+    int nj, j;                 /* partitions of this CTA, partition being issued */
+    int nsl;                   /* slices of partition j */
+    int t, tnext;              /* current / next slice of this warp in partition j */
+    int w, wr, nE, nc, ci;
+    uint2 dnext;
+    int switchesOwed;          /* partition boundaries crossed but not yet sent down the pipeline */
+    bool live;                 /* a current slice exists */
+
+    __device__ __forceinline__ void load_slice(uint2 d)
+    {
+        base = blob + static_cast<size_t>(d.x) * 256u;
+        w = static_cast<int>(d.y & 0xffffu);
+        wr = static_cast<int>(d.y >> 16);
+        nE = (w + KCE - 1) / KCE;
+        nc = max(1, nE + (wr + KCE - 1) / KCE);
+        ci = 0;
+    }
+
+    __device__ __forceinline__ int take(int lane)
+    {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(counters + j, 1);
+        return __shfl_sync(0xffffffffu, v, 0);
+    }
+
+    /* positions the walker on the next slice this warp gets, crossing partitions as needed */
+    __device__ __forceinline__ void next_slice(int lane)
+    {
+        for (;;) {
+            if (tnext < nsl) {
+                t = tnext;
+                load_slice(dnext);
+                tnext = take(lane);
+                if (tnext < nsl) dnext = __ldg(slices + partTab[8 * j + 2] + tnext);
+                live = true;
+                return;
+            }
+            if (j + 1 >= nj) { live = false; return; }
+            j += 1;
+            switchesOwed += 1;
+            nsl = partTab[8 * j + 3] - partTab[8 * j + 2];
+            tnext = take(lane);
+            if (tnext < nsl) dnext = __ldg(slices + partTab[8 * j + 2] + tnext);
+        }
+    }
+
+    __device__ __forceinline__ void start(const int *partTab_, int *counters_, const uint2 *slices_, const unsigned char *blob_, int nj_, int lane)
+    {
+        partTab = partTab_; counters = counters_; slices = slices_; blob = blob_; nj = nj_;
+        j = 0; switchesOwed = 0; live = false;
+        nsl = partTab[3] - partTab[2];
+        tnext = take(lane);
+        if (tnext < nsl) dnext = __ldg(slices + partTab[2] + tnext);
+        next_slice(lane);
+    }
+};
+
+template <int KCE>
+__device__ __forceinline__ PMeta issue_pchunk(PWalker<KCE> &wk, uint32_t slotAddr, uint32_t barAddr, int lane, uint64_t streamPolicy)
+{
+    constexpr uint32_t kValBytes = static_cast<uint32_t>(slot_val_bytes(KCE));
+    PMeta m;
+    m.kc = 0; m.flags = 0; m.t = 0;
+    if (wk.switchesOwed > 0) { /* the consumer changes buffers here */
+        wk.switchesOwed -= 1;
+        m.flags = 4 | 8;
+        return m;
+    }
+    if (!wk.live) return m;
+    m.t = wk.t;
+    const unsigned char *src0, *src1;
+    uint32_t b0, b1;
+    m.flags = 4;
+    if (wk.ci < wk.nE) {
+        const int k = wk.ci * KCE;
+        m.kc = min(KCE, wk.w - k);
+        src0 = wk.base + static_cast<uint32_t>(k) * 512u;
+        b0 = static_cast<uint32_t>(m.kc) * 512u;
+        src1 = wk.base + static_cast<uint32_t>(wk.w) * 512u + static_cast<uint32_t>(k >> 2) * 512u;
+        b1 = static_cast<uint32_t>((m.kc + 3) >> 2) * 512u;
+    } else {
+        const int k = (wk.ci - wk.nE) * KCE;
+        const unsigned char *rem = wk.base + static_cast<uint32_t>(wk.w) * 512u + static_cast<uint32_t>((wk.w + 3) >> 2) * 512u;
+        m.kc = max(0, min(KCE, wk.wr - k));
+        m.flags |= 1;
+        src0 = rem + static_cast<uint32_t>(k) * 512u;
+        b0 = static_cast<uint32_t>(m.kc) * 512u;
+        src1 = rem + static_cast<uint32_t>(wk.wr) * 512u + static_cast<uint32_t>(k >> 2) * 512u;
+        b1 = static_cast<uint32_t>((m.kc + 3) >> 2) * 512u;
+    }
+    if (lane == 0 && b0) {
+        mbar_expect_tx(barAddr, b0 + b1);
+        if (streamPolicy) {
+            tma_bulk_g2s_hint(slotAddr, src0, b0, barAddr, streamPolicy);
+            tma_bulk_g2s_hint(slotAddr + kValBytes, src1, b1, barAddr, streamPolicy);
+        } else {
+            tma_bulk_g2s(slotAddr, src0, b0, barAddr);
+            tma_bulk_g2s(slotAddr + kValBytes, src1, b1, barAddr);
+        }
+    }
+    if (++wk.ci == wk.nc) {
+        m.flags |= 2;
+        wk.next_slice(lane);
+    }
+    return m;
+}
+
+template <int kMaxThreads, int KCE>
+__global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const MainArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr uint32_t kSlotBytes = static_cast<uint32_t>(slot_bytes(KCE));
+    constexpr uint32_t kSlotValBytes = static_cast<uint32_t>(slot_val_bytes(KCE));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = blockDim.x >> 5;
+    const int G = gridDim.x;
+    const int nj = (a.nPartsTotal - static_cast<int>(blockIdx.x) + G - 1) / G; /* partitions of this CTA (>= 1: grid <= nParts) */
+
+    /* header: [0,16) window bars, [16,32) cache bars, [32,48) empty bars, [64,448) slot bars,
+     * [448,576) slice counters, [576,1600) partition table */
+    const uint32_t hdr = smem_u32(smem);
+    int *counters = reinterpret_cast<int *>(smem + 448);
+    int *partTab = reinterpret_cast<int *>(smem + 576);
+    const uint32_t winBytes = (static_cast<uint32_t>(a.W + 2) * 8u + 127u) & ~127u;
+    const uint32_t cacheBytes = (static_cast<uint32_t>(a.cacheCap) * 8u + 127u) & ~127u;
+    const uint32_t bufBytes = winBytes + cacheBytes;
+    unsigned char *buf0 = smem + kPersistHeader;
+    const uint32_t slotBar0 = hdr + 64u + static_cast<uint32_t>(warp * kSlotsPerWarp) * 8u;
+    const uint32_t slot0 = smem_u32(buf0) + 2u * bufBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tid < nj) {
+        const int slotIdx = static_cast<int>(blockIdx.x) + G * tid;
+        const int p = a.order ? __ldg(a.order + slotIdx) : slotIdx;
+        const int4 d0 = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p);
+        const int4 d1 = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p + 1);
+        reinterpret_cast<int4 *>(partTab)[2 * tid] = d0;
+        reinterpret_cast<int4 *>(partTab)[2 * tid + 1] = d1;
+        counters[tid] = 0;
+    }
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(hdr + 8u * b, 1);                              /* window: the TMA issuer's arrive.expect_tx */
+            mbar_init(hdr + 16u + 8u * b, static_cast<uint32_t>(nw * 32)); /* cache: every lane arrives (through cp.async) */
+            mbar_init(hdr + 32u + 8u * b, static_cast<uint32_t>(nw)); /* empty: one arrival per warp */
+        }
+        for (int i = 0; i < nw * kSlotsPerWarp; ++i) mbar_init(hdr + 64u + i * 8u, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uint64_t streamPolicy = a.l2hint ? make_evict_first_policy() : 0ull;
+    const uint64_t keepPolicy = a.l2hint ? make_evict_last_policy() : 0ull;
+    PWalker<KCE> wk;
+    wk.start(partTab, counters, reinterpret_cast<const uint2 *>(a.slices), a.blob, nj, lane);
+    PMeta meta[2];
+    meta[0] = issue_pchunk(wk, slot0, slotBar0, lane, streamPolicy);
+    meta[1] = issue_pchunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane, streamPolicy);
+    uint32_t phases = 0;
+
+    asm volatile("griddepcontrol.wait;" ::: "memory"); /* x and y belong to the stream's previous work */
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+
+    /* Staging of partition jj of this CTA into buffer jj&1 - its window (TMA, warp 0) and this
+     * warp's share of its remainder cache - as a state machine that never blocks the warp's chunk
+     * stream (120 KB in flight per SM is just the latency-bandwidth product: a warp that waits takes
+     * its 5 KB out of flight).  One step per loop iteration:
+     *   state 1  buffer free? (every warp has left partition jj-2: `empty` barrier, polled) ->
+     *            warp 0 starts the window copy; fetch up to 4 list entries per lane (registers)
+     *   state 2  (an iteration later, the entries have arrived) start the 8-byte asynchronous x
+     *            gathers into the cache; more entries -> back to state 1', else arrive on the cache
+     *            barrier through cp.async (it completes when this lane's gathers have landed)
+     * force = true (at a partition switch): run to completion, waiting where necessary. */
+    int dutyState = 0, dutyJ = 0, dutyPos = 0;
+    int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
+    auto duty_begin = [&](int jj) { dutyState = 1; dutyJ = jj; dutyPos = 0; };
+    auto duty_step = [&](bool force) {
+        while (dutyState != 0) {
+            const int b = dutyJ & 1;
+            const int cacheStart = partTab[8 * dutyJ + 4], cacheCount = partTab[8 * dutyJ + 5];
+            if (dutyState == 1) {
+                if (dutyPos == 0) {
+                    if (dutyJ >= 2) {
+                        const uint32_t par = static_cast<uint32_t>(((dutyJ - 2) >> 1) & 1);
+                        if (force) mbar_wait_bounded(hdr + 32u + 8u * b, par);
+                        else if (!mbar_try_wait(hdr + 32u + 8u * b, par)) return;
+                    }
+                    if (warp == 0) {
+                        const int ps_ = partTab[8 * dutyJ];
+                        double *win = reinterpret_cast<double *>(buf0 + static_cast<size_t>(b) * bufBytes);
+                        const int g0 = ps_ & ~1;
+                        const int len = min(ps_ + a.W, a.n) - g0;
+                        if (tma_ok) {
+                            if (lane == 0) {
+                                if (len & 1) win[len - 1] = a.x[g0 + len - 1]; /* odd tail element, released by the arrive below */
+                                const uint32_t bulkBytes = static_cast<uint32_t>(len & ~1) * 8u;
+                                mbar_expect_tx(hdr + 8u * b, bulkBytes);
+                                const char *src = reinterpret_cast<const char *>(a.x + g0);
+                                const uint32_t dst = smem_u32(win);
+                                for (uint32_t off = 0; off < bulkBytes; off += 32768u) {
+                                    if (keepPolicy) tma_bulk_g2s_hint(dst + off, src + off, min(32768u, bulkBytes - off), hdr + 8u * b, keepPolicy);
+                                    else tma_bulk_g2s(dst + off, src + off, min(32768u, bulkBytes - off), hdr + 8u * b);
+                                }
+                            }
+                        } else { /* x not 16-byte aligned: plain copies by warp 0 */
+                            for (int i = lane; i < len; i += 32) win[i] = a.x[g0 + i];
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(hdr + 8u * b);
+                        }
+                    }
+                }
+                /* this warp's entries: groups of 32 dealt round-robin over the warps, 4 groups per step */
+                const int32_t *cols = a.cacheCols + cacheStart;
+                const int i0 = (dutyPos * nw + warp) * 32 + lane, stride = nw * 32;
+                dc0 = i0 < cacheCount ? __ldg(cols + i0) : -1;
+                dc1 = i0 + stride < cacheCount ? __ldg(cols + i0 + stride) : -1;
+                dc2 = i0 + 2 * stride < cacheCount ? __ldg(cols + i0 + 2 * stride) : -1;
+                dc3 = i0 + 3 * stride < cacheCount ? __ldg(cols + i0 + 3 * stride) : -1;
+                dutyState = 2;
+                if (!force) return; /* let the loads fly while a chunk is consumed */
+            }
+            if (dutyState == 2) {
+                const uint32_t cacheA = smem_u32(buf0) + static_cast<uint32_t>(b) * bufBytes + winBytes;
+                const int i0 = (dutyPos * nw + warp) * 32 + lane, stride = nw * 32;
+                if (dc0 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0) * 8u, a.x + dc0);
+                if (dc1 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + stride) * 8u, a.x + dc1);
+                if (dc2 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 2 * stride) * 8u, a.x + dc2);
+                if (dc3 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 3 * stride) * 8u, a.x + dc3);
+                dutyPos += 4;
+                if (dutyPos * nw * 32 < cacheCount) {
+                    dutyState = 1; /* more entries: next 4 groups */
+                } else {
+                    cp_async_mbar_arrive_noinc(hdr + 16u + 8u * b); /* every lane: arrives when its gathers have landed */
+                    dutyState = 0;
+                }
+            }
+        }
+    };
+
+    /* consumer state for partition jC */
+    int jC = 0;
+    int ps = partTab[0], pe = partTab[1];
+    uint32_t xsAddr = smem_u32(buf0) + static_cast<uint32_t>(ps - (ps & ~1)) * 8u;
+    uint32_t cacheAddr = smem_u32(buf0) + winBytes;
+    bool cacheReady = false;
+    duty_begin(0);
+    duty_step(true);
+    if (nj > 1) duty_begin(1);
+    mbar_wait_bounded(hdr + 0u, 0);
+
+    double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
+    int s = 0;
+#pragma unroll 1
+    for (;;) {
+        const PMeta m = s ? meta[1] : meta[0];
+        if (!(m.flags & 4)) break;
+        const uint32_t slot = slot0 + static_cast<uint32_t>(s) * kSlotBytes;
+        const uint32_t bar = slotBar0 + static_cast<uint32_t>(s) * 8u;
+        if (m.flags & 8) {
+            /* this warp is done with partition jC: stage jC+1's successor if it has not yet, tell
+             * the others, move to the other buffer */
+            duty_step(true); /* whatever is left of staging partition jC+1 */
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hdr + 32u + 8u * static_cast<uint32_t>(jC & 1));
+            jC += 1;
+            const uint32_t b = static_cast<uint32_t>(jC & 1), par = static_cast<uint32_t>((jC >> 1) & 1);
+            ps = partTab[8 * jC]; pe = partTab[8 * jC + 1];
+            xsAddr = smem_u32(buf0) + b * bufBytes + static_cast<uint32_t>(ps - (ps & ~1)) * 8u;
+            cacheAddr = smem_u32(buf0) + b * bufBytes + winBytes;
+            cacheReady = false;
+            if (jC + 1 < nj) duty_begin(jC + 1);
+            mbar_wait_bounded(hdr + 8u * b, par);
+        } else {
+            if (m.kc) {
+                mbar_wait_bounded(bar, (phases >> s) & 1u);
+                phases ^= 1u << s;
+                if ((m.flags & 1) && !cacheReady) {
+                    mbar_wait_bounded(hdr + 16u + 8u * static_cast<uint32_t>(jC & 1), static_cast<uint32_t>((jC >> 1) & 1));
+                    cacheReady = true;
+                }
+                const uint32_t vAddr = slot + static_cast<uint32_t>(lane) * 16u;
+                if (!(a.dbg & ((m.flags & 1) ? 1 : 2))) {
+                    const bool rem = (m.flags & 1) != 0;
+                    const uint32_t xb = rem ? cacheAddr : xsAddr;
+                    double s0 = rem ? r0 : acc0, s1 = rem ? r1 : acc1;
+                    const uint32_t cAddr = slot + kSlotValBytes + static_cast<uint32_t>(lane) * 16u;
+                    const int nfull = m.kc >> 2;
+#pragma unroll 2
+                    for (int g = 0; g < nfull; ++g) {
+                        const uint4 c = lds_u32x4(cAddr + g * 512u);
+                        const double2 v0 = lds_f64x2(vAddr + (4 * g + 0) * 512u);
+                        const double2 v1 = lds_f64x2(vAddr + (4 * g + 1) * 512u);
+                        const double2 v2 = lds_f64x2(vAddr + (4 * g + 2) * 512u);
+                        const double2 v3 = lds_f64x2(vAddr + (4 * g + 3) * 512u);
+                        const double x00 = lds_f64(xb + (c.x & 0xffffu) * 8u), x01 = lds_f64(xb + (c.z & 0xffffu) * 8u);
+                        const double x10 = lds_f64(xb + (c.x >> 16) * 8u), x11 = lds_f64(xb + (c.z >> 16) * 8u);
+                        const double x20 = lds_f64(xb + (c.y & 0xffffu) * 8u), x21 = lds_f64(xb + (c.w & 0xffffu) * 8u);
+                        const double x30 = lds_f64(xb + (c.y >> 16) * 8u), x31 = lds_f64(xb + (c.w >> 16) * 8u);
+                        s0 = fma(v0.x, x00, s0);
+                        s1 = fma(v0.y, x01, s1);
+                        s0 = fma(v1.x, x10, s0);
+                        s1 = fma(v1.y, x11, s1);
+                        s0 = fma(v2.x, x20, s0);
+                        s1 = fma(v2.y, x21, s1);
+                        s0 = fma(v3.x, x30, s0);
+                        s1 = fma(v3.y, x31, s1);
+                    }
+                    const int tail = m.kc & 3;
+                    if (tail) {
+                        const uint4 c = lds_u32x4(cAddr + nfull * 512u);
+                        const uint32_t cols0[3] = {c.x & 0xffffu, c.x >> 16, c.y & 0xffffu};
+                        const uint32_t cols1[3] = {c.z & 0xffffu, c.z >> 16, c.w & 0xffffu};
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            if (i < tail) {
+                                const double2 v = lds_f64x2(vAddr + (4 * nfull + i) * 512u);
+                                s0 = fma(v.x, lds_f64(xb + cols0[i] * 8u), s0);
+                                s1 = fma(v.y, lds_f64(xb + cols1[i] * 8u), s1);
+                            }
+                        }
+                    }
+                    if (rem) { r0 = s0; r1 = s1; } else { acc0 = s0; acc1 = s1; }
+                }
+            }
+            if (m.flags & 2) {
+                const int r = ps + m.t * EHYB_SLICE_ROWS + lane;
+                if (r < pe) a.y[r] = acc0 + r0;
+                if (r + 32 < pe) a.y[r + 32] = acc1 + r1;
+                acc0 = acc1 = r0 = r1 = 0.0;
+                /* after a slice of the partition: stage the next partition (waits for the buffer
+                 * if a warp is still in the partition before this one; the x gathers themselves
+                 * are asynchronous) */
+                if (!a.prologueBarrier) duty_step(true);
+            }
+        }
+        __syncwarp();
+        /* experiment switch (EHYB_PROLOGUE_BARRIER=1): the staging as a polled state machine, one
+         * step per chunk - measured slower (100.0 vs 94.9 us at P=592: its checks sit in the hot
+         * loop) */
+        if (a.prologueBarrier) duty_step(false);
+        const PMeta mn = issue_pchunk(wk, slot, bar, lane, streamPolicy);
+        if (s) meta[1] = mn; else meta[0] = mn;
+        s ^= 1;
+    }
+    /* (every warp has passed all nj-1 switch markers here: the walker always ends in the last
+     * partition, and a marker completes the staging it owes before it leaves a partition) */
+    duty_step(true);
 }
 
 /* ---------------------------------------------------------------- overflow kernel -- */

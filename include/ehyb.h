@@ -219,11 +219,14 @@ typedef struct ehyb_session_opts {
     int l2_persist_x;   /* L2 access-policy window on x for the remainder gathers (default 1) */
     int64_t halo_cols;  /* extra x entries after the n local ones (multi-GPU), default 0 */
     int kernel;         /* 0 = default, 1 = direct (matrix streamed with 128-bit global loads),
-                           2 = staged (matrix streamed through shared memory by TMA) */
+                           2 = staged (matrix streamed through shared memory by TMA),
+                           3 = persistent (staged, one CTA per SM over several partitions with
+                           the window + remainder cache double-buffered; single GPU) */
 } ehyb_session_opts;
 
 #define EHYB_KERNEL_DIRECT 1
 #define EHYB_KERNEL_STAGED 2
+#define EHYB_KERNEL_PERSISTENT 3
 
 void ehyb_session_opts_default(ehyb_session_opts *o);
 

@@ -147,3 +147,45 @@ def test_power_law_matrix_general_path(orc, min_coverage, partition):
     assert ms > 0
     util.assert_within_gate(m.vector_recover(s.get_y()), m.y_golden, m.vector_recover(orc.csr_abs_spmv(a["rowIdx"], a["J"], a["V"], m.vector_reorder(x))))
     s.free(); lay.free(); m.free()
+
+
+# the persistent kernel (one CTA per SM over several partitions, double-buffered window + cache):
+# more partitions than SMs, so that a CTA walks 2..5 partitions and the warps cross partition
+# boundaries, change buffers and stage the next partition while consuming the current one
+PERSISTENT_CASES = [
+    # kind, dims, nParts, W
+    ("st27", (48, 48, 48), 300, 448),      # ~2 partitions per CTA
+    ("st27", (48, 48, 48), 700, 192),      # ~5 partitions per CTA, small windows
+    ("lap2d", (256, 256), 444, 192),       # 3 per CTA, 5-point rows (2 chunks per slice)
+    ("elas", (16, 16, 16), 450, 64),       # window smaller than the partitions: rows beyond it, heavy remainder
+    ("st27", (32, 32, 32), 8, 4224),       # fewer partitions than SMs: one partition per CTA
+]
+
+
+@pytest.mark.parametrize("kind,dims,P,W", PERSISTENT_CASES)
+def test_persistent_kernel_bit_exact_and_gate(orc, kind, dims, P, W):
+    n = util.lower_entries(kind, dims)[0]
+    x = orc.x_reference(n)
+    m = util.product_pipeline(kind, dims, P, W, 1, x=x)
+    lay = api.Layout(m, er_fill=0.0, cache_cap=16384)
+    st = lay.stats()
+    xr = m.vector_reorder(x)
+    s3 = api.Session(lay, kernel=api.KERNEL_PERSISTENT)
+    s2 = api.Session(lay, kernel=api.KERNEL_STAGED)
+    y3 = s3.spmv_host(xr)
+    y2 = s2.spmv_host(xr)
+    a = m.arrays()
+    util.assert_within_gate(y3, orc.csr_spmv(a["rowIdx"], a["J"], a["V"], xr), orc.csr_abs_spmv(a["rowIdx"], a["J"], a["V"], xr))
+    if st["nOverflow"] == 0:
+        assert np.array_equal(y3, y2), "persistent and staged kernels differ"
+        mo, ro = util.oracle_pipeline(orc, kind, dims, P, W, x=x)
+        y_emul = orc.emulate(orc.convert(ro), ro, orc.vector_reorder(x, ro["reorderList"]), use_fma=True)
+        assert np.array_equal(y3, y_emul)
+    # repeated products (back to back, different x) and the timed loop
+    for seed in (1, 2):
+        xs = m.vector_reorder(util.x_random(n, seed))
+        assert np.array_equal(s3.spmv_host(xs), s2.spmv_host(xs)) or st["nOverflow"] > 0
+    s3.set_x(xr)
+    ms, kms = s3.time_spmv(3, 20, kernel_only=True)
+    assert ms > 0 and np.array_equal(s3.get_y(), y3) or st["nOverflow"] > 0
+    s2.free(); s3.free(); lay.free(); m.free()
