@@ -234,118 +234,3 @@ def setup_slab(rank, world, grid, dist, partition="metis", exchange="p2p"):
               "ehyb_partition_graph")
     blk.finish(pl.nParts, pl.W, pl.ctasPerPart, pv, exchange=exchange)
     return blk, rowStarts
-
-
-EXCHANGE_TEXT = {
-    "p2p": "inside the main kernel: x entries stored into the neighbours' halo buffers over NVLink (CUDA IPC peer "
-           "memory, epoch flags), halo columns served from the shared-memory remainder cache; one launch per product",
-    "nccl": "pack kernel + grouped ncclSend/ncclRecv per product, overlapped with the main kernel; halo entries in the "
-            "overflow kernel",
-}
-
-
-def bench(args, rank, world, local, grid, workload, scaling="weak"):
-    """bench.py at N > 1 (called under torchrun, process group already initialised)."""
-    import torch
-    import torch.distributed as dist
-    from bench import ClockSampler, measured_peaks, stdout_to_stderr
-
-    t0 = time.time()
-    exchange = os.environ.get("EHYB_MG_EXCHANGE", "p2p")
-    if exchange == "p2p":
-        # every rank must be able to map its neighbours' memory, else all fall back to NCCL
-        ok = torch.tensor([1 if p2p_supported(local, world) else 0], device="cuda")
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            raise SystemExit("bench.py: the GPUs of this box have no peer access; set EHYB_MG_EXCHANGE=nccl")
-    with stdout_to_stderr():
-        blk, rowStarts = setup_slab(rank, world, grid, dist, os.environ.get("EHYB_MG_PARTITION", "metis"), exchange)
-        if exchange == "p2p":
-            blk.create_session_p2p(local, dist)
-        else:
-            ids = [unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            blk.create_session(local, ids[0])
-    t_prep = time.time() - t0
-    r0 = int(rowStarts[rank])
-    x_nat = x_of_global(np.arange(r0, r0 + blk.n))
-    x_perm = np.empty(blk.n)
-    x_perm[blk.coo["reorderList"]] = x_nat
-    blk.set_x(x_perm)
-
-    # parity of one distributed product: CPU CSR of the permuted local block on [x_local | halo]
-    blk.spmv()
-    y = blk.get_y()
-    if blk.timed_out():
-        raise SystemExit("bench.py: rank %d: a neighbour did not deliver its halo" % rank)
-    from oracle import oracle as O
-    orc = O.Oracle()
-    x_ext = np.concatenate([x_perm, x_of_global(blk.haloGlobal)])
-    y_ref = orc.csr_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_ext)
-    absAx = orc.csr_abs_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_ext)
-    gate_fail = int(np.count_nonzero(~(np.abs(y - y_ref) <= 1e-12 * absAx)))
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = blk.time_spmv(args.warmup, args.steps)
-    torch.cuda.synchronize()
-    dist.barrier()
-    clocks = sampler.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    tot = torch.tensor([blk.stats["nnz"], blk.stats["algBytes"], gate_fail, blk.nHalo], dtype=torch.float64, device="cuda")
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    nnz_all, alg_all, gate_all, halo_all = (float(v) for v in tot.tolist())
-
-    # end to end: host x -> device, distributed product, y -> host, every step
-    lib = blk.lib
-    xe = np.zeros(blk.n + blk.nHalo); xe[:blk.n] = x_perm
-    yh = np.empty(blk.n)
-    xd = C.c_void_p(); yd = C.c_void_p()
-    lib.ehyb_session_vectors(blk.handle, C.byref(xd), C.byref(yd))
-    dist.barrier()
-    te = time.perf_counter()
-    for _ in range(args.steps):
-        check(lib, lib.ehyb_set_x(blk.handle, xe.ctypes.data_as(L.c_dbl_p)), "ehyb_set_x")
-        check(lib, lib.ehyb_mg_spmv(blk.session, xd, yd), "ehyb_mg_spmv")
-        check(lib, lib.ehyb_get_y(blk.handle, yh.ctypes.data_as(L.c_dbl_p)), "ehyb_get_y")
-    dist.barrier()
-    te = time.perf_counter() - te
-
-    ms_per_step = ms_max / args.steps
-    if rank == 0:
-        peaks, peak_src = measured_peaks()
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = blk.stats["algBytes"] / (ms_per_step * 1e6)
-        out = {
-            "metric": "fp64 SpMV GFLOP/s (2*nnz/t), EHYB format", "value": round(2.0 * nnz_all / (ms_per_step * 1e6), 2),
-            "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_per_step, 6), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "global_grid": [grid[0], grid[1], grid[2] * world],
-                       "decomposition": "z-slabs, one per GPU; level-2 partition per GPU: " + os.environ.get("EHYB_MG_PARTITION", "metis"),
-                       "n_per_gpu": blk.n, "nnz_total": int(nnz_all), "halo_x_entries_total": int(halo_all),
-                       "partitions_per_gpu": blk.stats["nParts"], "window": blk.stats["W"],
-                       "exchange": EXCHANGE_TEXT[exchange], "nnz_overflow_rank0": blk.stats["nOverflow"],
-                       "remainder_cache_max": blk.stats["cacheMax"],
-                       "l2": "matrix data per GPU larger than L2, no flush", "host_prep_s": round(t_prep, 1)},
-            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                         "kernel": "ehyb_staged_kernel",
-                         "note": "rank 0 algorithmic bytes / whole-step time (the step is the main kernel with the "
-                                 "exchange inside it)" if exchange == "p2p" else
-                                 "rank 0 algorithmic bytes / whole-step time (main kernel + exchange + overflow)"},
-            "e2e": {"value": round(2.0 * nnz_all * args.steps / te / 1e9, 2), "unit": "GFLOP/s",
-                    "h2d_bytes_per_step": 8 * (blk.n + blk.nHalo), "d2h_bytes_per_step": 8 * blk.n,
-                    "api": "ehyb_set_x + ehyb_mg_spmv + ehyb_get_y per step, per rank"},
-            "gpu_launches": args.steps * blk.launches_per_spmv(),
-            "clocks": clocks,
-            "parity": {"rows_outside_1e-12_gate_all_ranks": int(gate_all)},
-        }
-        print(json.dumps(out), flush=True)
-    blk.free()
-    dist.barrier()
-    dist.destroy_process_group()
