@@ -431,6 +431,13 @@ def run_reference(args):
     timed with every host thread.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    # every host thread this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    # would time the CPU baseline on one core (must be set before the OpenMP runtime of the oracle loads)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     from oracle import oracle as O
     orc = O.Oracle()
     n, li, lj, lv = O.gen_stencil27_lower(*GRID)
