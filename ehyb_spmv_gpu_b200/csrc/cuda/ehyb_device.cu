@@ -108,24 +108,16 @@ static main_kernel_t pick_kernel(int kernel, int threads, int ctasPerSM)
     return ehyb_main_kernel<1024, 1>;
 }
 
-struct StagedVariant {
-    int kc;
-    main_kernel_t k512, k768;
-};
-static const StagedVariant kStaged[] = {
-    {4, ehyb_staged_kernel<512, 4>, ehyb_staged_kernel<768, 4>}, /* default: 2.5 KB slots, most warps */
-    {8, ehyb_staged_kernel<512, 8>, ehyb_staged_kernel<768, 8>},
-    {16, ehyb_staged_kernel<512, 16>, ehyb_staged_kernel<768, 16>},
-};
+/* staged kernel builds: 4-column chunks (2.5 KB slots: most warps for the staging capacity; 8 and
+ * 16 columns measured slower), x2 register budgets, x2 with / without the multi-GPU code */
+static main_kernel_t staged_kernel(int threads, bool peer)
+{
+    if (peer) return threads <= 512 ? ehyb_staged_kernel<512, 4, true> : ehyb_staged_kernel<768, 4, true>;
+    return threads <= 512 ? ehyb_staged_kernel<512, 4, false> : ehyb_staged_kernel<768, 4, false>;
+}
+
 /* persistent, double-buffered variant (ehyb_persistent_kernel): 4-column chunks only */
 static main_kernel_t persistent_kernel(int threads) { return threads <= 512 ? ehyb_persistent_kernel<512, 4> : ehyb_persistent_kernel<768, 4>; }
-
-static const StagedVariant *staged_variant(int kc)
-{
-    for (size_t i = 0; i < sizeof kStaged / sizeof kStaged[0]; ++i)
-        if (kStaged[i].kc == kc) return &kStaged[i];
-    return &kStaged[0];
-}
 
 static int env_int(const char *name, int dflt)
 {
@@ -197,8 +189,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     }
     if (kernel == EHYB_KERNEL_STAGED) {
         /* warps = staging capacity: 2 slots each, as many as fit next to the window */
-        const StagedVariant *sv = staged_variant(env_int("EHYB_CHUNK", 4));
-        const int kc = sv->kc;
+        const int kc = 4;
         h->kcEll = kc;
         h->kcRem = kc;
         const size_t fixed = (size_t)kStageHeader + winBytes + cacheBytes;
@@ -266,12 +257,11 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
         CU(cudaFuncSetAttribute(persistent_kernel(t), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
         CU(cudaFuncSetAttribute(persistent_kernel(t), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
-    for (size_t i = 0; i < sizeof kStaged / sizeof kStaged[0]; ++i) {
-        CU(cudaFuncSetAttribute(kStaged[i].k512, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-        CU(cudaFuncSetAttribute(kStaged[i].k768, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-        CU(cudaFuncSetAttribute(kStaged[i].k512, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(cudaFuncSetAttribute(kStaged[i].k768, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
+    for (int t = 512; t <= 768; t += 256)
+        for (int peer = 0; peer < 2; ++peer) {
+            CU(cudaFuncSetAttribute(staged_kernel(t, peer != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+            CU(cudaFuncSetAttribute(staged_kernel(t, peer != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
 
     h->use_graph = o->use_graph;
     h->pdl = env_int("EHYB_PDL", 1);
@@ -342,13 +332,11 @@ extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, 
     return EHYB_OK;
 }
 
-static main_kernel_t main_kernel_of(const ehyb_handle *h)
+/* peer: the launch carries a halo exchange, or the session records a per-CTA trace */
+static main_kernel_t main_kernel_of(const ehyb_handle *h, bool peer)
 {
     if (h->kernel == EHYB_KERNEL_PERSISTENT) return persistent_kernel(h->threads);
-    if (h->kernel == EHYB_KERNEL_STAGED) {
-        const StagedVariant *sv = staged_variant(h->kcEll);
-        return h->threads <= 512 ? sv->k512 : sv->k768;
-    }
+    if (h->kernel == EHYB_KERNEL_STAGED) return staged_kernel(h->threads, peer || h->trace != NULL);
     return pick_kernel(h->kernel, h->threads, h->ctasPerSM);
 }
 
@@ -385,7 +373,7 @@ static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStrea
         return EHYB_OK;
     }
     const MainArgs a = main_args(h, x_d, y_d, pa);
-    main_kernel_t k = main_kernel_of(h);
+    main_kernel_t k = main_kernel_of(h, pa != NULL);
     if (h->kernel == EHYB_KERNEL_PERSISTENT && pa != NULL)
         return ehyb_fail(EHYB_ERR_ARG, "the persistent kernel does not carry the peer-memory exchange (multi-GPU sessions use the staged kernel)");
     if ((h->kernel == EHYB_KERNEL_STAGED || h->kernel == EHYB_KERNEL_PERSISTENT) && h->pdl) {
@@ -595,7 +583,7 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
     if (kernel_ms) {
         /* main kernel alone: one event pair per launch, summed */
         const MainArgs a = main_args(h, h->x, h->y, NULL);
-        main_kernel_t k = main_kernel_of(h);
+        main_kernel_t k = main_kernel_of(h, false);
         cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)iters * 2, sizeof(cudaEvent_t));
         if (!ev) return ehyb_fail(EHYB_ERR_NOMEM, "ehyb_time_spmv: out of memory");
         for (int i = 0; i < 2 * iters; ++i) cudaEventCreate(&ev[i]);

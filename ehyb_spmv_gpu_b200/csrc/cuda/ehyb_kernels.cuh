@@ -735,7 +735,10 @@ __device__ __forceinline__ ChunkMeta issue_chunk(ChunkWalker<KCE> &wk, uint32_t 
     return m;
 }
 
-template <int kMaxThreads, int KCE>
+/* PEER: the multi-GPU build of the kernel (halo push, halo columns in the cache fill, per-CTA
+ * trace).  Single-GPU sessions launch the PEER = false build, which is ~1 000 instructions
+ * shorter: on kernels whose CTAs live a few microseconds the code size is measurable. */
+template <int kMaxThreads, int KCE, bool PEER>
 __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -752,8 +755,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     const int ps = part.x, pe = part.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = blockDim.x >> 5;
-    const bool pusher = a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas && warp == nw - 1;
-    unsigned long long *tr = a.trace ? a.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+    const bool pusher = PEER && a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas && warp == nw - 1;
+    unsigned long long *tr = PEER && a.trace ? a.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
     if (tr && tid == 0) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -787,7 +790,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     const uint32_t slot0 = cacheAddr + cacheBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
     const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
     /* in a CTA that pushes halo values the last warp does only that; the others fill the cache */
-    const bool pushCta = a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas;
+    const bool pushCta = PEER && a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas;
     const int nFill = pushCta && nw > 1 ? nw - 1 : nw;
 
     /* Programmatic dependent launch: let the next grid in the stream start as soon as SMs free
@@ -854,7 +857,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
          * gathered once per CTA (ascending list: neighbouring lanes mostly share sectors; halo
          * columns, >= n, are its tail and wait for the neighbours' push) */
         if (!pusher || nFill == nw) {
-            fill_remainder_cache_warp(cache, a.cacheCols + part2.x, part2.y, a.x, a.n, a.peer, warp, nFill, lane);
+            if constexpr (PEER) {
+                fill_remainder_cache_warp(cache, a.cacheCols + part2.x, part2.y, a.x, a.n, a.peer, warp, nFill, lane);
+            } else { /* no exchange in this build: halo columns, if any, are the tail of x */
+                for (int i = warp * 32 + lane; i < part2.y; i += nw * 32) cache[i] = ld_gather_f64(a.x + __ldg(a.cacheCols + part2.x + i));
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(cacheBar);
         }
@@ -867,7 +874,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
         /* x not 16-byte aligned: plain copies and a CTA barrier */
         for (int i = tid; i < len; i += blockDim.x) win[i] = a.x[g0 + i];
         if (pusher) peer_push_send(a.peer, a.x, lane, pr);
-        fill_remainder_cache(cache, a.cacheCols + part2.x, part2.y, a.x, a.n, a.peer, tid, blockDim.x);
+        if constexpr (PEER) {
+            fill_remainder_cache(cache, a.cacheCols + part2.x, part2.y, a.x, a.n, a.peer, tid, blockDim.x);
+        } else {
+            for (int i = tid; i < part2.y; i += blockDim.x) cache[i] = ld_gather_f64(a.x + __ldg(a.cacheCols + part2.x + i));
+        }
         __syncthreads();
         cacheReady = true;
     }
@@ -1166,7 +1177,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
     __syncthreads();
 
     const uint64_t streamPolicy = a.l2hint ? make_evict_first_policy() : 0ull;
-    const uint64_t keepPolicy = a.l2hint ? make_evict_last_policy() : 0ull;
+    uint64_t keepPolicy; /* x window: evict-last with the L2 hints, normal priority without */
+    if (a.l2hint) keepPolicy = make_evict_last_policy();
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(keepPolicy));
     PWalker<KCE> wk;
     wk.start(partTab, counters, reinterpret_cast<const uint2 *>(a.slices), a.blob, nj, lane);
     PMeta meta[2];
@@ -1177,80 +1190,55 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
     asm volatile("griddepcontrol.wait;" ::: "memory"); /* x and y belong to the stream's previous work */
     const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
 
-    /* Staging of partition jj of this CTA into buffer jj&1 - its window (TMA, warp 0) and this
-     * warp's share of its remainder cache - as a state machine that never blocks the warp's chunk
-     * stream (120 KB in flight per SM is just the latency-bandwidth product: a warp that waits takes
-     * its 5 KB out of flight).  One step per loop iteration:
-     *   state 1  buffer free? (every warp has left partition jj-2: `empty` barrier, polled) ->
-     *            warp 0 starts the window copy; fetch up to 4 list entries per lane (registers)
-     *   state 2  (an iteration later, the entries have arrived) start the 8-byte asynchronous x
-     *            gathers into the cache; more entries -> back to state 1', else arrive on the cache
-     *            barrier through cp.async (it completes when this lane's gathers have landed)
-     * force = true (at a partition switch): run to completion, waiting where necessary. */
-    int dutyState = 0, dutyJ = 0, dutyPos = 0;
-    int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
-    auto duty_begin = [&](int jj) { dutyState = 1; dutyJ = jj; dutyPos = 0; };
-    auto duty_step = [&](bool force) {
-        while (dutyState != 0) {
-            const int b = dutyJ & 1;
-            const int cacheStart = partTab[8 * dutyJ + 4], cacheCount = partTab[8 * dutyJ + 5];
-            if (dutyState == 1) {
-                if (dutyPos == 0) {
-                    if (dutyJ >= 2) {
-                        const uint32_t par = static_cast<uint32_t>(((dutyJ - 2) >> 1) & 1);
-                        if (force) mbar_wait_bounded(hdr + 32u + 8u * b, par);
-                        else if (!mbar_try_wait(hdr + 32u + 8u * b, par)) return;
-                    }
-                    if (warp == 0) {
-                        const int ps_ = partTab[8 * dutyJ];
-                        double *win = reinterpret_cast<double *>(buf0 + static_cast<size_t>(b) * bufBytes);
-                        const int g0 = ps_ & ~1;
-                        const int len = min(ps_ + a.W, a.n) - g0;
-                        if (tma_ok) {
-                            if (lane == 0) {
-                                if (len & 1) win[len - 1] = a.x[g0 + len - 1]; /* odd tail element, released by the arrive below */
-                                const uint32_t bulkBytes = static_cast<uint32_t>(len & ~1) * 8u;
-                                mbar_expect_tx(hdr + 8u * b, bulkBytes);
-                                const char *src = reinterpret_cast<const char *>(a.x + g0);
-                                const uint32_t dst = smem_u32(win);
-                                for (uint32_t off = 0; off < bulkBytes; off += 32768u) {
-                                    if (keepPolicy) tma_bulk_g2s_hint(dst + off, src + off, min(32768u, bulkBytes - off), hdr + 8u * b, keepPolicy);
-                                    else tma_bulk_g2s(dst + off, src + off, min(32768u, bulkBytes - off), hdr + 8u * b);
-                                }
-                            }
-                        } else { /* x not 16-byte aligned: plain copies by warp 0 */
-                            for (int i = lane; i < len; i += 32) win[i] = a.x[g0 + i];
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(hdr + 8u * b);
-                        }
-                    }
+    /* Staging of partition dutyJ of this CTA into buffer dutyJ&1: its window (TMA, warp 0) and this
+     * warp's share of its remainder cache.  Waits until every warp has left partition dutyJ-2
+     * (`empty` barrier), fetches the warp's list entries four groups at a time and gathers x with
+     * asynchronous 8-byte copies; every lane then arrives on the cache barrier through cp.async
+     * (the arrival completes when its gathers have landed), so the warp does not wait for them.
+     * Inlined at two places only (start-up and one site in the loop): the code size of this kernel
+     * matters (a polled, non-blocking variant with checks in every iteration measured slower). */
+    int dutyState = 0, dutyJ = 0; /* dutyState 1: partition dutyJ still has to be staged by this warp */
+    auto duty_begin = [&](int jj) { dutyState = 1; dutyJ = jj; };
+    auto duty_run = [&]() {
+        const int b = dutyJ & 1;
+        const int cacheStart = partTab[8 * dutyJ + 4], cacheCount = partTab[8 * dutyJ + 5];
+        if (dutyJ >= 2) mbar_wait_bounded(hdr + 32u + 8u * b, static_cast<uint32_t>(((dutyJ - 2) >> 1) & 1));
+        if (warp == 0) {
+            const int ps_ = partTab[8 * dutyJ];
+            double *win = reinterpret_cast<double *>(buf0 + static_cast<size_t>(b) * bufBytes);
+            const int g0 = ps_ & ~1;
+            const int len = min(ps_ + a.W, a.n) - g0;
+            if (tma_ok) {
+                if (lane == 0) {
+                    if (len & 1) win[len - 1] = a.x[g0 + len - 1]; /* odd tail element, released by the arrive below */
+                    const uint32_t bulkBytes = static_cast<uint32_t>(len & ~1) * 8u;
+                    mbar_expect_tx(hdr + 8u * b, bulkBytes);
+                    const char *src = reinterpret_cast<const char *>(a.x + g0);
+                    const uint32_t dst = smem_u32(win);
+                    for (uint32_t off = 0; off < bulkBytes; off += 32768u) tma_bulk_g2s_hint(dst + off, src + off, min(32768u, bulkBytes - off), hdr + 8u * b, keepPolicy);
                 }
-                /* this warp's entries: groups of 32 dealt round-robin over the warps, 4 groups per step */
-                const int32_t *cols = a.cacheCols + cacheStart;
-                const int i0 = (dutyPos * nw + warp) * 32 + lane, stride = nw * 32;
-                dc0 = i0 < cacheCount ? __ldg(cols + i0) : -1;
-                dc1 = i0 + stride < cacheCount ? __ldg(cols + i0 + stride) : -1;
-                dc2 = i0 + 2 * stride < cacheCount ? __ldg(cols + i0 + 2 * stride) : -1;
-                dc3 = i0 + 3 * stride < cacheCount ? __ldg(cols + i0 + 3 * stride) : -1;
-                dutyState = 2;
-                if (!force) return; /* let the loads fly while a chunk is consumed */
-            }
-            if (dutyState == 2) {
-                const uint32_t cacheA = smem_u32(buf0) + static_cast<uint32_t>(b) * bufBytes + winBytes;
-                const int i0 = (dutyPos * nw + warp) * 32 + lane, stride = nw * 32;
-                if (dc0 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0) * 8u, a.x + dc0);
-                if (dc1 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + stride) * 8u, a.x + dc1);
-                if (dc2 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 2 * stride) * 8u, a.x + dc2);
-                if (dc3 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 3 * stride) * 8u, a.x + dc3);
-                dutyPos += 4;
-                if (dutyPos * nw * 32 < cacheCount) {
-                    dutyState = 1; /* more entries: next 4 groups */
-                } else {
-                    cp_async_mbar_arrive_noinc(hdr + 16u + 8u * b); /* every lane: arrives when its gathers have landed */
-                    dutyState = 0;
-                }
+            } else { /* x not 16-byte aligned: plain copies by warp 0 */
+                for (int i = lane; i < len; i += 32) win[i] = a.x[g0 + i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(hdr + 8u * b);
             }
         }
+        const int32_t *cols = a.cacheCols + cacheStart;
+        const uint32_t cacheA = smem_u32(buf0) + static_cast<uint32_t>(b) * bufBytes + winBytes;
+        const int stride = nw * 32;
+        for (int i0 = warp * 32 + lane; i0 < cacheCount; i0 += 4 * stride) {
+            /* this warp's entries: groups of 32 dealt round-robin over the warps, 4 groups per round */
+            const int c0 = __ldg(cols + i0);
+            const int c1 = i0 + stride < cacheCount ? __ldg(cols + i0 + stride) : -1;
+            const int c2 = i0 + 2 * stride < cacheCount ? __ldg(cols + i0 + 2 * stride) : -1;
+            const int c3 = i0 + 3 * stride < cacheCount ? __ldg(cols + i0 + 3 * stride) : -1;
+            cp_async_8(cacheA + static_cast<uint32_t>(i0) * 8u, a.x + c0);
+            if (c1 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + stride) * 8u, a.x + c1);
+            if (c2 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 2 * stride) * 8u, a.x + c2);
+            if (c3 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 3 * stride) * 8u, a.x + c3);
+        }
+        cp_async_mbar_arrive_noinc(hdr + 16u + 8u * b); /* every lane: arrives when its gathers have landed */
+        dutyState = 0;
     };
 
     /* consumer state for partition jC */
@@ -1260,9 +1248,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
     uint32_t cacheAddr = smem_u32(buf0) + winBytes;
     bool cacheReady = false;
     duty_begin(0);
-    duty_step(true);
+    duty_run();
     if (nj > 1) duty_begin(1);
     mbar_wait_bounded(hdr + 0u, 0);
+    bool dutyDue = false; /* set at the end of a slice: stage the next partition at the top of the next iteration */
 
     double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
     int s = 0;
@@ -1272,10 +1261,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
         if (!(m.flags & 4)) break;
         const uint32_t slot = slot0 + static_cast<uint32_t>(s) * kSlotBytes;
         const uint32_t bar = slotBar0 + static_cast<uint32_t>(s) * 8u;
+        /* the staging of the next partition, at its single site in the loop: after this warp's
+         * first slice of the current partition, at the latest before it leaves the partition */
+        if (dutyState != 0 && (dutyDue || (m.flags & 8))) duty_run();
+        dutyDue = false;
         if (m.flags & 8) {
-            /* this warp is done with partition jC: stage jC+1's successor if it has not yet, tell
-             * the others, move to the other buffer */
-            duty_step(true); /* whatever is left of staging partition jC+1 */
+            /* this warp is done with partition jC: tell the others, move to the other buffer */
             __syncwarp();
             if (lane == 0) mbar_arrive(hdr + 32u + 8u * static_cast<uint32_t>(jC & 1));
             jC += 1;
@@ -1343,24 +1334,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
                 if (r < pe) a.y[r] = acc0 + r0;
                 if (r + 32 < pe) a.y[r + 32] = acc1 + r1;
                 acc0 = acc1 = r0 = r1 = 0.0;
-                /* after a slice of the partition: stage the next partition (waits for the buffer
-                 * if a warp is still in the partition before this one; the x gathers themselves
-                 * are asynchronous) */
-                if (!a.prologueBarrier) duty_step(true);
+                dutyDue = true;
             }
         }
         __syncwarp();
-        /* experiment switch (EHYB_PROLOGUE_BARRIER=1): the staging as a polled state machine, one
-         * step per chunk - measured slower (100.0 vs 94.9 us at P=592: its checks sit in the hot
-         * loop) */
-        if (a.prologueBarrier) duty_step(false);
         const PMeta mn = issue_pchunk(wk, slot, bar, lane, streamPolicy);
         if (s) meta[1] = mn; else meta[0] = mn;
         s ^= 1;
     }
     /* (every warp has passed all nj-1 switch markers here: the walker always ends in the last
      * partition, and a marker completes the staging it owes before it leaves a partition) */
-    duty_step(true);
 }
 
 /* ---------------------------------------------------------------- overflow kernel -- */
