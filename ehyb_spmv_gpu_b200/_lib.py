@@ -116,13 +116,13 @@ EXPORTS = [
     "mm_read_mtx_crd_entry", "mm_read_mtx_crd_data", "mm_write_mtx_crd", "mm_read_unsymmetric_sparse",
     # ehyb.h
     "ehyb_last_error", "ehyb_version", "ehyb_device_count", "ehyb_device_query", "ehyb_device_info_b200",
-    "ehyb_plan", "ehyb_plan_reference", "ehyb_build_graph", "ehyb_set_partitioner", "ehyb_partition_graph",
+    "ehyb_plan", "ehyb_plan_kernel", "ehyb_plan_reference", "ehyb_build_graph", "ehyb_set_partitioner", "ehyb_partition_graph",
     "ehyb_reorder_with_partition", "ehyb_reorder", "ehyb_partition_blocks", "ehyb_free_host",
     "ehyb_layout_build", "ehyb_layout_build_csr", "ehyb_layout_get", "ehyb_layout_to_reference",
     "ehyb_layout_free", "ehyb_layout_save", "ehyb_layout_load", "ehyb_cache_save", "ehyb_cache_load",
     "ehyb_session_opts_default", "ehyb_upload", "ehyb_spmv", "ehyb_spmv_host",
     "ehyb_spmv_host_batch", "ehyb_session_vectors", "ehyb_set_x", "ehyb_get_y", "ehyb_time_spmv",
-    "ehyb_launches_per_spmv", "ehyb_pcg_opts_default", "ehyb_pcg_solve", "ehyb_session_size", "ehyb_trace_read", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
+    "ehyb_launches_per_spmv", "ehyb_pcg_opts_default", "ehyb_pcg_solve", "ehyb_session_size", "ehyb_session_kernel", "ehyb_trace_read", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
     "ehyb_gen_lower", "ehyb_coo_from_lower", "ehyb_coo_from_general", "ehyb_gen_rmat", "ehyb_x_reference",
     "ehyb_read_mtx", "ehyb_write_mtx", "ehyb_coo_free",
     "ehyb_mg_local_build", "ehyb_mg_local_halo", "ehyb_mg_local_set_send", "ehyb_mg_local_graph",
@@ -154,6 +154,8 @@ def load(path: Path | None = None, check_exports: bool = True) -> C.CDLL:
             raise ImportError(f"{p} does not export: {', '.join(missing)}")
     lib.ehyb_last_error.restype = C.c_char_p
     lib.ehyb_version.restype = C.c_char_p
+    if hasattr(lib, "ehyb_session_kernel"):
+        lib.ehyb_session_kernel.restype = C.c_char_p
     if hasattr(lib, "ehyb_stream"):
         lib.ehyb_stream.restype = C.c_void_p
     if path is None:

@@ -43,11 +43,13 @@ def device_query(device: int = 0) -> DeviceInfo:
     return d
 
 
-def plan(n: int, dev: DeviceInfo | None = None) -> Plan:
+def plan(n: int, dev: DeviceInfo | None = None, kernel: int = 2) -> Plan:
+    """ehyb_plan_kernel: partition parameters for the staged kernel (default; what the multi-GPU
+    blocks use) or, with kernel=KERNEL_PERSISTENT, for the persistent kernel of single-GPU sessions."""
     lib = L.load()
     p = Plan()
     dev = dev or device_info_b200()
-    check(lib, lib.ehyb_plan(n, C.byref(dev), C.byref(p)), "ehyb_plan")
+    check(lib, lib.ehyb_plan_kernel(n, C.byref(dev), int(kernel), C.byref(p)), "ehyb_plan_kernel")
     return p
 
 
@@ -405,6 +407,9 @@ class Session:
               "ehyb_pcg_solve")
         return x, dict(iters=r.iters, converged=bool(r.converged), rel_residual=r.rel_residual,
                        true_rel_residual=r.true_rel_residual, ms=r.ms)
+
+    def kernel_name(self) -> str:
+        return self.lib.ehyb_session_kernel(self.h).decode()
 
     def launches_per_spmv(self) -> int:
         return int(self.lib.ehyb_launches_per_spmv(self.h))

@@ -162,7 +162,11 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     h->n = v->n; h->ncols = v->ncols + (o->halo_cols > 0 && v->ncols == v->n ? o->halo_cols : 0);
     h->nnz = v->nnz; h->nOvf = v->nOverflow; h->blobBytes = v->blobBytes; h->algBytes = v->algBytes;
     h->nParts = v->nParts; h->W = v->W; h->kpp = v->ctasPerPart > 0 ? v->ctasPerPart : 1; h->nSlices = v->nSlices;
-    int kernel = o->kernel > 0 ? o->kernel : env_int("EHYB_KERNEL", EHYB_KERNEL_STAGED);
+    /* default: the persistent kernel where the layout was planned for it (>= 3 partitions per SM,
+     * one CTA per partition, room for >= 16 warps next to its two buffers), else the staged one */
+    int kernel = o->kernel > 0 ? o->kernel : env_int("EHYB_KERNEL", 0);
+    const int autoKernel = kernel <= 0;
+    if (autoKernel) kernel = v->nParts >= 3 * prop.multiProcessorCount ? EHYB_KERNEL_PERSISTENT : EHYB_KERNEL_STAGED;
     int threads = o->threads > 0 ? o->threads : env_int("EHYB_THREADS", 0);
     const size_t winBytes = (((size_t)v->W + 2) * sizeof(double) + 127) & ~(size_t)127;
     h->cacheCap = (v->cacheMax + 15) & ~15;
@@ -177,7 +181,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
         int nw = fixed + perWarp <= prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - fixed) / perWarp) : 0;
         if (nw > kMaxStageWarps) nw = kMaxStageWarps;
         if (threads > 0 && threads / 32 < nw) nw = threads / 32 > 0 ? threads / 32 : 1;
-        if (h->kpp != 1 || (h->nParts + grid - 1) / grid > kMaxPartsPerCta || nw < 8) {
+        if (h->kpp != 1 || (h->nParts + grid - 1) / grid > kMaxPartsPerCta || nw < (autoKernel ? 16 : 8)) {
             kernel = EHYB_KERNEL_STAGED;
         } else {
             h->kcEll = h->kcRem = 4;
@@ -622,6 +626,13 @@ extern "C" int ehyb_trace_read(ehyb_handle *h, unsigned long long *out, int *cta
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(out, h->trace, sizeof(unsigned long long) * 8 * (size_t)*ctas, cudaMemcpyDeviceToHost));
     return EHYB_OK;
+}
+
+extern "C" const char *ehyb_session_kernel(const ehyb_handle *h)
+{
+    if (!h) return "";
+    if (h->skipMain) return "ehyb_overflow_kernel";
+    return h->kernel == EHYB_KERNEL_PERSISTENT ? "ehyb_persistent_kernel" : h->kernel == EHYB_KERNEL_STAGED ? "ehyb_staged_kernel" : "ehyb_main_kernel";
 }
 
 extern "C" int ehyb_session_size(const ehyb_handle *h, int64_t *n, int64_t *ncols)

@@ -48,11 +48,23 @@ static int env_int(const char *name, int dflt)
 
 #define EHYB_SMEM_RESERVE 512 /* mbarriers in front of the window */
 
-int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out)
+int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out) { return ehyb_plan_kernel(n, dev, EHYB_KERNEL_STAGED, out); }
+
+/*
+ * kernel = EHYB_KERNEL_PERSISTENT: partitions sized for the persistent kernel, which holds TWO
+ * {window, remainder cache} buffers next to its staging slots and hides the partition start-up:
+ * three partitions per SM instead of two (config 2: 92.2 us vs 94.3 us staged) and a window of at
+ * most ~6 K entries, so that two buffers leave room for >= 16 warps of staging (256^3: 805 us vs
+ * 840 us).  Matrices too small for three partitions of minRows rows per SM get the staged plan;
+ * ehyb_upload falls back to the staged kernel by itself when the persistent one does not fit
+ * (very long remainder-cache lists).
+ */
+int ehyb_plan_kernel(int n, const ehyb_device_info *dev, int kernel, ehyb_plan_t *out)
 {
     if (n <= 0 || !dev || !out || dev->sm_count <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan: bad argument");
     const int sms = dev->sm_count;
-    int partsPerSM = env_int("EHYB_PARTS_PER_SM", 2);
+    const int persistent = kernel == EHYB_KERNEL_PERSISTENT && (double)n / (3.0 * sms) >= 2048.0 && !getenv("EHYB_PARTS_PER_SM");
+    int partsPerSM = env_int("EHYB_PARTS_PER_SM", persistent ? 3 : 2);
     int ctasPerSM = env_int("EHYB_CTAS_PER_SM", 1);
     int threads = env_int("EHYB_THREADS", 0);
     /* shared memory next to the window: staging slots of the matrix stream (what is in flight
@@ -68,6 +80,12 @@ int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out)
     if (budget > dev->smem_optin_bytes) budget = dev->smem_optin_bytes;
     budget -= staging;
     int wMax = (int)((budget - EHYB_SMEM_RESERVE) / 8 - 2);
+    if (persistent) {
+        /* two buffers of window + ~24 KB of cache next to 16 warps x 2 slots of 2.5 KB and the header */
+        const long two = (long)dev->smem_optin_bytes - 1664 - 16L * 2 * 2560;
+        const int wP = (int)((two / 2 - 24 * 1024) / 8 - 2);
+        if (wP < wMax) wMax = wP;
+    }
     wMax -= wMax % 64;
     if (wMax > 65536) wMax = 65536;
     if (wMax < 64) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan: no shared memory for a window");

@@ -77,9 +77,9 @@ static void session_on_layout(const ehyb_layout *L, const double *vectorIn, doub
     int64_t smem = 0;
     ehyb_session_info(h, &threads, &ctas, &grid, &smem, &persist);
     printf("EHYB-B200: %d partitions x %d CTA, window %d (%lld B smem), %d threads/CTA, %d CTA/SM, %d slices, "
-           "overflow %lld entries, L2 window on x %s\n",
+           "overflow %lld entries, L2 window on x %s, kernel %s (grid %d)\n",
            v.nParts, v.ctasPerPart, v.W, (long long)smem, threads, ctas, v.nSlices, (long long)v.nOverflow,
-           persist ? "on" : "off");
+           persist ? "on" : "off", ehyb_session_kernel(h), grid);
 
     if (ehyb_set_x(h, vectorIn)) ehyb_die("spmvGPuEHYB: H2D");
     float ms = 0.f, kms = 0.f;

@@ -82,6 +82,13 @@ static int finish(int n, const double *yReorder, const int *reorderList, const d
     return failed;
 }
 
+/* Which kernel the partitions are sized for (single GPU).  The persistent kernel double-buffers
+ * window + remainder cache, which pays for matrices with short remainder lists (stencils: config 2
+ * 92.2 us vs 94.3 us, 256^3 809 vs 840 us); with ~80 entries per row (3-dof elasticity) the lists
+ * are too long for two buffers, the session falls back to the staged kernel, and the finer
+ * partitioning then costs (config 3: 428 us vs 403 us): those keep the staged plan. */
+static int plan_kernel_for(int64_t n, int64_t nnz) { return nnz <= 40 * n ? EHYB_KERNEL_PERSISTENT : EHYB_KERNEL_STAGED; }
+
 static void usage(void)
 {
     printf("usage: spmv.out -i <iterations> (-m <name> | -M <file.mtx> | -g lap2d:NX:NY | -g st27:NX:NY:NZ | -g elas:NX:NY:NZ)\n"
@@ -146,7 +153,7 @@ int main(int argc, char *argv[])
             ehyb_layout_get(L, &v);
             ehyb_plan_t want;
             if (useRefPlan) ehyb_plan_reference(n, sym, &want);
-            else ehyb_plan(n, &dev, &want);
+            else ehyb_plan_kernel(n, &dev, plan_kernel_for(n, v.nnz), &want);
             if (oP > 0) want.nParts = oP;
             if (oW > 0) want.W = oW;
             if (oK > 0) want.ctasPerPart = oK;
@@ -224,7 +231,7 @@ int main(int argc, char *argv[])
     /* ------------------------------- partition parameters ------------------------------- */
     ehyb_plan_t plan;
     if (useRefPlan) ehyb_plan_reference(A.dimension, symmetric, &plan);
-    else ehyb_plan(A.dimension, &dev, &plan);
+    else ehyb_plan_kernel(A.dimension, &dev, plan_kernel_for(A.dimension, A.totalNum), &plan);
     if (oP > 0) plan.nParts = oP;
     if (oW > 0) plan.W = oW;
     if (oK > 0) plan.ctasPerPart = oK;

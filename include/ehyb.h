@@ -64,6 +64,10 @@ int ehyb_device_query(int device, ehyb_device_info *out);
 /* Nominal B200 values, so that host-side planning and format build can run without a GPU. */
 void ehyb_device_info_b200(ehyb_device_info *out);
 
+#define EHYB_KERNEL_DIRECT 1
+#define EHYB_KERNEL_STAGED 2
+#define EHYB_KERNEL_PERSISTENT 3
+
 typedef struct ehyb_plan_t {
     int nParts;      /* P */
     int W;           /* x window length in elements (vectorCacheSize) */
@@ -74,6 +78,10 @@ typedef struct ehyb_plan_t {
 
 /* B200 plan from the matrix size and the device (replaces solver_test.c:158-182). */
 int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out);
+/* The same for a given kernel (EHYB_KERNEL_* below; ehyb_plan = the staged kernel, which the
+ * multi-GPU sessions use): EHYB_KERNEL_PERSISTENT sizes the partitions for the persistent kernel
+ * of single-GPU sessions (three or more smaller partitions per SM), see plan.c. */
+int ehyb_plan_kernel(int n, const ehyb_device_info *dev, int kernel, ehyb_plan_t *out);
 /* The reference's own heuristic for an 82/80-SM, 93 KB device, including its int16_t wrap
  * (SURVEY.md Appendix C).  ctasPerPart = 0 where the reference leaves it uninitialised. */
 int ehyb_plan_reference(int n, int symmetric, ehyb_plan_t *out);
@@ -218,15 +226,13 @@ typedef struct ehyb_session_opts {
     int use_graph;      /* capture the per-product launches in a CUDA graph (default 1) */
     int l2_persist_x;   /* L2 access-policy window on x for the remainder gathers (default 1) */
     int64_t halo_cols;  /* extra x entries after the n local ones (multi-GPU), default 0 */
-    int kernel;         /* 0 = default, 1 = direct (matrix streamed with 128-bit global loads),
+    int kernel;         /* 0 = default (persistent where the layout allows it, else staged),
+                           1 = direct (matrix streamed with 128-bit global loads),
                            2 = staged (matrix streamed through shared memory by TMA),
                            3 = persistent (staged, one CTA per SM over several partitions with
                            the window + remainder cache double-buffered; single GPU) */
 } ehyb_session_opts;
 
-#define EHYB_KERNEL_DIRECT 1
-#define EHYB_KERNEL_STAGED 2
-#define EHYB_KERNEL_PERSISTENT 3
 
 void ehyb_session_opts_default(ehyb_session_opts *o);
 
@@ -293,6 +299,8 @@ void ehyb_pcg_opts_default(ehyb_pcg_opts *o);
  * in the same numbering for Jacobi preconditioning, or NULL for plain CG. */
 int ehyb_pcg_solve(ehyb_handle *h, const double *diag_h, const double *b_h, double *x_h, const ehyb_pcg_opts *opts,
                    ehyb_pcg_result *res);
+/* name of the kernel that computes the session's products */
+const char *ehyb_session_kernel(const ehyb_handle *h);
 /* rows and columns of the session's operator */
 int ehyb_session_size(const ehyb_handle *h, int64_t *n, int64_t *ncols);
 
