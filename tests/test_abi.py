@@ -69,6 +69,15 @@ def test_version_plan_and_errors(lib):
     assert small.nParts * small.ctasPerPart >= 148
     rc = lib.ehyb_plan(0, C.byref(d), C.byref(p))
     assert rc == -1 and b"ehyb_plan" in lib.ehyb_last_error()
+    # the plan for the persistent kernel: three or more partitions per SM, windows small enough that
+    # two {window, 24 KB cache} buffers leave 16 warps of staging; small matrices keep the staged plan
+    for n in (1048576, 2097152, 16777216):
+        st, pe = api.plan(n, d), api.plan(n, d, kernel=api.KERNEL_PERSISTENT)
+        assert pe.nParts % 148 == 0 and pe.nParts >= 3 * 148 and pe.nParts > st.nParts and pe.ctasPerPart == 1
+        assert pe.W % 64 == 0 and pe.W >= n / pe.nParts and 2 * (pe.W * 8 + 24 * 1024) + 16 * 2 * 2560 + 1664 <= d.smem_optin_bytes
+        assert (pe.nParts + 147) // 148 <= 32
+    sp = api.plan(20000, d, kernel=api.KERNEL_PERSISTENT)
+    assert (sp.nParts, sp.W, sp.ctasPerPart) == (small.nParts, small.W, small.ctasPerPart)
 
 
 def test_no_gpu_means_loud_failure(lib):
