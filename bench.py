@@ -6,15 +6,20 @@
 
 A step is one y = A x product.  Workload at every N: BASELINE.json configs[1], the 3-D
 27-point stencil 128^3 (n 2 097 152, nnz 55 742 968, fp64) PER GPU: at N > 1 the global grid
-is 128 x 128 x 128N, rank r owns z-slab r (weak scaling) and exchanges its x halo planes with
-its neighbours every product (NCCL send/recv inside libehyb.so).  Inputs are resident in HBM
-when the timed region starts; the matrix data (~600 MB) is larger than L2 (126 MB).
+is 128 x 128 x 128N, rank r owns z-slab r (weak scaling) and the x halo planes are exchanged
+every product INSIDE the main kernel (stores into the neighbours' memory over NVLink, CUDA IPC;
+EHYB_MG_EXCHANGE=nccl selects the NCCL send/recv baseline).  Inputs are resident in HBM when the
+timed region starts; the matrix data (~600 MB) is larger than L2 (126 MB).
+EHYB_BENCH_GRID=NXxNYxNZ [EHYB_BENCH_SCALING=strong] runs other grids / one global grid cut into
+slabs (BASELINE.json configs[4] at a size the host pipeline holds).
 
 The JSON line carries: value (GFLOP/s = 2 nnz / t, all ranks), roofline (algorithmic bytes of
-the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json), e2e (the same
-metric through the host-buffer entry point, H2D of x and D2H of y inside the timed region),
-cpu_baseline (the oracle's CSR product on the host cores; rank 0, N=1 only), clocks.
-`--impl reference` times the reference's CPU path (CSR over its own arrays, all host threads).
+the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json; traffic = DRAM bytes
+per launch from the committed ncu capture), e2e (the same metric through the host-buffer entry
+point, H2D of x and D2H of y inside the timed region), cpu_baseline (the oracle's CSR product on
+the host cores; rank 0, N=1 only), comparisons (cuSPARSE CSR on the same GPU, after the timed
+region), clocks.  `--impl reference` times the reference's CPU path (CSR over its own arrays, all
+host threads).  The oracle is used only as checker and CPU baseline, never on the product path.
 """
 from __future__ import annotations
 
