@@ -15,6 +15,30 @@ sys.path.insert(0, str(ROOT))
 os.environ.setdefault("EHYB_MTMETIS_BIN", str(ROOT / "bin" / "ehyb_mtmetis"))
 
 
+def setup_oneway(rank, world, dist, exchange, n_local=6000):
+    """A block lower-bidiagonal random matrix: rank r references its own columns and columns of
+    rank r-1 only.  The halo dependencies are ONE-WAY (rank 0 sends and never receives, the last
+    rank receives and never sends): the flag protocol must still pair every sender with its
+    receiver for the reuse of the halo buffers."""
+    from ehyb_spmv_gpu_b200 import api
+    from ehyb_spmv_gpu_b200 import multigpu as mg
+    rng = np.random.default_rng(100 + rank)
+    rowStarts = np.arange(world + 1, dtype=np.int64) * n_local
+    r0 = int(rowStarts[rank])
+    cols, vals, rowPtr = [], [], [0]
+    for i in range(n_local):
+        own = np.unique(np.concatenate([[i], rng.integers(max(0, i - 40), min(n_local, i + 40), 6)])) + r0
+        ext = np.unique(rng.integers(0, n_local, 3)) + (r0 - n_local) if rank > 0 and i % 3 == 0 else np.zeros(0, np.int64)
+        c = np.concatenate([ext, own]).astype(np.int64)
+        cols.append(c); vals.append(rng.uniform(-1, 1, len(c))); rowPtr.append(rowPtr[-1] + len(c))
+    blk = mg.DistributedBlock(rank, world, rowStarts, np.array(rowPtr, np.int64), np.concatenate(cols), np.concatenate(vals))
+    blk.exchange_lists(dist)
+    assert (blk.nHalo > 0) == (rank > 0) and (int(blk.sendCount.sum()) > 0) == (rank < world - 1)
+    pl = api.plan(blk.n, api.device_query(rank))
+    blk.finish(pl.nParts, pl.W, pl.ctasPerPart, None, exchange=exchange)
+    return blk, rowStarts
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -24,13 +48,16 @@ def main():
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     exchange, partition = sys.argv[1], sys.argv[2]
-    grid = tuple(int(v) for v in sys.argv[3].split("x"))
+    grid = tuple(int(v) for v in sys.argv[3].split("x")) if "x" in sys.argv[3] else None
     products = int(sys.argv[4]) if len(sys.argv) > 4 else 7
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     if exchange == "p2p":
         assert mg.p2p_supported(rank, world), "no peer access between the GPUs of this box"
-    blk, rowStarts = mg.setup_slab(rank, world, grid, dist, partition, exchange)
+    if partition == "oneway":
+        blk, rowStarts = setup_oneway(rank, world, dist, exchange)
+    else:
+        blk, rowStarts = mg.setup_slab(rank, world, grid, dist, partition, exchange)
     if exchange == "p2p":
         blk.create_session_p2p(rank, dist)
         assert blk.launches_per_spmv() == 1 + (1 if blk.stats["nOverflow"] else 0)

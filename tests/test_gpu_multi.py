@@ -33,6 +33,8 @@ CASES = [
     ("p2p", "blocks", "10x9x5"),     # tiny: a few partitions, several CTAs each, one pushing CTA
     ("p2p", "metis", "24x20x9"),
     ("p2p", "metis", "64x64x24"),    # ~100 k rows per rank: many partitions, several pushing CTAs
+    ("p2p", "oneway", "-"),          # rank r needs x from rank r-1 only: one-way halo dependencies
+    ("nccl", "oneway", "-"),
     ("nccl", "metis", "24x20x9"),
     ("nccl", "blocks", "64x64x24"),
 ]
