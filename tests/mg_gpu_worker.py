@@ -31,10 +31,16 @@ def setup_oneway(rank, world, dist, exchange, n_local=6000):
         ext = np.unique(rng.integers(0, n_local, 3)) + (r0 - n_local) if rank > 0 and i % 3 == 0 else np.zeros(0, np.int64)
         c = np.concatenate([ext, own]).astype(np.int64)
         cols.append(c); vals.append(rng.uniform(-1, 1, len(c))); rowPtr.append(rowPtr[-1] + len(c))
-    blk = mg.DistributedBlock(rank, world, rowStarts, np.array(rowPtr, np.int64), np.concatenate(cols), np.concatenate(vals))
+    rowPtr, cols, vals = np.array(rowPtr, np.int64), np.concatenate(cols), np.concatenate(vals)
+    blk = mg.DistributedBlock(rank, world, rowStarts, rowPtr, cols, vals)
+    blk.rows_global = (rowPtr, cols, vals)   # for reference products in the tests
     blk.exchange_lists(dist)
     assert (blk.nHalo > 0) == (rank > 0) and (int(blk.sendCount.sum()) > 0) == (rank < world - 1)
-    pl = api.plan(blk.n, api.device_query(rank))
+    try:
+        dev = api.device_query(rank)
+    except Exception:                        # the CPU (gloo) tier: nominal B200
+        dev = api.device_info_b200()
+    pl = api.plan(blk.n, dev)
     blk.finish(pl.nParts, pl.W, pl.ctasPerPart, None, exchange=exchange)
     return blk, rowStarts
 

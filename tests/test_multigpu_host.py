@@ -18,7 +18,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("world,partition,exchange", [(2, "blocks", "nccl"), (3, "blocks", "p2p"), (2, "metis", "p2p"),
-                                                      (2, "metis", "nccl")])
+                                                      (2, "metis", "nccl"), (3, "oneway", "p2p"), (3, "oneway", "nccl")])
 def test_distributed_product_gloo(world, partition, exchange):
     if partition == "metis" and not (ROOT / "bin" / "ehyb_mtmetis").exists():
         pytest.skip("bin/ehyb_mtmetis not built")
