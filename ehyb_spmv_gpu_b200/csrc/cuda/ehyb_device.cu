@@ -45,6 +45,7 @@ struct ehyb_handle {
     double *ovfVal;
     int32_t *cacheCols;
     int32_t *order;      /* CTA slot -> partition (NULL: identity), see ehyb_staged_kernel */
+    int32_t *ctaTab;     /* persistent kernel: partition table in CTA-slot order (8 ints per slot) */
     unsigned long long *trace; /* development: per-CTA timeline of the last product (EHYB_TRACE=1) */
     int cacheCap;        /* elements of the shared-memory remainder cache */
     int smCount;
@@ -55,7 +56,20 @@ struct ehyb_handle {
     cudaGraphExec_t gexec;
     const double *gx;
     double *gy;
+    /* multi-GPU, peer-memory exchange: word in mapped pinned host memory that a kernel sets when a
+     * wait on a neighbour ran into the time limit (sticky); NULL for single-GPU sessions */
+    volatile uint32_t *peerStatus_h;
+    int forcePeerBuild; /* development ($EHYB_FORCE_PEER_BUILD): single-GPU sessions run the multi-GPU build of the kernel */
 };
+
+/* after a synchronisation: a product whose halo never arrived must not pass for a result */
+static int peer_check(const ehyb_handle *h)
+{
+    if (h->peerStatus_h && *h->peerStatus_h)
+        return ehyb_fail(EHYB_ERR_PEER, "a neighbour GPU did not deliver (or release) its halo within the time limit "
+                                        "($EHYB_P2P_TIMEOUT_MS): the products since then are not valid");
+    return EHYB_OK;
+}
 
 extern "C" int ehyb_device_count(int *count)
 {
@@ -117,7 +131,35 @@ static main_kernel_t staged_kernel(int threads, bool peer)
 }
 
 /* persistent, double-buffered variant (ehyb_persistent_kernel): 4-column chunks only */
-static main_kernel_t persistent_kernel(int threads) { return threads <= 512 ? ehyb_persistent_kernel<512, 4> : ehyb_persistent_kernel<768, 4>; }
+static main_kernel_t persistent_kernel(int threads, bool peer)
+{
+    if (peer) return threads <= 512 ? ehyb_persistent_kernel<512, 4, true> : ehyb_persistent_kernel<768, 4, true>;
+    return threads <= 512 ? ehyb_persistent_kernel<512, 4, false> : ehyb_persistent_kernel<768, 4, false>;
+}
+
+/* The persistent kernel's partition table: slot s = c + grid*j is the j-th partition of CTA c;
+ * row = {rowStart, rowEnd, sliceStart, sliceEnd, cacheStart, cacheCount, flags, 0}, flags bit 0 =
+ * the partition's cache list reaches into the halo columns (>= n).  order == NULL: identity. */
+static int build_cta_tab(ehyb_handle *h, const ehyb_layout_view *v, const int32_t *order)
+{
+    const size_t P = (size_t)h->nParts;
+    int32_t *tab = (int32_t *)malloc(P * 8 * sizeof(int32_t));
+    if (!tab) return ehyb_fail(EHYB_ERR_NOMEM, "partition table: out of memory");
+    for (size_t s = 0; s < P; ++s) {
+        const ehyb_part_desc *d = &v->parts[order ? order[s] : (int32_t)s];
+        int32_t *t = tab + 8 * s;
+        t[0] = d->rowStart; t[1] = d->rowEnd; t[2] = d->sliceStart; t[3] = d->sliceEnd;
+        t[4] = d->cacheStart; t[5] = d->cacheCount;
+        t[6] = d->cacheCount > 0 && v->cacheCols[d->cacheStart + d->cacheCount - 1] >= v->n ? 1 : 0;
+        t[7] = 0;
+    }
+    cudaError_t e = cudaSuccess;
+    if (!h->ctaTab) e = cudaMalloc(&h->ctaTab, P * 8 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(h->ctaTab, tab, P * 8 * sizeof(int32_t), cudaMemcpyHostToDevice);
+    free(tab);
+    if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "partition table: %s", cudaGetErrorString(e));
+    return EHYB_OK;
+}
 
 static int env_int(const char *name, int dflt)
 {
@@ -132,7 +174,7 @@ extern "C" void ehyb_free(ehyb_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     cudaFree(h->parts); cudaFree(h->slices); cudaFree(h->blob);
-    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->trace);
+    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->ctaTab); cudaFree(h->trace);
     cudaFree(h->x); cudaFree(h->y);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->xb[i]); cudaFree(h->yb[i]);
@@ -172,16 +214,16 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     h->cacheCap = (v->cacheMax + 15) & ~15;
     const size_t cacheBytes = ((size_t)h->cacheCap * sizeof(double) + 127) & ~(size_t)127;
     if (kernel == EHYB_KERNEL_PERSISTENT) {
-        /* one CTA per SM over several partitions, {window, cache} double-buffered: needs one CTA
-         * per partition, at most kMaxPartsPerCta partitions per CTA and room for >= 8 warps of
-         * staging next to the two buffers; otherwise the staged kernel */
+        /* one CTA per SM over all of its partitions, {window, cache} double-buffered: needs one CTA
+         * per partition and room for >= 8 warps of staging next to the two buffers (16 to be chosen
+         * by default); otherwise the staged kernel */
         const int grid = h->nParts < prop.multiProcessorCount ? h->nParts : prop.multiProcessorCount;
         const size_t fixed = (size_t)kPersistHeader + 2 * (winBytes + cacheBytes);
         const size_t perWarp = (size_t)kSlotsPerWarp * slot_bytes(4);
         int nw = fixed + perWarp <= prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - fixed) / perWarp) : 0;
         if (nw > kMaxStageWarps) nw = kMaxStageWarps;
         if (threads > 0 && threads / 32 < nw) nw = threads / 32 > 0 ? threads / 32 : 1;
-        if (h->kpp != 1 || (h->nParts + grid - 1) / grid > kMaxPartsPerCta || nw < (autoKernel ? 16 : 8)) {
+        if (h->kpp != 1 || nw < (autoKernel ? 16 : 8)) {
             kernel = EHYB_KERNEL_STAGED;
         } else {
             h->kcEll = h->kcRem = 4;
@@ -257,9 +299,14 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    for (int t = 512; t <= 768; t += 256) {
-        CU(cudaFuncSetAttribute(persistent_kernel(t), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-        CU(cudaFuncSetAttribute(persistent_kernel(t), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (int t = 512; t <= 768; t += 256)
+        for (int peer = 0; peer < 2; ++peer) {
+            CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+            CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+    if (kernel == EHYB_KERNEL_PERSISTENT) {
+        int rcTab = build_cta_tab(h, v, NULL);
+        if (rcTab) return rcTab;
     }
     for (int t = 512; t <= 768; t += 256)
         for (int peer = 0; peer < 2; ++peer) {
@@ -269,6 +316,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
 
     h->use_graph = o->use_graph;
     h->pdl = env_int("EHYB_PDL", 1);
+    h->forcePeerBuild = env_int("EHYB_FORCE_PEER_BUILD", 0);
     h->dbgSkip = env_int("EHYB_DEBUG_SKIP", 0); /* development: timing experiments without the arithmetic */
     h->haloInOverflow = v->haloInOverflow;
     /* nothing lives in slices (layout.c: coverage below min_coverage, everything in the COO list):
@@ -339,7 +387,7 @@ extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, 
 /* peer: the launch carries a halo exchange, or the session records a per-CTA trace */
 static main_kernel_t main_kernel_of(const ehyb_handle *h, bool peer)
 {
-    if (h->kernel == EHYB_KERNEL_PERSISTENT) return persistent_kernel(h->threads);
+    if (h->kernel == EHYB_KERNEL_PERSISTENT) return persistent_kernel(h->threads, peer || h->trace != NULL || h->forcePeerBuild);
     if (h->kernel == EHYB_KERNEL_STAGED) return staged_kernel(h->threads, peer || h->trace != NULL);
     return pick_kernel(h->kernel, h->threads, h->ctasPerSM);
 }
@@ -359,6 +407,7 @@ static MainArgs main_args(const ehyb_handle *h, const double *x_d, double *y_d, 
     a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
     a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = h->dbgSkip; a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
     a.order = h->order;
+    a.ctaTab = h->ctaTab;
     a.nPartsTotal = h->nParts;
     a.l2hint = h->l2hint;
     a.dynamicDeal = h->dynamicDeal;
@@ -378,8 +427,6 @@ static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStrea
     }
     const MainArgs a = main_args(h, x_d, y_d, pa);
     main_kernel_t k = main_kernel_of(h, pa != NULL);
-    if (h->kernel == EHYB_KERNEL_PERSISTENT && pa != NULL)
-        return ehyb_fail(EHYB_ERR_ARG, "the persistent kernel does not carry the peer-memory exchange (multi-GPU sessions use the staged kernel)");
     if ((h->kernel == EHYB_KERNEL_STAGED || h->kernel == EHYB_KERNEL_PERSISTENT) && h->pdl) {
         /* programmatic dependent launch: this grid may start while the previous kernel of the
          * stream drains; it orders itself with griddepcontrol.wait before touching x or y */
@@ -482,7 +529,7 @@ extern "C" int ehyb_sync(ehyb_handle *h)
     if (!h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_sync: NULL");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
-    return EHYB_OK;
+    return peer_check(h);
 }
 
 extern "C" void *ehyb_stream(ehyb_handle *h) { return h ? (void *)h->stream : NULL; }
@@ -510,7 +557,7 @@ extern "C" int ehyb_get_y(ehyb_handle *h, double *y_h)
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(y_h, h->y, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return EHYB_OK;
+    return peer_check(h);
 }
 
 extern "C" int ehyb_spmv_host(ehyb_handle *h, const double *x_h, double *y_h)
@@ -755,7 +802,8 @@ struct ehyb_mg_session {
     double **pushDst_d[2];       /* device: [nSend] destination of every send-list entry, per parity */
     uint32_t **peerFlag_d;       /* device: [nPeers] flags[my rank][0] on every neighbour */
     int32_t *peerPushCtas_d;     /* device: [nranks] pushing CTAs of every rank (flag words to poll) */
-    uint32_t *status_d;
+    uint32_t *status_d;          /* device view of status_h */
+    uint32_t *status_h;          /* mapped pinned host word, see ehyb_handle.peerStatus_h */
     uint32_t epoch, recvMask, nbrMask;
     int nPeers, pushCtas, connected;
     unsigned long long timeoutNs;
@@ -793,7 +841,8 @@ extern "C" void ehyb_mg_session_free(ehyb_mg_session *s)
         free(s->peerBase);
     }
     cudaFree(s->shared); cudaFree(s->pushDst_d[0]); cudaFree(s->pushDst_d[1]); cudaFree(s->peerFlag_d);
-    cudaFree(s->peerPushCtas_d); cudaFree(s->status_d);
+    cudaFree(s->peerPushCtas_d);
+    if (s->status_h) { if (s->h) s->h->peerStatus_h = NULL; cudaFreeHost(s->status_h); }
     cudaFree(s->sendIdx_d); cudaFree(s->sendBuf_d);
     if (s->evX) cudaEventDestroy(s->evX);
     if (s->evHalo) cudaEventDestroy(s->evHalo);
@@ -824,7 +873,10 @@ static int mg_session_base(const ehyb_mg_local *L, int rank, int nranks, int dev
     ehyb_session_opts o;
     ehyb_session_opts_default(&o);
     o.device = device;
-    o.kernel = EHYB_KERNEL_STAGED; /* the halo push and pull live in the staged kernel */
+    /* the halo push and pull live in the persistent and in the staged kernel; the direct one is
+     * not a choice here.  Default (0): persistent where the layout allows it ($EHYB_MG_KERNEL) */
+    o.kernel = env_int("EHYB_MG_KERNEL", 0);
+    if (o.kernel == EHYB_KERNEL_DIRECT) o.kernel = EHYB_KERNEL_STAGED;
     rc = ehyb_upload(layout, &o, &s->h);
     if (rc) { free(s); return rc; }
     auto body = [&]() -> int {
@@ -934,26 +986,36 @@ extern "C" int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int 
         s->sharedBytes = (2 * s->haloStride + flagsBytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
         CU(cudaMalloc(&s->shared, s->sharedBytes));
         CU(cudaMemset(s->shared, 0, s->sharedBytes));
-        CU(cudaMalloc(&s->status_d, 256));
-        CU(cudaMemset(s->status_d, 0, 256));
+        CU(cudaHostAlloc((void **)&s->status_h, 256, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(s->status_h, 0, 256);
+        CU(cudaHostGetDevicePointer((void **)&s->status_d, s->status_h, 0));
+        s->h->peerStatus_h = s->status_h;
         CU(cudaDeviceSynchronize());
-        s->timeoutNs = (unsigned long long)env_int("EHYB_P2P_TIMEOUT_MS", 10000) * 1000000ull;
+        /* time limit of every wait on a neighbour = bound on the launch skew between the ranks
+         * (0: no limit) */
+        const int toMs = env_int("EHYB_P2P_TIMEOUT_MS", 10000);
+        s->timeoutNs = toMs > 0 ? (unsigned long long)toMs * 1000000ull : 0ull;
         /* the CTAs that push (their last warp does) are resident in the first wave of the main
          * kernel: at most one per SM and no more than the grid; >= 64 entries each */
         ehyb_handle *h = s->h;
+        if (h->kernel == EHYB_KERNEL_DIRECT) return ehyb_fail(EHYB_ERR_LIMIT, "the window leaves no room for the staging slots: no kernel with the halo exchange fits");
         int64_t ctas = (s->nSend + 63) / 64;
         if (env_int("EHYB_P2P_PUSH_CTAS", 0) > 0) ctas = env_int("EHYB_P2P_PUSH_CTAS", 0);
-        const int64_t grid = (int64_t)h->nParts * h->kpp;
-        if (ctas > grid) ctas = grid;
+        if (ctas > h->grid) ctas = h->grid;
         if (ctas > h->smCount) ctas = h->smCount;
         if (ctas > kMaxPushCtas) ctas = kMaxPushCtas;
         if (ctas < 1) ctas = 1;
         s->pushCtas = (int)ctas;
-        /* dispatch order (CTAs start in blockIdx order): a first wave of partitions WITHOUT halo
-         * columns in their remainder cache (the lists are ascending, so the last entry tells) -
-         * these CTAs push, nobody in them waits; then the partitions that need halo values, by
-         * which time the neighbours' push of this product has arrived; then the rest, so that
-         * the tail of the kernel is made of ordinary partitions */
+        /* Dispatch order.  Partitions WITH halo columns in their remainder cache (the lists are
+         * ascending, so the last entry tells) wait for the neighbours' push of this product; the
+         * CTAs that push must not.
+         *   staged kernel (CTAs start in blockIdx order): a first wave of partitions without halo
+         *     columns - these CTAs push, nobody in them waits -, then the partitions that need halo
+         *     values, by which time the neighbours' push has arrived, then the rest, so that the
+         *     tail of the kernel is made of ordinary partitions;
+         *   persistent kernel (slot c + grid*j = j-th partition of CTA c): all the partitions
+         *     without halo columns first, the others last - every CTA meets them at the end of its
+         *     list, when the neighbours have long delivered. */
         ehyb_layout_view v;
         int rc2 = ehyb_layout_get(layout, &v);
         if (rc2) return rc2;
@@ -963,6 +1025,7 @@ extern "C" int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int 
         const int reorder = env_int("EHYB_P2P_ORDER", 1);
         int firstWave = h->smCount * h->ctasPerSM / h->kpp;
         if (firstWave < 1) firstWave = 1;
+        if (h->kernel == EHYB_KERNEL_PERSISTENT) firstWave = h->nParts;
         int nPlain = 0;
         for (int p = 0; p < h->nParts; ++p) {
             const int cnt = v.parts[p].cacheCount;
@@ -973,6 +1036,10 @@ extern "C" int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int 
         for (int pass = 0; pass < 3; ++pass)
             for (int p = 0; p < h->nParts; ++p)
                 if (cls[p] == pass) order[k++] = p;
+        if (h->kernel == EHYB_KERNEL_PERSISTENT) {
+            rc2 = build_cta_tab(h, &v, order);
+            if (rc2) { free(order); free(cls); return rc2; }
+        }
         free(cls);
         cudaError_t e = cudaMalloc(&h->order, sizeof(int32_t) * (size_t)h->nParts);
         if (e == cudaSuccess) e = cudaMemcpy(h->order, order, sizeof(int32_t) * (size_t)h->nParts, cudaMemcpyHostToDevice);
@@ -1075,10 +1142,8 @@ extern "C" int ehyb_mg_status(ehyb_mg_session *s, int *timed_out)
     *timed_out = 0;
     if (s->exchange != EHYB_MG_P2P) return EHYB_OK;
     CU(cudaSetDevice(s->h->device));
-    uint32_t st = 0;
     CU(cudaStreamSynchronize(s->h->stream));
-    CU(cudaMemcpy(&st, s->status_d, sizeof st, cudaMemcpyDeviceToHost));
-    *timed_out = st != 0;
+    *timed_out = *(volatile uint32_t *)s->status_h != 0;
     return EHYB_OK;
 }
 

@@ -75,6 +75,7 @@ struct MainArgs {
     const int32_t *cacheCols; /* per-partition remainder cache lists (permuted columns) */
     int cacheCap;             /* shared-memory cache capacity in elements (>= longest list) */
     const int32_t *order;     /* CTA slot -> partition (NULL: identity) */
+    const int32_t *ctaTab;    /* persistent kernel: the partition table in CTA order, 8 ints per slot (see there) */
     int prologueBarrier;      /* staged kernel, experiments: CTA barrier after window + cache staging */
     int dynamicDeal;          /* staged kernel: slices beyond the first nw are taken on demand (shared-memory counter) */
     int l2hint;               /* staged kernel: L2 eviction hints on the TMA copies (stream evict-first, x evict-last) */
@@ -196,11 +197,14 @@ __device__ __forceinline__ int2 ld_stream_s32x2(const int2 *p, uint64_t pol)
     return v;
 }
 
-/* x gather of the remainder: read-only path, default caching (x is the L2-resident vector) */
+/* x gather of the remainder: a COHERENT load served by L2 (ld.global.cg).  Not the read-only
+ * (.nc) path: under programmatic dependent launch this kernel is already resident while the
+ * stream's previous kernel still writes x (a solver's vector update), and .nc requires data that
+ * is read-only for the whole lifetime of the kernel.  Every gather happens once per CTA. */
 __device__ __forceinline__ double ld_gather_f64(const double *p)
 {
     double v;
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -227,9 +231,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 
 /* Warp-collective (all 32 lanes, converged): waits until the first `firstOnly ? 1 : pushCtas(g)`
  * flag words of every rank g in `mask` show `epoch` or later (flags only grow; compared modulo
- * 2^32).  Bounded: a peer that never shows up sets *status instead of hanging the GPU, and the
- * host reports it (ehyb_mg_status). */
-__device__ __noinline__ void peer_wait(const uint32_t *flags, uint32_t mask, int nranks, const int32_t *peerPushCtas, bool firstOnly,
+ * 2^32).  Bounded (timeoutNs != 0): a peer that does not show up within the limit sets *status
+ * - sticky, read by the host after every synchronisation: ehyb_sync, ehyb_get_y and the timed
+ * loops then fail with EHYB_ERR_PEER - and the function returns false: the caller must not push
+ * into a buffer the neighbour may still read.  The limit therefore also bounds the launch skew
+ * between the ranks; timeoutNs == 0 waits without limit. */
+__device__ __noinline__ bool peer_wait(const uint32_t *flags, uint32_t mask, int nranks, const int32_t *peerPushCtas, bool firstOnly,
                                        uint32_t epoch, unsigned long long timeoutNs, uint32_t *status)
 {
     const int lane = threadIdx.x & 31;
@@ -244,13 +251,14 @@ __device__ __noinline__ void peer_wait(const uint32_t *flags, uint32_t mask, int
             if (__all_sync(0xffffffffu, ok)) break;
             const unsigned long long now = global_timer_ns();
             if (t0 == 0) t0 = now;
-            if (__any_sync(0xffffffffu, now - t0 > timeoutNs)) {
-                if (lane == 0) atomicExch(status, 1u);
-                return;
+            if (timeoutNs != 0 && __any_sync(0xffffffffu, now - t0 > timeoutNs)) {
+                if (lane == 0) atomicExch_system(status, 1u);
+                return false;
             }
             __nanosleep(64);
         }
     }
+    return true;
 }
 
 /* halo value of column c >= n: written by a peer over NVLink, L2 is the point of coherence */
@@ -293,13 +301,14 @@ struct PushRegs {
     int idx[4];
     unsigned long long dst[4];
     int i0, i1;
+    bool ok; /* the neighbours are done with the halo buffer of this parity */
 };
 
 __device__ __forceinline__ void peer_push_prepare(const PeerArgs &pa, int lane, PushRegs &pr)
 {
     /* the neighbours' halo buffer of this parity was last read by their product epoch-2, which
      * is complete once any of their CTAs has signalled epoch-1 (it passed its dependency wait) */
-    peer_wait(pa.flags, pa.nbrMask, pa.nranks, pa.peerPushCtas, true, pa.epoch - 1u, pa.timeoutNs, pa.status);
+    pr.ok = peer_wait(pa.flags, pa.nbrMask, pa.nranks, pa.peerPushCtas, true, pa.epoch - 1u, pa.timeoutNs, pa.status);
     const int chunk = (pa.pushCount + pa.pushCtas - 1) / pa.pushCtas;
     pr.i0 = static_cast<int>(blockIdx.x) * chunk;
     pr.i1 = min(pr.i0 + chunk, pa.pushCount);
@@ -314,6 +323,9 @@ __device__ __forceinline__ void peer_push_prepare(const PeerArgs &pa, int lane, 
 
 __device__ __forceinline__ void peer_push_send(const PeerArgs &pa, const double *x, int lane, const PushRegs &pr)
 {
+    /* a neighbour that never released the buffer (time limit, *status set): neither data nor flag -
+     * it would overwrite values still being read; the neighbours' waits then fail loudly as well */
+    if (!pr.ok) return;
     double v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = ld_gather_f64(x + pr.idx[u]);
@@ -340,6 +352,39 @@ __device__ __forceinline__ void peer_push_send(const PeerArgs &pa, const double 
     __syncwarp(); /* every lane's stores are ordered before lane j's release below */
     if (lane < pa.nPeers) st_release_sys_u32(pa.peerFlag[lane] + blockIdx.x, pa.epoch);
     for (int j = 32 + lane; j < pa.nPeers; j += 32) st_release_sys_u32(pa.peerFlag[j] + blockIdx.x, pa.epoch);
+}
+
+/* The same push without registers held across the dependency wait (persistent kernel: its register
+ * budget is the consumer loop's): `ok` = result of the release check, made before the wait. */
+__device__ __forceinline__ bool peer_push_check(const PeerArgs &pa)
+{
+    return peer_wait(pa.flags, pa.nbrMask, pa.nranks, pa.peerPushCtas, true, pa.epoch - 1u, pa.timeoutNs, pa.status);
+}
+
+__device__ __noinline__ void peer_push_all(const PeerArgs &pa, const double *x, int lane, bool ok)
+{
+    if (!ok) return; /* see peer_push_send */
+    const int chunk = (pa.pushCount + pa.pushCtas - 1) / pa.pushCtas;
+    const int i0 = static_cast<int>(blockIdx.x) * chunk, i1 = min(i0 + chunk, pa.pushCount);
+    const unsigned long long *dstTab = reinterpret_cast<const unsigned long long *>(pa.pushDst);
+    for (int base = i0; base < i1; base += 128) {
+        int idx[4];
+        unsigned long long dst[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * 32 + lane;
+            idx[u] = i < i1 ? __ldg(pa.pushIdx + i) : 0;
+            dst[u] = i < i1 ? __ldg(dstTab + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_gather_f64(x + idx[u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (dst[u]) *reinterpret_cast<double *>(dst[u]) = v[u];
+    }
+    __syncwarp(); /* every lane's stores are ordered before lane j's release below */
+    for (int j = lane; j < pa.nPeers; j += 32) st_release_sys_u32(pa.peerFlag[j] + blockIdx.x, pa.epoch);
 }
 
 /* one ELL group: 4 columns x 2 rows per lane */
@@ -966,24 +1011,34 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
  * The staged kernel stops the matrix stream of an SM for ~6 us at every partition boundary (CTA
  * exit + start, descriptor chain, window + cache staging: per-CTA timeline in
  * profiles/r1_notes.md), while HBM delivers ~7.5 TB/s in the steady phase.  This variant keeps
- * ONE CTA per SM alive over several (smaller) partitions and double-buffers the explicit cache:
+ * ONE CTA per SM alive over ALL of its partitions and double-buffers the explicit cache:
  *
  *   - shared memory holds two {x window, remainder cache} buffers; while the warps consume
  *     partition j from buffer j&1, partition j+1 is staged into the other one: the window by a
  *     TMA bulk copy (warp 0), the cache by every warp's share of the gathers, both right after a
  *     warp's first slice of partition j ("duty"), behind the `empty` mbarrier that tells that
  *     every warp has left partition j-1;
- *   - a warp's chunk stream does not know partition boundaries: when its walker runs out of
- *     slices in partition j it goes on issuing chunks of partition j+1 (slices are dealt from one
- *     shared-memory counter per partition), with a "switch" marker in the two-slot pipeline
- *     where the consumer has to change buffers;
+ *   - the slices of a CTA's partitions form ONE sequence, dealt to the warps from one
+ *     shared-memory counter (within a partition the rows are sorted by length, so this is
+ *     longest-job-first); a warp's chunk stream does not know partition boundaries: when the
+ *     next slice it is dealt lies in a later partition, a "switch" marker per boundary goes down
+ *     its two-slot pipeline where the consumer has to change buffers;
+ *   - the CTA's partitions are rows of a table in GLOBAL memory (a.ctaTab, 32 bytes per
+ *     partition, built by the session: slot c + grid*j = the j-th partition of CTA c), read
+ *     through L1/L2 one slice ahead of their use: any number of partitions per CTA
+ *     (27-point 512^3 on one GPU: 32 768 partitions, 222 per CTA);
  *   - no CTA-wide barrier after the start-up; warps are at most one partition apart.
  *
- * grid = min(#SMs, nParts), block = NW*32, one CTA per SM; CTA c takes the partitions
- * order[c + grid*j].  smem = 1664 B header (mbarriers, slice counters, partition table) +
- * 2 * (align128((W+2)*8) + align128(cacheCap*8)) + NW * 2 * slot.  Requires ctasPerPart == 1
- * and at most kMaxPartsPerCta partitions per CTA.  Single-GPU sessions only (the peer-memory
- * exchange lives in the staged kernel).
+ * PEER: the multi-GPU build.  The last warp of the first pushCtas CTAs (all of them are
+ * resident: the grid is one CTA per SM) sends its share of the x entries the neighbours need
+ * before it joins the product; halo columns are the tail of the partitions' ascending cache
+ * lists: a warp whose share of a list reaches into the halo waits (once per product) for the
+ * neighbours' flags and reads the halo buffer; the session orders every CTA's partitions so that
+ * those with halo columns come last, when the neighbours' push has long arrived.
+ *
+ * grid = min(#SMs, nParts), block = NW*32, one CTA per SM.
+ * smem = 512 B header (mbarriers, sequence counter) + 2 * (align128((W+2)*8) +
+ * align128(cacheCap*8)) + NW * 2 * slot.  Requires ctasPerPart == 1.
  */
 /* mbarrier wait with a time limit: a protocol error between the warps must abort the kernel
  * (trap: the launch fails with an error), never leave the GPU spinning */
@@ -993,7 +1048,7 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
     const unsigned long long t0 = global_timer_ns();
     unsigned polls = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 1023u) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
+        if ((++polls & 1023u) == 0 && global_timer_ns() - t0 > 20000000000ull) __trap();
     }
 }
 
@@ -1007,9 +1062,12 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar)
 {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
 
-constexpr int kPersistHeader = 1664;
-constexpr int kMaxPartsPerCta = 32;
+constexpr int kPersistHeader = 512;
 
 struct PMeta {
     int kc;    /* columns in the chunk */
@@ -1017,17 +1075,19 @@ struct PMeta {
     int t;     /* slice (local index in its partition) */
 };
 
-/* issue side of a warp: walks the slices it is dealt, partition after partition */
+/* issue side of a warp: walks the slices it is dealt out of the CTA's sequence */
 template <int KCE>
 struct PWalker {
-    const int *partTab;        /* shared: 8 ints per partition of this CTA {ps, pe, sliceStart, sliceEnd, cacheStart, cacheCount, -, -} */
-    int *counters;             /* shared: next undealt slice of every partition of this CTA */
+    const int4 *tab;           /* this CTA's rows of the partition table: row j at tab[strideJ * j] */
+    int *counter;              /* shared: next undealt slice of the CTA's sequence */
     const uint2 *slices;       /* global slice descriptors */
     const unsigned char *blob;
     const unsigned char *base; /* current slice */
-    int nj, j;                 /* partitions of this CTA, partition being issued */
-    int nsl;                   /* slices of partition j */
-    int t, tnext;              /* current / next slice of this warp in partition j */
+    int strideJ, nj;
+    int j;                     /* partition of the current slice */
+    int t;                     /* current slice, local index in partition j */
+    int qn, jn;                /* next slice of this warp (sequence number) and its partition */
+    int baseN, nslN, sliceStartN; /* partition jn: first sequence number, slices, first descriptor */
     int w, wr, nE, nc, ci;
     uint2 dnext;
     int switchesOwed;          /* partition boundaries crossed but not yet sent down the pipeline */
@@ -1043,41 +1103,52 @@ struct PWalker {
         ci = 0;
     }
 
-    __device__ __forceinline__ int take(int lane)
+    /* takes the next sequence number and finds its partition and descriptor (one slice ahead of
+     * their use: the table and descriptor loads overlap the chunks of the current slice) */
+    __device__ __forceinline__ void take(int lane)
     {
         int v = 0;
-        if (lane == 0) v = atomicAdd(counters + j, 1);
-        return __shfl_sync(0xffffffffu, v, 0);
+        if (lane == 0) v = atomicAdd(counter, 1);
+        qn = __shfl_sync(0xffffffffu, v, 0);
+        while (jn < nj && qn >= baseN + nslN) {
+            baseN += nslN;
+            jn += 1;
+            if (jn < nj) {
+                const int4 e = __ldg(tab + static_cast<size_t>(strideJ) * jn);
+                sliceStartN = e.z;
+                nslN = e.w - e.z;
+            }
+        }
+        if (jn < nj) dnext = __ldg(slices + sliceStartN + (qn - baseN));
     }
 
-    /* positions the walker on the next slice this warp gets, crossing partitions as needed */
+    /* positions the walker on the next slice this warp gets, crossing partitions as needed; when
+     * the sequence is exhausted the remaining boundaries are still owed: every warp passes every
+     * partition of the CTA (it owes each of them its share of the staging and an `empty` arrival) */
     __device__ __forceinline__ void next_slice(int lane)
     {
-        for (;;) {
-            if (tnext < nsl) {
-                t = tnext;
-                load_slice(dnext);
-                tnext = take(lane);
-                if (tnext < nsl) dnext = __ldg(slices + partTab[8 * j + 2] + tnext);
-                live = true;
-                return;
-            }
-            if (j + 1 >= nj) { live = false; return; }
-            j += 1;
-            switchesOwed += 1;
-            nsl = partTab[8 * j + 3] - partTab[8 * j + 2];
-            tnext = take(lane);
-            if (tnext < nsl) dnext = __ldg(slices + partTab[8 * j + 2] + tnext);
+        if (jn >= nj) {
+            switchesOwed += nj - 1 - j;
+            j = nj - 1;
+            live = false;
+            return;
         }
+        switchesOwed += jn - j;
+        j = jn;
+        t = qn - baseN;
+        load_slice(dnext);
+        take(lane);
+        live = true;
     }
 
-    __device__ __forceinline__ void start(const int *partTab_, int *counters_, const uint2 *slices_, const unsigned char *blob_, int nj_, int lane)
+    __device__ __forceinline__ void start(const int4 *tab_, int strideJ_, int *counter_, const uint2 *slices_, const unsigned char *blob_, int nj_, int lane)
     {
-        partTab = partTab_; counters = counters_; slices = slices_; blob = blob_; nj = nj_;
-        j = 0; switchesOwed = 0; live = false;
-        nsl = partTab[3] - partTab[2];
-        tnext = take(lane);
-        if (tnext < nsl) dnext = __ldg(slices + partTab[2] + tnext);
+        tab = tab_; strideJ = strideJ_; counter = counter_; slices = slices_; blob = blob_; nj = nj_;
+        j = 0; jn = 0; baseN = 0; switchesOwed = 0; live = false;
+        const int4 e = __ldg(tab);
+        sliceStartN = e.z;
+        nslN = e.w - e.z;
+        take(lane);
         next_slice(lane);
     }
 };
@@ -1132,7 +1203,7 @@ __device__ __forceinline__ PMeta issue_pchunk(PWalker<KCE> &wk, uint32_t slotAdd
     return m;
 }
 
-template <int kMaxThreads, int KCE>
+template <int kMaxThreads, int KCE, bool PEER>
 __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const MainArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1142,30 +1213,37 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
     const int nw = blockDim.x >> 5;
     const int G = gridDim.x;
     const int nj = (a.nPartsTotal - static_cast<int>(blockIdx.x) + G - 1) / G; /* partitions of this CTA (>= 1: grid <= nParts) */
+    /* row j of this CTA in the partition table: {rowStart, rowEnd, sliceStart, sliceEnd},
+     * {cacheStart, cacheCount, flags (1: the cache list has halo columns), -} */
+    const int4 *tab = reinterpret_cast<const int4 *>(a.ctaTab) + 2 * static_cast<size_t>(blockIdx.x);
+    const int strideJ = 2 * G;
 
     /* header: [0,16) window bars, [16,32) cache bars, [32,48) empty bars, [64,448) slot bars,
-     * [448,576) slice counters, [576,1600) partition table */
+     * [448,452) sequence counter */
     const uint32_t hdr = smem_u32(smem);
-    int *counters = reinterpret_cast<int *>(smem + 448);
-    int *partTab = reinterpret_cast<int *>(smem + 576);
+    int *seqCounter = reinterpret_cast<int *>(smem + 448);
     const uint32_t winBytes = (static_cast<uint32_t>(a.W + 2) * 8u + 127u) & ~127u;
     const uint32_t cacheBytes = (static_cast<uint32_t>(a.cacheCap) * 8u + 127u) & ~127u;
     const uint32_t bufBytes = winBytes + cacheBytes;
     unsigned char *buf0 = smem + kPersistHeader;
     const uint32_t slotBar0 = hdr + 64u + static_cast<uint32_t>(warp * kSlotsPerWarp) * 8u;
     const uint32_t slot0 = smem_u32(buf0) + 2u * bufBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
+    const bool pusher = PEER && a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas && warp == nw - 1;
+    /* development (EHYB_TRACE=1, PEER build): 8 stamps per CTA - start, previous grid complete, push
+     * done, first window staged, last warp done, SM, longest wait for the neighbours' flags (ns),
+     * when that wait ended */
+    unsigned long long *tr = PEER && a.trace ? a.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+    if (PEER && tr && tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        tr[0] = global_timer_ns();
+        tr[5] = smid;
+        tr[2] = tr[4] = tr[6] = tr[7] = 0;
+    }
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (tid < nj) {
-        const int slotIdx = static_cast<int>(blockIdx.x) + G * tid;
-        const int p = a.order ? __ldg(a.order + slotIdx) : slotIdx;
-        const int4 d0 = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p);
-        const int4 d1 = __ldg(reinterpret_cast<const int4 *>(a.parts) + 2 * p + 1);
-        reinterpret_cast<int4 *>(partTab)[2 * tid] = d0;
-        reinterpret_cast<int4 *>(partTab)[2 * tid + 1] = d1;
-        counters[tid] = 0;
-    }
     if (tid == 0) {
+        *seqCounter = 0;
         for (int b = 0; b < 2; ++b) {
             mbar_init(hdr + 8u * b, 1);                              /* window: the TMA issuer's arrive.expect_tx */
             mbar_init(hdr + 16u + 8u * b, static_cast<uint32_t>(nw * 32)); /* cache: every lane arrives (through cp.async) */
@@ -1181,14 +1259,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
     if (a.l2hint) keepPolicy = make_evict_last_policy();
     else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(keepPolicy));
     PWalker<KCE> wk;
-    wk.start(partTab, counters, reinterpret_cast<const uint2 *>(a.slices), a.blob, nj, lane);
+    wk.start(tab, strideJ, seqCounter, reinterpret_cast<const uint2 *>(a.slices), a.blob, nj, lane);
     PMeta meta[2];
     meta[0] = issue_pchunk(wk, slot0, slotBar0, lane, streamPolicy);
     meta[1] = issue_pchunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane, streamPolicy);
     uint32_t phases = 0;
 
+    /* multi-GPU, pushing warp: everything of the halo push that does not need x */
+    bool pushOk = false;
+    if (PEER && pusher) pushOk = peer_push_check(a.peer);
+
     asm volatile("griddepcontrol.wait;" ::: "memory"); /* x and y belong to the stream's previous work */
     const bool tma_ok = (reinterpret_cast<uintptr_t>(a.x) & 15) == 0;
+    if (PEER && tr && tid == 0) tr[1] = global_timer_ns();
+    /* This CTA's share of the x entries the neighbours need (last warp only) goes out right after
+     * the warp has issued its share of the first partition's staging - unless that partition has
+     * halo columns itself (table flag; the session orders those last whenever it can): a warp must
+     * never wait for its neighbours' flags before it has pushed, two GPUs doing that would deadlock. */
+    bool pushPending = PEER && pusher;
+    if (PEER && pushPending && (__ldg(tab + 1).z & 1)) {
+        peer_push_all(a.peer, a.x, lane, pushOk);
+        pushPending = false;
+    }
 
     /* Staging of partition dutyJ of this CTA into buffer dutyJ&1: its window (TMA, warp 0) and this
      * warp's share of its remainder cache.  Waits until every warp has left partition dutyJ-2
@@ -1198,16 +1290,21 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
      * Inlined at two places only (start-up and one site in the loop): the code size of this kernel
      * matters (a polled, non-blocking variant with checks in every iteration measured slower). */
     int dutyState = 0, dutyJ = 0; /* dutyState 1: partition dutyJ still has to be staged by this warp */
+    int nxtPs = 0, nxtPe = 0;     /* rows of the partition staged last = the one the consumer enters next */
+    bool haloReady = false;       /* PEER: this warp has seen the neighbours' flags of this product */
     auto duty_begin = [&](int jj) { dutyState = 1; dutyJ = jj; };
     auto duty_run = [&]() {
         const int b = dutyJ & 1;
-        const int cacheStart = partTab[8 * dutyJ + 4], cacheCount = partTab[8 * dutyJ + 5];
+        const int4 e0 = __ldg(tab + static_cast<size_t>(strideJ) * dutyJ);
+        const int4 e1 = __ldg(tab + static_cast<size_t>(strideJ) * dutyJ + 1);
+        const int cacheStart = e1.x, cacheCount = e1.y;
+        nxtPs = e0.x; nxtPe = e0.y;
         if (dutyJ >= 2) mbar_wait_bounded(hdr + 32u + 8u * b, static_cast<uint32_t>(((dutyJ - 2) >> 1) & 1));
         if (warp == 0) {
-            const int ps_ = partTab[8 * dutyJ];
+            const int ps_ = e0.x;
             double *win = reinterpret_cast<double *>(buf0 + static_cast<size_t>(b) * bufBytes);
             const int g0 = ps_ & ~1;
-            const int len = min(ps_ + a.W, a.n) - g0;
+            const int len = max(0, min(ps_ + a.W, a.n) - g0);
             if (tma_ok) {
                 if (lane == 0) {
                     if (len & 1) win[len - 1] = a.x[g0 + len - 1]; /* odd tail element, released by the arrive below */
@@ -1226,31 +1323,66 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
         const int32_t *cols = a.cacheCols + cacheStart;
         const uint32_t cacheA = smem_u32(buf0) + static_cast<uint32_t>(b) * bufBytes + winBytes;
         const int stride = nw * 32;
+        bool halo = false; /* PEER: this lane met a halo column (>= n): the tail of the ascending list */
         for (int i0 = warp * 32 + lane; i0 < cacheCount; i0 += 4 * stride) {
             /* this warp's entries: groups of 32 dealt round-robin over the warps, 4 groups per round */
             const int c0 = __ldg(cols + i0);
             const int c1 = i0 + stride < cacheCount ? __ldg(cols + i0 + stride) : -1;
             const int c2 = i0 + 2 * stride < cacheCount ? __ldg(cols + i0 + 2 * stride) : -1;
             const int c3 = i0 + 3 * stride < cacheCount ? __ldg(cols + i0 + 3 * stride) : -1;
-            cp_async_8(cacheA + static_cast<uint32_t>(i0) * 8u, a.x + c0);
-            if (c1 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + stride) * 8u, a.x + c1);
-            if (c2 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 2 * stride) * 8u, a.x + c2);
-            if (c3 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 3 * stride) * 8u, a.x + c3);
+            if (PEER) {
+                halo = halo || c0 >= a.n || c1 >= a.n || c2 >= a.n || c3 >= a.n;
+                if (c0 < a.n) cp_async_8(cacheA + static_cast<uint32_t>(i0) * 8u, a.x + c0);
+                if (c1 >= 0 && c1 < a.n) cp_async_8(cacheA + static_cast<uint32_t>(i0 + stride) * 8u, a.x + c1);
+                if (c2 >= 0 && c2 < a.n) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 2 * stride) * 8u, a.x + c2);
+                if (c3 >= 0 && c3 < a.n) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 3 * stride) * 8u, a.x + c3);
+            } else {
+                cp_async_8(cacheA + static_cast<uint32_t>(i0) * 8u, a.x + c0);
+                if (c1 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + stride) * 8u, a.x + c1);
+                if (c2 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 2 * stride) * 8u, a.x + c2);
+                if (c3 >= 0) cp_async_8(cacheA + static_cast<uint32_t>(i0 + 3 * stride) * 8u, a.x + c3);
+            }
         }
-        cp_async_mbar_arrive_noinc(hdr + 16u + 8u * b); /* every lane: arrives when its gathers have landed */
+        if (PEER && __any_sync(0xffffffffu, halo)) {
+            /* halo columns: wait (once per product and warp) for the neighbours' push, then read
+             * the halo buffer - peer-written, L2 is the point of coherence - with plain stores into
+             * the cache; these lanes arrive on the cache barrier themselves (release) once their
+             * asynchronous gathers have landed */
+            if (a.peer.flags != nullptr && !haloReady) {
+                const unsigned long long tw = PEER && tr ? global_timer_ns() : 0ull;
+                peer_wait(a.peer.flags, a.peer.recvMask, a.peer.nranks, a.peer.peerPushCtas, false, a.peer.epoch, a.peer.timeoutNs, a.peer.status);
+                haloReady = true;
+                if (PEER && tr && lane == 0) {
+                    const unsigned long long te = global_timer_ns();
+                    atomicMax(tr + 6, te - tw);
+                    atomicMax(tr + 7, te);
+                }
+            }
+            for (int i = warp * 32 + lane; i < cacheCount; i += stride) {
+                const int c = __ldg(cols + i);
+                if (c >= a.n) reinterpret_cast<double *>(buf0 + static_cast<size_t>(b) * bufBytes + winBytes)[i] = ld_halo_f64(a.peer, a.n, c);
+            }
+            cp_async_wait_all();
+            mbar_arrive(hdr + 16u + 8u * b);
+        } else {
+            cp_async_mbar_arrive_noinc(hdr + 16u + 8u * b); /* every lane: arrives when its gathers have landed */
+        }
         dutyState = 0;
     };
 
     /* consumer state for partition jC */
     int jC = 0;
-    int ps = partTab[0], pe = partTab[1];
-    uint32_t xsAddr = smem_u32(buf0) + static_cast<uint32_t>(ps - (ps & ~1)) * 8u;
-    uint32_t cacheAddr = smem_u32(buf0) + winBytes;
     bool cacheReady = false;
     duty_begin(0);
     duty_run();
+    if (PEER && pushPending) peer_push_all(a.peer, a.x, lane, pushOk);
+    if (PEER && tr && pusher && lane == 0) tr[2] = global_timer_ns();
+    int ps = nxtPs, pe = nxtPe;
+    uint32_t xsAddr = smem_u32(buf0) + static_cast<uint32_t>(ps - (ps & ~1)) * 8u;
+    uint32_t cacheAddr = smem_u32(buf0) + winBytes;
     if (nj > 1) duty_begin(1);
     mbar_wait_bounded(hdr + 0u, 0);
+    if (PEER && tr && tid == 0) tr[3] = global_timer_ns();
     bool dutyDue = false; /* set at the end of a slice: stage the next partition at the top of the next iteration */
 
     double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
@@ -1271,7 +1403,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
             if (lane == 0) mbar_arrive(hdr + 32u + 8u * static_cast<uint32_t>(jC & 1));
             jC += 1;
             const uint32_t b = static_cast<uint32_t>(jC & 1), par = static_cast<uint32_t>((jC >> 1) & 1);
-            ps = partTab[8 * jC]; pe = partTab[8 * jC + 1];
+            ps = nxtPs; pe = nxtPe; /* (the staging of partition jC by this warp came last) */
             xsAddr = smem_u32(buf0) + b * bufBytes + static_cast<uint32_t>(ps - (ps & ~1)) * 8u;
             cacheAddr = smem_u32(buf0) + b * bufBytes + winBytes;
             cacheReady = false;
@@ -1342,6 +1474,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
         if (s) meta[1] = mn; else meta[0] = mn;
         s ^= 1;
     }
+    if (PEER && tr && lane == 0) atomicMax(tr + 4, global_timer_ns());
     /* (every warp has passed all nj-1 switch markers here: the walker always ends in the last
      * partition, and a marker completes the staging it owes before it leaves a partition) */
 }

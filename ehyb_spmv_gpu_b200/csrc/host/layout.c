@@ -637,6 +637,31 @@ int ehyb_layout_import(const ehyb_layout_view *sc, void *const *arrays, ehyb_lay
     }
     for (int s = 0; s < sc->nSlices && !bad; ++s)
         bad = (int64_t)slices[s].off256 * 256 + slice_bytes(slices[s].w, slices[s].wr) > sc->blobBytes;
+    /* every row of a partition lives in one of its slices, and every 16-bit index stays inside
+     * what the kernels stage in shared memory: the x window (rows [rowStart, min(rowStart+W, n)))
+     * for ELL columns, the partition's cache list for remainder columns.  A bad index would be an
+     * out-of-bounds shared-memory read on the device, a short slice range rows of y never written. */
+    const unsigned char *blob = (const unsigned char *)arrays[2];
+    int badIdx = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : badIdx)
+    for (int p = 0; p < sc->nParts; ++p) {
+        if (bad) continue;
+        const ehyb_part_desc *d = &parts[p];
+        if (d->sliceEnd - d->sliceStart != (d->rowEnd - d->rowStart + SR - 1) / SR) { badIdx = 1; continue; }
+        const int64_t winLen = (int64_t)d->rowStart + sc->W < sc->n ? sc->W : sc->n - d->rowStart;
+        for (int s = d->sliceStart; s < d->sliceEnd; ++s) {
+            const int w = slices[s].w, wr = slices[s].wr;
+            const unsigned char *base = blob + (int64_t)slices[s].off256 * 256;
+            const uint16_t *ec = (const uint16_t *)(base + reg_ell_col(w));
+            const uint16_t *rcol = (const uint16_t *)(base + reg_rem_col(w, wr));
+            if (w > 0 && winLen <= 0) { badIdx = 1; break; }
+            if (wr > 0 && d->cacheCount <= 0) { badIdx = 1; break; }
+            const int64_t nE = (int64_t)((w + 3) / 4) * 256, nR = (int64_t)((wr + 3) / 4) * 256;
+            for (int64_t i = 0; i < nE; ++i) badIdx |= ec[i] >= winLen;
+            for (int64_t i = 0; i < nR; ++i) badIdx |= rcol[i] >= d->cacheCount;
+        }
+    }
+    bad |= badIdx;
     for (int64_t i = 0; i < sc->cacheTotal && !bad; ++i) bad = cacheCols[i] < 0 || cacheCols[i] >= sc->ncols;
     const int32_t *ovfRow = (const int32_t *)arrays[3], *ovfCol = (const int32_t *)arrays[4];
     for (int64_t i = 0; i < sc->nOverflow && !bad; ++i)

@@ -87,7 +87,7 @@ int ehyb_plan_kernel(int n, const ehyb_device_info *dev, int kernel, ehyb_plan_t
         if (wP < wMax) wMax = wP;
     }
     wMax -= wMax % 64;
-    if (wMax > 65536) wMax = 65536;
+    if (wMax > 65472) wMax = 65472; /* the boundary struct carries W in a uint16_t (spmv.h): 65536 would wrap to 0 */
     if (wMax < 64) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan: no shared memory for a window");
 
     int P = sms * partsPerSM, kpp = 1;

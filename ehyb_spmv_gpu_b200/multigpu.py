@@ -224,7 +224,9 @@ def setup_slab(rank, world, grid, dist, partition="metis", exchange="p2p"):
         dev = api.device_query(int(os.environ.get("LOCAL_RANK", "0")))
     except Exception:
         dev = api.device_info_b200()
-    pl = api.plan(blk.n, dev)
+    # partitions sized for the persistent kernel (which carries the halo exchange) unless
+    # EHYB_MG_PLAN=staged asks for the staged kernel's two-per-SM plan
+    pl = api.plan(blk.n, dev, kernel=api.KERNEL_STAGED if os.environ.get("EHYB_MG_PLAN") == "staged" else api.KERNEL_PERSISTENT)
     pv = None
     if partition == "metis":
         xa, ad = blk.local_graph()

@@ -9,7 +9,7 @@
  * Parity status: PINNED.  Every function below is checked byte-for-byte
  * against the unmodified reference sources compiled in place
  * (oracle/_ref/libehyb_ref.so, see oracle/Makefile and
- * tests/test_oracle_vs_ref.py) and against the reference-derived
+ * tests/test_oracle_pinned.py) and against the reference-derived
  * known-answer values of SURVEY.md Appendix D (tests/golden/).
  *
  * Each function cites the reference file:line it follows (paths are

@@ -28,7 +28,33 @@ def read_trace(lib, handle):
     return buf.reshape(-1, 8)
 
 
+def summarise_persistent(tag, rank, tr, ms_per):
+    """persistent kernel: one CTA per SM for the whole product (stamps: see ehyb_persistent_kernel)"""
+    tr = tr[tr[:, 0] > 0]
+    t = tr.astype(np.float64)
+    T0 = t[:, 1].min()
+    start, dep, push, staged, end = ((t[:, i] - T0) / 1e3 for i in range(5))
+    out = ["[%s rank %d] persistent kernel, %d CTAs: %.2f us/product; span (first dep-wait passed -> last warp done) %.1f us"
+           % (tag, rank, len(t), ms_per * 1e3, end.max())]
+    out.append("  CTA start before its dep-wait: mean %.1f us (prologue overlapped with the previous product); dep-wait passed %.2f..%.2f"
+               % ((dep - start).mean(), dep.min(), dep.max()))
+    out.append("  first window staged %.2f..%.2f us after the dep-wait (mean %.2f)" % ((staged - dep).min(), (staged - dep).max(), (staged - dep).mean()))
+    out.append("  CTA end: %.1f..%.1f (mean %.1f) -> idle tail mean %.1f us" % (end.min(), end.max(), end.mean(), (end.max() - end).mean()))
+    pushed = tr[:, 2] > 0
+    if pushed.any():
+        out.append("  push: %d CTAs, done %.2f..%.2f us after their dep-wait (mean %.2f)"
+                   % (pushed.sum(), (push - dep)[pushed].min(), (push - dep)[pushed].max(), (push - dep)[pushed].mean()))
+    waited = tr[:, 6] > 0
+    if waited.any():
+        out.append("  halo wait: %d CTAs, longest wait per CTA %.2f..%.2f us (mean %.2f), ended at %.1f..%.1f us of the product"
+                   % (waited.sum(), tr[waited, 6].min() / 1e3, tr[waited, 6].max() / 1e3, tr[waited, 6].mean() / 1e3,
+                      ((t[:, 7] - T0) / 1e3)[waited].min(), ((t[:, 7] - T0) / 1e3)[waited].max()))
+    print("\n".join(out), flush=True)
+
+
 def summarise(tag, rank, tr, ms_per, halo_parts=None):
+    if os.environ.get("EHYB_TRACE_PERSISTENT"):
+        return summarise_persistent(tag, rank, tr, ms_per)
     t = tr.astype(np.float64)
     T0 = t[:, 1].min()               # first CTA past the wait for the previous product
     start, dep, push, staged, end = ((t[:, i] - T0) / 1e3 for i in range(5))
@@ -88,6 +114,8 @@ def main():
         ms = ms[0] if isinstance(ms, tuple) else ms
         tr = read_trace(lib, s.h)
         np.save(out_dir / ("trace_%s_rank0.npy" % tag), tr)
+        if s.kernel_name() == "ehyb_persistent_kernel":
+            os.environ["EHYB_TRACE_PERSISTENT"] = "1"
         summarise(tag, 0, tr, ms / 200)
         return
     import torch.distributed as dist
@@ -107,6 +135,9 @@ def main():
     torch.cuda.synchronize()
     tr = read_trace(lib, blk.handle)
     np.save(out_dir / ("trace_%s_rank%d.npy" % (tag, rank)), tr)
+    lib.ehyb_session_kernel.restype = C.c_char_p
+    if lib.ehyb_session_kernel(blk.handle) == b"ehyb_persistent_kernel":
+        os.environ["EHYB_TRACE_PERSISTENT"] = "1"
     # partitions whose remainder cache holds halo columns
     v = api.LayoutView()
     lib.ehyb_layout_get(blk.layout, C.byref(v))

@@ -90,8 +90,42 @@ def main():
         bad = np.flatnonzero(~(np.abs(y - y_ref) <= 1e-12 * absAx))
         assert bad.size == 0, "rank %d product %d: %d rows outside the gate, first %s" % (rank, k, bad.size, bad[:5])
         worst = max(worst, float(np.abs(y - y_ref).max()))
+        x_perm_last, x_ext_last = x_perm, x_ext
     assert not blk.timed_out(), "a neighbour did not deliver its halo in time"
-    # back-to-back products without host synchronisation in between (the timed loop)
+    # K products queued back to back WITHOUT any host synchronisation in between, every one with
+    # its own x_k (what a solver does): product k+1 starts early (programmatic dependent launch), a
+    # sender may run ahead of its receiver, and the halo buffers alternate - a halo value of the
+    # wrong product in any y_k fails the gate of x_k
+    K = 6
+    lib = blk.lib
+    xs = torch.zeros((K, blk.n + blk.nHalo), dtype=torch.float64, device="cuda")
+    ys = torch.full((K, blk.n), float("nan"), dtype=torch.float64, device="cuda")
+    x_exts = []
+    for k in range(K):
+        x_nat = mg.x_of_global(gl) * (0.5 + k) - 0.02 * k
+        x_perm = np.empty(blk.n)
+        x_perm[blk.coo["reorderList"]] = x_nat
+        xs[k, :blk.n] = torch.from_numpy(x_perm)
+        x_exts.append(np.concatenate([x_perm, mg.x_of_global(blk.haloGlobal) * (0.5 + k) - 0.02 * k]))
+    torch.cuda.synchronize()
+    dist.barrier()
+    for k in range(K):
+        L.check(lib, lib.ehyb_mg_spmv(blk.session, C.c_void_p(xs[k].data_ptr()), C.c_void_p(ys[k].data_ptr())), "ehyb_mg_spmv")
+    L.check(lib, lib.ehyb_sync(blk.handle), "ehyb_sync")
+    torch.cuda.synchronize()
+    for k in range(K):
+        yk = ys[k].cpu().numpy()
+        y_ref = orc.csr_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_exts[k])
+        absAx = orc.csr_abs_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_exts[k])
+        bad = np.flatnonzero(~(np.abs(yk - y_ref) <= 1e-12 * absAx))
+        assert bad.size == 0, "rank %d queued product %d: %d rows outside the gate, first %s" % (rank, k, bad.size, bad[:5])
+    # restore the last checked x / y of the loop above for the timed loop below
+    blk.set_x(x_perm_last)
+    blk.spmv()
+    y = blk.get_y()
+    y_ref = orc.csr_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_ext_last)
+    absAx = orc.csr_abs_spmv(blk.coo["rowIdx"], blk.coo["J"], blk.coo["V"], x_ext_last)
+    # back-to-back products of the same x (the timed loop)
     ms = blk.time_spmv(3, 50)
     assert ms > 0
     y2 = blk.get_y()

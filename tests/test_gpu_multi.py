@@ -41,8 +41,9 @@ CASES = [
 
 
 @pytest.mark.parametrize("exchange,partition,grid", CASES)
+@pytest.mark.parametrize("kernel", ["staged", "persistent"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_distributed_product_on_gpus(world, exchange, partition, grid):
+def test_distributed_product_on_gpus(world, exchange, partition, grid, kernel):
     if _gpus() < world:
         pytest.skip("needs %d GPUs" % world)
     if partition == "metis" and not (ROOT / "bin" / "ehyb_mtmetis").exists():
@@ -51,7 +52,8 @@ def test_distributed_product_on_gpus(world, exchange, partition, grid):
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), OMP_NUM_THREADS="4", EHYB_P2P_TIMEOUT_MS="20000")
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="4", EHYB_P2P_TIMEOUT_MS="20000",
+                   EHYB_MG_KERNEL={"staged": "2", "persistent": "3"}[kernel])
         procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "mg_gpu_worker.py"), exchange, partition, grid],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
