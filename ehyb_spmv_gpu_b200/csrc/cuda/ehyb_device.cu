@@ -133,9 +133,14 @@ static main_kernel_t staged_kernel(int threads, bool peer)
 /* persistent, double-buffered variant (ehyb_persistent_kernel): 4-column chunks only */
 static main_kernel_t persistent_kernel(int threads, bool peer)
 {
-    if (peer) return threads <= 512 ? ehyb_persistent_kernel<512, 4, true> : ehyb_persistent_kernel<768, 4, true>;
-    return threads <= 512 ? ehyb_persistent_kernel<512, 4, false> : ehyb_persistent_kernel<768, 4, false>;
+    /* register budgets: 128 at <= 512 threads, 102 at <= 640, 80 at 768.  The multi-GPU build keeps a
+     * few more values live (calls into the exchange code): it spills at 80 registers, so peer
+     * sessions run at most kPeerPersistWarps = 20 warps (measured at config 2: 20 warps already
+     * stream at 99 % of the copy peak) */
+    if (peer) return threads <= 512 ? ehyb_persistent_kernel<512, 4, true> : ehyb_persistent_kernel<640, 4, true>;
+    return threads <= 512 ? ehyb_persistent_kernel<512, 4, false> : threads <= 640 ? ehyb_persistent_kernel<640, 4, false> : ehyb_persistent_kernel<768, 4, false>;
 }
+constexpr int kPeerPersistWarps = 20;
 
 /* The persistent kernel's partition table: slot s = c + grid*j is the j-th partition of CTA c;
  * row = {rowStart, rowEnd, sliceStart, sliceEnd, cacheStart, cacheCount, flags, 0}, flags bit 0 =
@@ -191,7 +196,7 @@ extern "C" void ehyb_free(ehyb_handle *h)
     free(h);
 }
 
-static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, ehyb_handle *h)
+static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, ehyb_handle *h, bool peerSession)
 {
     CU(cudaSetDevice(o->device));
     cudaDeviceProp prop;
@@ -222,6 +227,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
         const size_t perWarp = (size_t)kSlotsPerWarp * slot_bytes(4);
         int nw = fixed + perWarp <= prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - fixed) / perWarp) : 0;
         if (nw > kMaxStageWarps) nw = kMaxStageWarps;
+        if ((peerSession || env_int("EHYB_FORCE_PEER_BUILD", 0) || env_int("EHYB_TRACE", 0)) && nw > kPeerPersistWarps) nw = kPeerPersistWarps;
         if (threads > 0 && threads / 32 < nw) nw = threads / 32 > 0 ? threads / 32 : 1;
         if (h->kpp != 1 || nw < (autoKernel ? 16 : 8)) {
             kernel = EHYB_KERNEL_STAGED;
@@ -299,7 +305,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    for (int t = 512; t <= 768; t += 256)
+    for (int t = 512; t <= 768; t += 128)
         for (int peer = 0; peer < 2; ++peer) {
             CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
             CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -362,7 +368,15 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     return EHYB_OK;
 }
 
+static int upload_session(const ehyb_layout *L, const ehyb_session_opts *opts, bool peerSession, ehyb_handle **out);
+
 extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, ehyb_handle **out)
+{
+    return upload_session(L, opts, false, out);
+}
+
+/* peerSession: the session will run the multi-GPU build of its kernel (peer-memory exchange) */
+static int upload_session(const ehyb_layout *L, const ehyb_session_opts *opts, bool peerSession, ehyb_handle **out)
 {
     if (!L || !out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_upload: NULL argument");
     ehyb_session_opts o;
@@ -373,7 +387,7 @@ extern "C" int ehyb_upload(const ehyb_layout *L, const ehyb_session_opts *opts, 
     if (rc) return rc;
     ehyb_handle *h = (ehyb_handle *)calloc(1, sizeof *h);
     if (!h) return ehyb_fail(EHYB_ERR_NOMEM, "ehyb_upload: out of memory");
-    rc = upload_impl(&v, &o, h);
+    rc = upload_impl(&v, &o, h, peerSession);
     if (rc) {
         char msg[512];
         snprintf(msg, sizeof msg, "%s", ehyb_last_error());
@@ -877,7 +891,7 @@ static int mg_session_base(const ehyb_mg_local *L, int rank, int nranks, int dev
      * not a choice here.  Default (0): persistent where the layout allows it ($EHYB_MG_KERNEL) */
     o.kernel = env_int("EHYB_MG_KERNEL", 0);
     if (o.kernel == EHYB_KERNEL_DIRECT) o.kernel = EHYB_KERNEL_STAGED;
-    rc = ehyb_upload(layout, &o, &s->h);
+    rc = upload_session(layout, &o, exchange == EHYB_MG_P2P, &s->h);
     if (rc) { free(s); return rc; }
     auto body = [&]() -> int {
         CU(cudaSetDevice(device));

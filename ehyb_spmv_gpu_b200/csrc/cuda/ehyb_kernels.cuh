@@ -1203,8 +1203,35 @@ __device__ __forceinline__ PMeta issue_pchunk(PWalker<KCE> &wk, uint32_t slotAdd
     return m;
 }
 
+/* Multi-GPU build, cold path of the staging: this warp's share of a partition's cache list reaches
+ * into the halo columns (>= n, the tail of the ascending list).  Waits (once per product and warp)
+ * for the neighbours' push, reads the halo buffer - peer-written, L2 is the point of coherence -
+ * with plain stores into the cache, and lets every lane arrive on the cache barrier itself
+ * (release) once its asynchronous gathers have landed.  Returns the new haloReady. */
+__device__ __noinline__ bool stage_halo_columns(const MainArgs &a, const int32_t *cols, int cacheCount, double *cache, uint32_t cacheBar,
+                                                bool haloReady, unsigned long long *tr)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, stride = blockDim.x;
+    if (a.peer.flags != nullptr && !haloReady) {
+        const unsigned long long tw = tr ? global_timer_ns() : 0ull;
+        peer_wait(a.peer.flags, a.peer.recvMask, a.peer.nranks, a.peer.peerPushCtas, false, a.peer.epoch, a.peer.timeoutNs, a.peer.status);
+        if (tr && lane == 0) {
+            const unsigned long long te = global_timer_ns();
+            atomicMax(tr + 6, te - tw);
+            atomicMax(tr + 7, te);
+        }
+    }
+    for (int i = warp * 32 + lane; i < cacheCount; i += stride) {
+        const int c = __ldg(cols + i);
+        if (c >= a.n) cache[i] = ld_halo_f64(a.peer, a.n, c);
+    }
+    cp_async_wait_all();
+    mbar_arrive(cacheBar);
+    return true;
+}
+
 template <int kMaxThreads, int KCE, bool PEER>
-__global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const MainArgs a)
+__global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const __grid_constant__ MainArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr uint32_t kSlotBytes = static_cast<uint32_t>(slot_bytes(KCE));
@@ -1344,26 +1371,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const M
             }
         }
         if (PEER && __any_sync(0xffffffffu, halo)) {
-            /* halo columns: wait (once per product and warp) for the neighbours' push, then read
-             * the halo buffer - peer-written, L2 is the point of coherence - with plain stores into
-             * the cache; these lanes arrive on the cache barrier themselves (release) once their
-             * asynchronous gathers have landed */
-            if (a.peer.flags != nullptr && !haloReady) {
-                const unsigned long long tw = PEER && tr ? global_timer_ns() : 0ull;
-                peer_wait(a.peer.flags, a.peer.recvMask, a.peer.nranks, a.peer.peerPushCtas, false, a.peer.epoch, a.peer.timeoutNs, a.peer.status);
-                haloReady = true;
-                if (PEER && tr && lane == 0) {
-                    const unsigned long long te = global_timer_ns();
-                    atomicMax(tr + 6, te - tw);
-                    atomicMax(tr + 7, te);
-                }
-            }
-            for (int i = warp * 32 + lane; i < cacheCount; i += stride) {
-                const int c = __ldg(cols + i);
-                if (c >= a.n) reinterpret_cast<double *>(buf0 + static_cast<size_t>(b) * bufBytes + winBytes)[i] = ld_halo_f64(a.peer, a.n, c);
-            }
-            cp_async_wait_all();
-            mbar_arrive(hdr + 16u + 8u * b);
+            /* (out of line: the code size of the loop around this staging is measurable) */
+            haloReady = stage_halo_columns(a, cols, cacheCount, reinterpret_cast<double *>(buf0 + static_cast<size_t>(b) * bufBytes + winBytes),
+                                           hdr + 16u + 8u * b, haloReady, tr);
         } else {
             cp_async_mbar_arrive_noinc(hdr + 16u + 8u * b); /* every lane: arrives when its gathers have landed */
         }
