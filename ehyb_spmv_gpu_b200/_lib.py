@@ -132,6 +132,9 @@ EXPORTS = [
     "ehyb_mg_status", "ehyb_mg_launches_per_spmv",
     "ehyb_mg_session_free", "ehyb_gen_stencil27_rows", "ehyb_host_alloc_pinned", "ehyb_host_free_pinned",
     "ehyb_session_info",
+    "ehyb_layout_builder_begin", "ehyb_layout_builder_add", "ehyb_layout_builder_finish", "ehyb_layout_builder_abort",
+    "ehyb_grid_brick_graph", "ehyb_partition_graph_weighted", "ehyb_grid_decomp_create", "ehyb_grid_decomp_info",
+    "ehyb_grid_decomp_free", "ehyb_mg_grid_build", "ehyb_mg_local_natural_ids", "ehyb_grid_natural_ids", "ehyb_grid_rows",
 ]
 
 _lib = None

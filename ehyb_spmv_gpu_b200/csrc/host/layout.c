@@ -59,6 +59,7 @@ struct ehyb_layout {
     int32_t *rowCached; /* [n] remainder entries whose column is in the partition's cache */
     int32_t *cacheCols; /* concatenated per-partition cache lists (ascending permuted columns) */
     int64_t *ovfPtr;   /* [n+1] overflow entries of the row */
+    int blobBorrowed;  /* the blob belongs to a streamed builder (a chunk written in place) */
 };
 
 int ehyb_convert_reference_layout(const matrixCOO *in, matrixEHYB *out, int *sizeBlockELL, int *sizeER, int quiet);
@@ -66,7 +67,8 @@ int ehyb_convert_reference_layout(const matrixCOO *in, matrixEHYB *out, int *siz
 void ehyb_layout_free(ehyb_layout *L)
 {
     if (!L) return;
-    free(L->parts); free(L->slices); free(L->blob);
+    free(L->parts); free(L->slices);
+    if (!L->blobBorrowed) free(L->blob);
     free(L->ovfRow); free(L->ovfCol); free(L->ovfVal);
     free(L->rowEll); free(L->rowRemIn); free(L->rowCached); free(L->cacheCols); free(L->ovfPtr);
     free(L);
@@ -114,8 +116,12 @@ static inline int cache_find(const int32_t *list, int count, int32_t c)
     return -1;
 }
 
-static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *col, const double *val, int nParts,
-                             const int32_t *pb, const ehyb_layout_opts *opts, int allOverflow, ehyb_layout **out);
+/* where a chunk's slice data goes when the caller (the streamed builder) owns one big blob:
+ * zero-filled memory of `cap` bytes; used if the chunk fits, else the chunk allocates its own */
+typedef struct { unsigned char *dst; int64_t cap; int used; } blob_target;
+
+static int layout_build_impl(int64_t nGlobal64, int64_t rowBase64, int64_t n64, const int64_t *rowPtr, const int32_t *col, const double *val,
+                             int nParts, const int32_t *pb, const ehyb_layout_opts *opts, int allOverflow, blob_target *bt, ehyb_layout **out);
 
 /*
  * Format decision for matrices the explicit cache cannot help (power-law graphs: R-MAT scale 24
@@ -128,7 +134,7 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
                           const int32_t *pb, const ehyb_layout_opts *opts, ehyb_layout **out)
 {
     if (!opts || !out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_build: bad argument");
-    int rc = layout_build_impl(n64, rowPtr, col, val, nParts, pb, opts, 0, out);
+    int rc = layout_build_impl(n64, 0, n64, rowPtr, col, val, nParts, pb, opts, 0, NULL, out);
     if (rc) return rc;
     const double minCov = opts->min_coverage > 0 ? opts->min_coverage : (opts->min_coverage < 0 ? 0.0 : EHYB_DEFAULT_MIN_COVERAGE);
     const ehyb_layout_view *v = &(*out)->v;
@@ -137,17 +143,23 @@ int ehyb_layout_build_csr(int64_t n64, const int64_t *rowPtr, const int32_t *col
     if (v->nnz > 0 && (double)(v->nnzEll + v->nnzRemInSlice) < minCov * (double)v->nnz && v->ncols == v->n) {
         ehyb_layout_free(*out);
         *out = NULL;
-        rc = layout_build_impl(n64, rowPtr, col, val, nParts, pb, opts, 1, out);
+        rc = layout_build_impl(n64, 0, n64, rowPtr, col, val, nParts, pb, opts, 1, NULL, out);
     }
     return rc;
 }
 
-static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *col, const double *val, int nParts,
-                             const int32_t *pb, const ehyb_layout_opts *opts, int allOverflow, ehyb_layout **out)
+/* Builds the layout of the rows [rowBase, rowBase + nRows) of a matrix with nGlobal rows: either
+ * the whole matrix (rowBase 0, nRows == nGlobal) or one chunk of consecutive partitions of it
+ * (streamed build, ehyb_layout_builder_add).  rowPtr[nRows + 1] is relative to the chunk
+ * (rowPtr[0] == 0), pb[nParts + 1] and the columns are absolute.  A chunk's layout numbers its
+ * slices, cache lists and blob offsets from zero (the builder shifts them when it appends). */
+static int layout_build_impl(int64_t nGlobal64, int64_t rowBase64, int64_t n64, const int64_t *rowPtr, const int32_t *col, const double *val,
+                             int nParts, const int32_t *pb, const ehyb_layout_opts *opts, int allOverflow, blob_target *bt, ehyb_layout **out)
 {
-    if (!rowPtr || !col || !val || !pb || !opts || !out || n64 <= 0 || n64 > INT_MAX || nParts <= 0)
+    if (!rowPtr || !col || !val || !pb || !opts || !out || n64 <= 0 || nGlobal64 > INT_MAX || rowBase64 < 0 || rowBase64 + n64 > nGlobal64 || nParts <= 0)
         return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_build: bad argument");
-    const int n = (int)n64, P = nParts, W = opts->W;
+    const int n = (int)nGlobal64, rb = (int)rowBase64, nRows = (int)n64, P = nParts, W = opts->W;
+    const int isChunk = nRows != n;
     const int64_t ncols = opts->ncols > 0 ? opts->ncols : n;
     const int longThr = opts->long_row_threshold > 0 ? opts->long_row_threshold : EHYB_REF_LONG_ROW;
     const double fill = opts->er_fill < 0 ? 0.0 : opts->er_fill;
@@ -164,7 +176,7 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
     if (W <= 0 || W > 65536) return ehyb_fail(EHYB_ERR_LIMIT, "window %d outside (0, 65536]: column indices are 16-bit", W);
     if (cacheCap > 65536) cacheCap = 65536;
     if (ncols < n || ncols > INT_MAX) return ehyb_fail(EHYB_ERR_ARG, "ncols %lld must be in [n, 2^31)", (long long)ncols);
-    if (pb[0] != 0 || pb[P] != n) return ehyb_fail(EHYB_ERR_ARG, "partBoundary must run from 0 to n");
+    if (pb[0] != rb || pb[P] != rb + nRows) return ehyb_fail(EHYB_ERR_ARG, "partBoundary must run from %d to %d", rb, rb + nRows);
     for (int p = 0; p < P; ++p)
         if (pb[p] > pb[p + 1]) return ehyb_fail(EHYB_ERR_ARG, "partBoundary not monotone at %d", p);
 
@@ -175,10 +187,10 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
     int32_t **cacheList = (int32_t **)calloc((size_t)P, sizeof(int32_t *)); /* per partition, ascending */
     int32_t *wrCap = (int32_t *)malloc((size_t)P * sizeof(int32_t));          /* per partition: widest in-slice remainder */
     L->parts = (ehyb_part_desc *)calloc((size_t)P, sizeof(ehyb_part_desc));
-    L->rowEll = (int32_t *)calloc((size_t)n, sizeof(int32_t));
-    L->rowRemIn = (int32_t *)calloc((size_t)n, sizeof(int32_t));
-    L->rowCached = (int32_t *)calloc((size_t)n, sizeof(int32_t));
-    L->ovfPtr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
+    L->rowEll = (int32_t *)calloc((size_t)nRows, sizeof(int32_t));
+    L->rowRemIn = (int32_t *)calloc((size_t)nRows, sizeof(int32_t));
+    L->rowCached = (int32_t *)calloc((size_t)nRows, sizeof(int32_t));
+    L->ovfPtr = (int64_t *)calloc((size_t)nRows + 1, sizeof(int64_t));
     if (!cacheList || !wrCap || !L->parts || !L->rowEll || !L->rowRemIn || !L->rowCached || !L->ovfPtr) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout: out of memory"); goto fail; }
     /* distributed blocks: an entry whose column is in the halo [n, ncols) arrives with the
      * exchange, after the main kernel has started: it is never cached, always overflow */
@@ -221,7 +233,7 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
             int64_t inWin = 0;
             for (int r = ps; r < pe; ++r) {
                 if (r - ps >= W) break;
-                for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) inWin += (col[e] >= ps && col[e] < winEnd);
+                for (int64_t e = rowPtr[r - rb]; e < rowPtr[r + 1 - rb]; ++e) inWin += (col[e] >= ps && col[e] < winEnd);
             }
             const int64_t fair = inWin / SR / EHYB_BALANCE_WARPS; /* columns per warp, evenly spread */
             int64_t lim = 2 * fair;
@@ -232,19 +244,19 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
         for (int r = ps; r < pe; ++r) {
             int ell = 0;
             const int inWindowRow = r - ps < W; /* rows beyond the window are remainder as a whole (convert.c:128-134) */
-            for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
+            for (int64_t e = rowPtr[r - rb]; e < rowPtr[r + 1 - rb]; ++e) {
                 const int c = col[e];
                 if (c < 0 || c >= ncols) bad = 1;
                 ell += (inWindowRow && c >= ps && c < winEnd);
             }
             if (allOverflow || (scanning && ell > partThr)) { /* long rows sit at the head of the partition */
                 firstReg = r + 1;
-                L->rowEll[r] = -1;
+                L->rowEll[r - rb] = -1;
                 continue;
             }
             scanning = 0;
-            L->rowEll[r] = ell;
-            nExt += rowPtr[r + 1] - rowPtr[r] - ell;
+            L->rowEll[r - rb] = ell;
+            nExt += rowPtr[r + 1 - rb] - rowPtr[r - rb] - ell;
         }
         nLong += firstReg - ps;
         if (cacheCap == 0 || nExt == 0 || bad) continue;
@@ -253,7 +265,7 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
         int64_t m = 0;
         for (int r = firstReg; r < pe; ++r) {
             const int inWindowRow = r - ps < W;
-            for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
+            for (int64_t e = rowPtr[r - rb]; e < rowPtr[r + 1 - rb]; ++e) {
                 const int c = col[e];
                 if (inWindowRow && c >= ps && c < winEnd) continue;
                 if (haloOvf && c >= n) continue;
@@ -294,19 +306,19 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
              * (so that in-slice + overflow, concatenated, is the original order): count the
              * leading remainder entries whose column is cached */
             int cached = 0;
-            for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
+            for (int64_t e = rowPtr[r - rb]; e < rowPtr[r + 1 - rb]; ++e) {
                 const int c = col[e];
                 if (inWindowRow && c >= ps && c < winEnd) continue;
                 if ((haloOvf && c >= n) || cache_find(chosen, nChosen, c) < 0) break;
                 cached += 1;
             }
-            L->rowCached[r] = cached;
+            L->rowCached[r - rb] = cached;
         }
         /* the same balance rule for the in-slice remainder width: at most twice a warp's fair
          * share of all the partition's columns (ELL + cached remainder), never below 32 */
         if (fairCols >= 0) {
             int64_t sumCached = 0;
-            for (int r = firstReg; r < pe; ++r) sumCached += L->rowCached[r];
+            for (int r = firstReg; r < pe; ++r) sumCached += L->rowCached[r - rb];
             int64_t lim = 2 * (fairCols + sumCached / SR / EHYB_BALANCE_WARPS);
             if (lim < 32) lim = 32;
             if (lim < wrCap[p]) wrCap[p] = (int32_t)lim;
@@ -341,10 +353,10 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
                 const int r1 = r0 + SR < pe ? r0 + SR : pe;
                 int m = 0, rem[SR];
                 for (int r = r0; r < r1; ++r) {
-                    const int64_t len = rowPtr[r + 1] - rowPtr[r];
-                    if (L->rowEll[r] < 0) { ovfAlways += len; continue; }
-                    rem[m++] = L->rowCached[r];
-                    ovfAlways += len - L->rowEll[r] - L->rowCached[r];
+                    const int64_t len = rowPtr[r + 1 - rb] - rowPtr[r - rb];
+                    if (L->rowEll[r - rb] < 0) { ovfAlways += len; continue; }
+                    rem[m++] = L->rowCached[r - rb];
+                    ovfAlways += len - L->rowEll[r - rb] - L->rowCached[r - rb];
                 }
                 qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
                 int wrA = m >= 1 ? rem[0] : 0, wrB = m >= SR / 2 ? rem[SR / 2 - 1] : 0;
@@ -371,9 +383,9 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
             const int r1 = r0 + SR < pe ? r0 + SR : pe;
             int w = 0, m = 0, rem[SR];
             for (int r = r0; r < r1; ++r) {
-                if (L->rowEll[r] < 0) continue;
-                if (L->rowEll[r] > w) w = L->rowEll[r];
-                rem[m++] = L->rowCached[r] > 65535 ? 65535 : L->rowCached[r];
+                if (L->rowEll[r - rb] < 0) continue;
+                if (L->rowEll[r - rb] > w) w = L->rowEll[r - rb];
+                rem[m++] = L->rowCached[r - rb] > 65535 ? 65535 : L->rowCached[r - rb];
             }
             qsort(rem, (size_t)m, sizeof(int), cmp_int_desc);
             int wr = m >= need ? rem[need - 1] : 0;
@@ -384,18 +396,18 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
             sliceOff[s + 1] = slice_bytes(w, wr);
             int64_t sumE = 0, sumR = 0;
             for (int r = r0; r < r1; ++r) {
-                const int64_t len = rowPtr[r + 1] - rowPtr[r];
-                if (L->rowEll[r] < 0) { /* long row: everything overflows */
-                    L->ovfPtr[r + 1] = len;
+                const int64_t len = rowPtr[r + 1 - rb] - rowPtr[r - rb];
+                if (L->rowEll[r - rb] < 0) { /* long row: everything overflows */
+                    L->ovfPtr[r + 1 - rb] = len;
                     nnzOvf += len;
                     continue;
                 }
-                const int in = L->rowCached[r] < wr ? L->rowCached[r] : wr;
-                L->rowRemIn[r] = in;
-                L->ovfPtr[r + 1] = len - L->rowEll[r] - in;
-                sumE += L->rowEll[r];
+                const int in = L->rowCached[r - rb] < wr ? L->rowCached[r - rb] : wr;
+                L->rowRemIn[r - rb] = in;
+                L->ovfPtr[r + 1 - rb] = len - L->rowEll[r - rb] - in;
+                sumE += L->rowEll[r - rb];
                 sumR += in;
-                nnzOvf += len - L->rowEll[r] - in;
+                nnzOvf += len - L->rowEll[r - rb] - in;
             }
             nnzEll += sumE;
             nnzRemIn += sumR;
@@ -411,11 +423,17 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
         sliceOff[s + 1] += sliceOff[s];
     }
     const int64_t blobBytes = sliceOff[nSlices];
-    for (int r = 0; r < n; ++r) L->ovfPtr[r + 1] += L->ovfPtr[r];
-    const int64_t nOvf = L->ovfPtr[n];
+    for (int r = 0; r < nRows; ++r) L->ovfPtr[r + 1] += L->ovfPtr[r];
+    const int64_t nOvf = L->ovfPtr[nRows];
     if (nOvf > INT_MAX) { rc = ehyb_fail(EHYB_ERR_LIMIT, "overflow list exceeds 2^31 entries"); goto fail; }
 
-    L->blob = (unsigned char *)calloc((size_t)(blobBytes ? blobBytes : 256), 1);
+    if (bt && bt->dst && blobBytes <= bt->cap) { /* straight into the caller's blob (already zero) */
+        L->blob = bt->dst;
+        L->blobBorrowed = 1;
+        bt->used = 1;
+    } else {
+        L->blob = (unsigned char *)calloc((size_t)(blobBytes ? blobBytes : 256), 1);
+    }
     L->ovfRow = (int32_t *)malloc((size_t)(nOvf ? nOvf : 1) * sizeof(int32_t));
     L->ovfCol = (int32_t *)malloc((size_t)(nOvf ? nOvf : 1) * sizeof(int32_t));
     L->ovfVal = (double *)malloc((size_t)(nOvf ? nOvf : 1) * sizeof(double));
@@ -439,18 +457,18 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
             uint16_t *rcol = (uint16_t *)(base + reg_rem_col(w, wr));
             for (int r = r0; r < r1; ++r) {
                 const int t = r - r0, lane = t % 32, h = t / 32;
-                const int isLong = L->rowEll[r] < 0;
+                const int isLong = L->rowEll[r - rb] < 0;
                 const int inWindowRow = !isLong && r - ps < W;
                 int kE = 0, kR = 0;
-                int64_t o = L->ovfPtr[r];
-                for (int64_t e = rowPtr[r]; e < rowPtr[r + 1]; ++e) {
+                int64_t o = L->ovfPtr[r - rb];
+                for (int64_t e = rowPtr[r - rb]; e < rowPtr[r + 1 - rb]; ++e) {
                     const int c = col[e];
                     int ci = -1;
                     if (inWindowRow && c >= ps && c < winEnd) {
                         ev[((int64_t)kE * 32 + lane) * 2 + h] = val[e];
                         ec[(((int64_t)(kE / 4) * 32 + lane) * 2 + h) * 4 + kE % 4] = (uint16_t)(c - ps);
                         ++kE;
-                    } else if (!isLong && kR < L->rowRemIn[r] && (ci = cache_find(cl, cn, c)) >= 0) {
+                    } else if (!isLong && kR < L->rowRemIn[r - rb] && (ci = cache_find(cl, cn, c)) >= 0) {
                         rv[((int64_t)kR * 32 + lane) * 2 + h] = val[e];
                         rcol[(((int64_t)(kR / 4) * 32 + lane) * 2 + h) * 4 + kR % 4] = (uint16_t)ci;
                         ++kR;
@@ -464,11 +482,11 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
             }
         }
     }
-    for (int r = 0; r < n; ++r)
+    for (int r = 0; r < nRows; ++r)
         if (L->rowEll[r] < 0) L->rowEll[r] = 0; /* long rows own no ELL entries */
 
     ehyb_layout_view *v = &L->v;
-    v->n = n; v->ncols = ncols; v->nnz = rowPtr[n];
+    v->n = nRows; v->ncols = ncols; v->nnz = rowPtr[nRows];
     v->nParts = P; v->W = W; v->ctasPerPart = opts->ctasPerPart > 0 ? opts->ctasPerPart : 1; v->nSlices = nSlices;
     v->parts = L->parts; v->slices = L->slices; v->blob = L->blob; v->blobBytes = blobBytes;
     v->nOverflow = nOvf; v->ovfRow = L->ovfRow; v->ovfCol = L->ovfCol; v->ovfVal = L->ovfVal;
@@ -476,7 +494,7 @@ static int layout_build_impl(int64_t n64, const int64_t *rowPtr, const int32_t *
     v->haloInOverflow = haloOvf;
     v->nnzEll = nnzEll; v->nnzRemInSlice = nnzRemIn; v->nnzOverflow = nnzOvf;
     v->padEll = padEll; v->padRem = padRem; v->nLongRows = nLong;
-    v->algBytes = 8 * v->nnz + 2 * nnzEll + 4 * (v->nnz - nnzEll) + 8 * ncols + 8 * (int64_t)n;
+    v->algBytes = 8 * v->nnz + 2 * nnzEll + 4 * (v->nnz - nnzEll) + (isChunk ? 0 : 8 * ncols + 8 * (int64_t)n); /* x and y once per matrix */
     v->formatBytes = blobBytes + (int64_t)nSlices * (int64_t)sizeof(ehyb_slice_desc) +
                      (int64_t)P * (int64_t)sizeof(ehyb_part_desc) + nOvf * 16 + cacheTotal * 4;
     if (nnzEll + nnzRemIn + nnzOvf != v->nnz) { rc = ehyb_fail(EHYB_ERR_ARG, "layout: entry count mismatch"); goto fail; }
@@ -518,6 +536,182 @@ int ehyb_layout_build(const matrixCOO *m, const ehyb_layout_opts *opts_in, ehyb_
 }
 
 /* ---------------------------------------------------------------------------------- */
+/* streamed build: the matrix arrives as chunks of consecutive partitions               */
+/* ---------------------------------------------------------------------------------- */
+
+/*
+ * The one-shot build holds the whole permuted matrix (12 B per entry) next to the layout
+ * (~10.5 B per entry) - and its callers the generator output and the unpermuted copy before that:
+ * ~70 B per entry at the peak, which is what kept BASELINE.json config 5 (27-point 512^3, 3.6 G
+ * entries) out of reach.  The builder takes the permuted rows a few partitions at a time
+ * (CSR, absolute local column numbers: the permutation is known up front) and appends their
+ * slices to one blob, so the peak is the layout itself plus one chunk.  The result is the layout
+ * the one-shot build produces for the same rows, options and er_fill >= 0, byte for byte
+ * (tests/test_stream_build.py); er_fill < 0 chooses per chunk instead of per matrix.
+ */
+struct ehyb_layout_builder {
+    ehyb_layout_opts opts;
+    int64_t n, ncols;
+    ehyb_layout *L;
+    int64_t rowsDone;
+    int64_t partsCap, slicesCap, blobCap, cacheCap, ovfCap;
+    int keepRowInfo;
+};
+
+void ehyb_layout_builder_abort(ehyb_layout_builder *B)
+{
+    if (!B) return;
+    ehyb_layout_free(B->L);
+    free(B);
+}
+
+int ehyb_layout_builder_begin(int64_t n, const ehyb_layout_opts *opts, ehyb_layout_builder **out)
+{
+    if (!opts || !out || n <= 0 || n > INT_MAX || opts->W <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_builder_begin: bad argument");
+    ehyb_layout_builder *B = (ehyb_layout_builder *)calloc(1, sizeof *B);
+    if (!B) return ehyb_fail(EHYB_ERR_NOMEM, "layout builder: out of memory");
+    B->opts = *opts;
+    B->n = n;
+    B->ncols = opts->ncols > 0 ? opts->ncols : n;
+    B->opts.ncols = B->ncols;
+    B->opts.min_coverage = -1.0; /* the all-overflow fallback is a whole-matrix decision */
+    B->L = (ehyb_layout *)calloc(1, sizeof(ehyb_layout));
+    if (!B->L) { free(B); return ehyb_fail(EHYB_ERR_NOMEM, "layout builder: out of memory"); }
+    /* per-row bookkeeping (20 B per row) only serves the de-interleave and the cache file */
+    B->keepRowInfo = n <= ((int64_t)64 << 20);
+    if (B->keepRowInfo) {
+        B->L->rowEll = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+        B->L->rowRemIn = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+        B->L->rowCached = (int32_t *)calloc((size_t)n, sizeof(int32_t));
+        B->L->ovfPtr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
+        if (!B->L->rowEll || !B->L->rowRemIn || !B->L->rowCached || !B->L->ovfPtr) { ehyb_layout_builder_abort(B); return ehyb_fail(EHYB_ERR_NOMEM, "layout builder: out of memory"); }
+    }
+    *out = B;
+    return EHYB_OK;
+}
+
+static int grow(void **p, int64_t *cap, int64_t need, size_t elem)
+{
+    if (need <= *cap) return 0;
+    int64_t nc = *cap + *cap / 2 + 1024;
+    if (nc < need) nc = need;
+    void *q = realloc(*p, (size_t)nc * elem);
+    if (!q) return -1;
+    *p = q;
+    *cap = nc;
+    return 0;
+}
+
+int ehyb_layout_builder_add(ehyb_layout_builder *B, int nParts, const int32_t *partBoundary, const int64_t *rowPtr, const int32_t *col,
+                            const double *val)
+{
+    if (!B || !partBoundary || !rowPtr || !col || !val || nParts <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_builder_add: bad argument");
+    if (partBoundary[0] != B->rowsDone) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_builder_add: the chunk starts at row %d, %lld rows were added so far", partBoundary[0], (long long)B->rowsDone);
+    const int64_t nRows = (int64_t)partBoundary[nParts] - partBoundary[0];
+    if (nRows <= 0 || B->rowsDone + nRows > B->n) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_builder_add: bad row range");
+    ehyb_layout *L = B->L, *C = NULL;
+    ehyb_layout_view *v = &L->v;
+    /* the blob: allocated after the first chunk from its bytes per row (+3 %), zero-filled lazily
+     * by calloc; later chunks are written in place while they fit */
+    blob_target bt = {NULL, 0, 0};
+    if (L->blob && v->blobBytes < B->blobCap) { bt.dst = L->blob + v->blobBytes; bt.cap = B->blobCap - v->blobBytes; }
+    int rc;
+    if (nRows == B->n) rc = layout_build_impl(B->n, 0, nRows, rowPtr, col, val, nParts, partBoundary, &B->opts, 0, NULL, &C);
+    else rc = layout_build_impl(B->n, B->rowsDone, nRows, rowPtr, col, val, nParts, partBoundary, &B->opts, 0, &bt, &C);
+    if (rc) return rc;
+    const ehyb_layout_view *cv = &C->v;
+    rc = EHYB_ERR_NOMEM;
+    if (grow((void **)&L->parts, &B->partsCap, (int64_t)v->nParts + nParts, sizeof(ehyb_part_desc))) goto done;
+    if (grow((void **)&L->slices, &B->slicesCap, (int64_t)v->nSlices + cv->nSlices, sizeof(ehyb_slice_desc))) goto done;
+    if (grow((void **)&L->cacheCols, &B->cacheCap, v->cacheTotal + cv->cacheTotal + 1, sizeof(int32_t))) goto done;
+    if (cv->nOverflow > 0) {
+        int64_t c1 = B->ovfCap, c2 = B->ovfCap, c3 = B->ovfCap;
+        if (grow((void **)&L->ovfRow, &c1, v->nOverflow + cv->nOverflow, sizeof(int32_t)) || grow((void **)&L->ovfCol, &c2, v->nOverflow + cv->nOverflow, sizeof(int32_t)) ||
+            grow((void **)&L->ovfVal, &c3, v->nOverflow + cv->nOverflow, sizeof(double))) goto done;
+        B->ovfCap = c1 < c2 ? (c1 < c3 ? c1 : c3) : (c2 < c3 ? c2 : c3);
+    }
+    if ((v->blobBytes + cv->blobBytes) / 256 > (int64_t)UINT32_MAX || (int64_t)v->nSlices + cv->nSlices > INT_MAX || v->cacheTotal + cv->cacheTotal > INT_MAX ||
+        v->nOverflow + cv->nOverflow > INT_MAX) { rc = ehyb_fail(EHYB_ERR_LIMIT, "layout builder: a 32-bit offset would overflow"); goto done; }
+    if (!bt.used) {
+        if (v->blobBytes + cv->blobBytes > B->blobCap) {
+            /* first chunk: size the blob for the whole matrix; later: the estimate was short */
+            const double perRow = (double)(v->blobBytes + cv->blobBytes) / (double)(B->rowsDone + nRows);
+            int64_t want = (int64_t)(perRow * (double)B->n * 1.03) + ((int64_t)1 << 20);
+            if (want < v->blobBytes + cv->blobBytes) want = v->blobBytes + cv->blobBytes;
+            want = (want + 255) & ~(int64_t)255;
+            unsigned char *nb = (unsigned char *)calloc((size_t)want, 1);
+            if (!nb) { rc = ehyb_fail(EHYB_ERR_NOMEM, "layout builder: out of memory (%lld bytes)", (long long)want); goto done; }
+            if (v->blobBytes) memcpy(nb, L->blob, (size_t)v->blobBytes);
+            free(L->blob);
+            L->blob = nb;
+            B->blobCap = want;
+        }
+        memcpy(L->blob + v->blobBytes, cv->blob, (size_t)cv->blobBytes);
+    }
+    for (int p = 0; p < nParts; ++p) {
+        ehyb_part_desc d = cv->parts[p];
+        d.sliceStart += v->nSlices; d.sliceEnd += v->nSlices;
+        d.cacheStart += (int32_t)v->cacheTotal;
+        L->parts[v->nParts + p] = d;
+    }
+    const uint32_t off0 = (uint32_t)(v->blobBytes / 256);
+    for (int s2 = 0; s2 < cv->nSlices; ++s2) {
+        ehyb_slice_desc d = cv->slices[s2];
+        d.off256 += off0;
+        L->slices[v->nSlices + s2] = d;
+    }
+    if (cv->cacheTotal) memcpy(L->cacheCols + v->cacheTotal, cv->cacheCols, (size_t)cv->cacheTotal * sizeof(int32_t));
+    if (cv->nOverflow) {
+        memcpy(L->ovfRow + v->nOverflow, cv->ovfRow, (size_t)cv->nOverflow * sizeof(int32_t));
+        memcpy(L->ovfCol + v->nOverflow, cv->ovfCol, (size_t)cv->nOverflow * sizeof(int32_t));
+        memcpy(L->ovfVal + v->nOverflow, cv->ovfVal, (size_t)cv->nOverflow * sizeof(double));
+    }
+    if (B->keepRowInfo) {
+        memcpy(L->rowEll + B->rowsDone, C->rowEll, (size_t)nRows * sizeof(int32_t));
+        memcpy(L->rowRemIn + B->rowsDone, C->rowRemIn, (size_t)nRows * sizeof(int32_t));
+        memcpy(L->rowCached + B->rowsDone, C->rowCached, (size_t)nRows * sizeof(int32_t));
+        for (int64_t r = 0; r <= nRows; ++r) L->ovfPtr[B->rowsDone + r] = v->nOverflow + C->ovfPtr[r];
+    }
+    v->nParts += nParts; v->nSlices += cv->nSlices; v->blobBytes += cv->blobBytes; v->cacheTotal += cv->cacheTotal; v->nOverflow += cv->nOverflow;
+    if (cv->cacheMax > v->cacheMax) v->cacheMax = cv->cacheMax;
+    v->nnz += cv->nnz; v->nnzEll += cv->nnzEll; v->nnzRemInSlice += cv->nnzRemInSlice; v->nnzOverflow += cv->nnzOverflow;
+    v->padEll += cv->padEll; v->padRem += cv->padRem; v->nLongRows += cv->nLongRows;
+    v->haloInOverflow = cv->haloInOverflow;
+    v->ctasPerPart = cv->ctasPerPart;
+    B->rowsDone += nRows;
+    rc = EHYB_OK;
+done:
+    if (rc == EHYB_ERR_NOMEM) ehyb_fail(EHYB_ERR_NOMEM, "layout builder: out of memory");
+    ehyb_layout_free(C);
+    return rc;
+}
+
+int ehyb_layout_builder_finish(ehyb_layout_builder *B, ehyb_layout **out)
+{
+    if (!B || !out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_builder_finish: NULL argument");
+    if (B->rowsDone != B->n) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_builder_finish: %lld of %lld rows were added", (long long)B->rowsDone, (long long)B->n);
+    ehyb_layout *L = B->L;
+    ehyb_layout_view *v = &L->v;
+    if (B->blobCap > v->blobBytes + ((int64_t)1 << 20)) { /* give the unused tail of the estimate back */
+        unsigned char *nb = (unsigned char *)realloc(L->blob, (size_t)(v->blobBytes ? v->blobBytes : 256));
+        if (nb) L->blob = nb;
+    }
+    if (!L->ovfRow) { /* the device session expects valid (if empty) arrays */
+        L->ovfRow = (int32_t *)malloc(sizeof(int32_t)); L->ovfCol = (int32_t *)malloc(sizeof(int32_t)); L->ovfVal = (double *)malloc(sizeof(double));
+    }
+    if (!L->cacheCols) L->cacheCols = (int32_t *)malloc(sizeof(int32_t));
+    v->n = B->n; v->ncols = B->ncols; v->W = B->opts.W;
+    v->parts = L->parts; v->slices = L->slices; v->blob = L->blob;
+    v->ovfRow = L->ovfRow; v->ovfCol = L->ovfCol; v->ovfVal = L->ovfVal; v->cacheCols = L->cacheCols;
+    v->algBytes = 8 * v->nnz + 2 * v->nnzEll + 4 * (v->nnz - v->nnzEll) + 8 * v->ncols + 8 * v->n;
+    v->formatBytes = v->blobBytes + (int64_t)v->nSlices * (int64_t)sizeof(ehyb_slice_desc) + (int64_t)v->nParts * (int64_t)sizeof(ehyb_part_desc) +
+                     v->nOverflow * 16 + v->cacheTotal * 4;
+    *out = L;
+    free(B);
+    return EHYB_OK;
+}
+
+/* ---------------------------------------------------------------------------------- */
 /* de-interleave: tuned layout -> reference layout                                     */
 /* ---------------------------------------------------------------------------------- */
 
@@ -526,6 +720,7 @@ int ehyb_layout_to_reference(const ehyb_layout *L, matrixEHYB *out, int *sizeBlo
     if (!L || !out || !sizeBlockELL || !sizeER) return ehyb_fail(EHYB_ERR_ARG, "ehyb_layout_to_reference: NULL argument");
     const ehyb_layout_view *v = &L->v;
     if (v->nnz > INT_MAX || v->ncols != v->n) return ehyb_fail(EHYB_ERR_LIMIT, "reference layout needs nnz < 2^31 and no halo columns");
+    if (!L->rowEll || !L->ovfPtr) return ehyb_fail(EHYB_ERR_LIMIT, "this layout was streamed without its per-row bookkeeping (more than 64 M rows)");
     const int n = (int)v->n, P = v->nParts;
     const int64_t nnz = v->nnz;
     matrixCOO c;

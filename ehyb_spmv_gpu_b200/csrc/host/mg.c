@@ -26,29 +26,7 @@
 #include <string.h>
 #include "common.h"
 
-struct ehyb_mg_local {
-    int rank, nranks;
-    int64_t *rowStarts; /* [nranks+1] */
-    int64_t n;          /* local rows */
-    int64_t nnz;
-    /* local matrix, columns renumbered [own | halo]; natural local row order until finish() */
-    int64_t *rowPtr;
-    int32_t *col;
-    double *val;
-    /* halo */
-    int64_t nHalo;
-    int64_t *haloGlobal; /* [nHalo] sorted global columns */
-    int64_t *recvCount;  /* [nranks] */
-    /* send */
-    int64_t nSend;
-    int64_t *sendCount;  /* [nranks] */
-    int64_t *sendGlobal; /* [nSend] global rows peers need, grouped by peer */
-    int32_t *sendIdx;    /* [nSend] the same as permuted local indices (after finish) */
-    /* level 2 */
-    matrixCOO coo;       /* permuted local block (after finish) */
-    int finished;
-    ehyb_layout *layout;
-};
+#include "mg_internal.h"
 
 static int cmp_i64(const void *a, const void *b)
 {
@@ -61,7 +39,8 @@ void ehyb_mg_local_free(ehyb_mg_local *L)
     if (!L) return;
     free(L->rowStarts); free(L->rowPtr); free(L->col); free(L->val);
     free(L->haloGlobal); free(L->recvCount); free(L->sendCount); free(L->sendGlobal); free(L->sendIdx);
-    if (L->finished) ehyb_coo_free(&L->coo);
+    if (L->finished && !L->streamed) ehyb_coo_free(&L->coo);
+    free(L->perm);
     ehyb_layout_free(L->layout);
     free(L);
 }
@@ -166,6 +145,18 @@ int ehyb_mg_local_set_send(ehyb_mg_local *L, const int64_t *sendCount, const int
     memcpy(L->sendCount, sendCount, (size_t)L->nranks * sizeof(int64_t));
     if (tot) memcpy(L->sendGlobal, sendGlobal, (size_t)tot * sizeof(int64_t));
     L->nSend = tot;
+    return ehyb_mg_local_update_send_idx(L);
+}
+
+int ehyb_mg_local_update_send_idx(ehyb_mg_local *L)
+{
+    const int32_t *perm = L->streamed ? L->perm : L->coo.reorderList;
+    if (!L->finished || !perm) return EHYB_OK; /* set_send came first: finish() calls again */
+    free(L->sendIdx);
+    L->sendIdx = (int32_t *)malloc((size_t)(L->nSend ? L->nSend : 1) * sizeof(int32_t));
+    if (!L->sendIdx) return ehyb_fail(EHYB_ERR_NOMEM, "mg: out of memory");
+    const int64_t r0 = L->rowStarts[L->rank];
+    for (int64_t i = 0; i < L->nSend; ++i) L->sendIdx[i] = perm[L->sendGlobal[i] - r0];
     return EHYB_OK;
 }
 
@@ -224,11 +215,8 @@ int ehyb_mg_local_finish(ehyb_mg_local *L, int nParts, int W, int ctasPerPart, c
     free(pv);
     if (rc) return rc;
     /* send list in permuted local numbering */
-    free(L->sendIdx);
-    L->sendIdx = (int32_t *)malloc((size_t)(L->nSend ? L->nSend : 1) * sizeof(int32_t));
-    if (!L->sendIdx) return ehyb_fail(EHYB_ERR_NOMEM, "mg: out of memory");
-    const int64_t r0 = L->rowStarts[L->rank];
-    for (int64_t i = 0; i < L->nSend; ++i) L->sendIdx[i] = m->reorderList[L->sendGlobal[i] - r0];
+    rc = ehyb_mg_local_update_send_idx(L);
+    if (rc) return rc;
     ehyb_layout_opts o;
     memset(&o, 0, sizeof o);
     o.W = W; o.ctasPerPart = ctasPerPart > 0 ? ctasPerPart : 1; o.er_fill = er_fill;
@@ -244,7 +232,7 @@ int ehyb_mg_local_view(const ehyb_mg_local *L, const matrixCOO **coo, const ehyb
                        const int32_t **sendIdx, const int64_t **sendCount)
 {
     if (!L || !L->finished) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_local_view: not finished");
-    if (coo) *coo = &L->coo;
+    if (coo) *coo = L->streamed ? NULL : &L->coo;
     if (layout) *layout = L->layout;
     if (nSend) *nSend = L->nSend;
     if (sendIdx) *sendIdx = L->sendIdx;

@@ -50,8 +50,9 @@ static int find_helper(char *out, size_t cap)
     return -1;
 }
 
-static int helper_partition(uint32_t n, const uint32_t *xadj, const uint32_t *adjncy, uint32_t nparts,
-                            uint32_t nthreads, float ub, uint32_t *where)
+/* vwgt / adjwgt: both NULL (the reference's call) or both given (coarsened graphs, grid.c) */
+static int helper_partition(uint32_t n, const uint32_t *xadj, const uint32_t *adjncy, const int32_t *vwgt, const int32_t *adjwgt,
+                            uint32_t nparts, uint32_t nthreads, float ub, uint32_t *where)
 {
     char bin[1024];
     if (find_helper(bin, sizeof bin))
@@ -62,10 +63,11 @@ static int helper_partition(uint32_t n, const uint32_t *xadj, const uint32_t *ad
     if (gfd < 0 || wfd < 0) return ehyb_fail(EHYB_ERR_IO, "mkstemp failed");
     close(wfd);
     FILE *f = fdopen(gfd, "wb");
-    uint32_t hdr[4] = {0x47594845u, n, nparts, nthreads};
+    uint32_t hdr[4] = {vwgt ? 0x57594845u /* 'EHYW': weights follow */ : 0x47594845u /* 'EHYG' */, n, nparts, nthreads};
     int bad = fwrite(hdr, sizeof hdr, 1, f) != 1 || fwrite(&ub, 4, 1, f) != 1 ||
               fwrite(xadj, 4, (size_t)n + 1, f) != (size_t)n + 1 ||
               fwrite(adjncy, 4, xadj[n], f) != xadj[n];
+    if (!bad && vwgt) bad = fwrite(vwgt, 4, n, f) != n || fwrite(adjwgt, 4, xadj[n], f) != xadj[n];
     bad |= fclose(f) != 0;
     int rc = EHYB_OK;
     if (bad) {
@@ -102,7 +104,24 @@ int ehyb_partition_graph(uint32_t n, const uint32_t *xadj, const uint32_t *adjnc
     }
     const float ub = 1.001f; /* reordering.c:273 */
     int rc = g_fn ? g_fn(n, xadj, adjncy, nparts, nthreads, ub, where, g_user)
-                  : helper_partition(n, xadj, adjncy, nparts, nthreads, ub, where);
+                  : helper_partition(n, xadj, adjncy, NULL, NULL, nparts, nthreads, ub, where);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; ++i)
+        if (where[i] >= nparts) return ehyb_fail(EHYB_ERR_PARTITION, "partitioner returned part %u >= %u", where[i], nparts);
+    return EHYB_OK;
+}
+
+/* The same call with vertex and edge weights: the level-1 partition of a COARSENED graph (bricks
+ * of a grid, grid.c) into one block per GPU.  Always through the helper binary. */
+int ehyb_partition_graph_weighted(uint32_t n, const uint32_t *xadj, const uint32_t *adjncy, const int32_t *vwgt, const int32_t *adjwgt,
+                                  uint32_t nparts, uint32_t nthreads, float ubvec, uint32_t *where)
+{
+    if (!xadj || !adjncy || !vwgt || !adjwgt || !where || nparts == 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_partition_graph_weighted: bad argument");
+    if (nparts == 1) {
+        memset(where, 0, (size_t)n * sizeof(uint32_t));
+        return EHYB_OK;
+    }
+    int rc = helper_partition(n, xadj, adjncy, vwgt, adjwgt, nparts, nthreads, ubvec > 1.0f ? ubvec : 1.001f, where);
     if (rc) return rc;
     for (uint32_t i = 0; i < n; ++i)
         if (where[i] >= nparts) return ehyb_fail(EHYB_ERR_PARTITION, "partitioner returned part %u >= %u", where[i], nparts);

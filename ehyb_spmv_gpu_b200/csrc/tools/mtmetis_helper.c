@@ -8,8 +8,10 @@
  * (unsymmetric, 6 threads): ncon 1, no weights, ubvec 1.001, default options otherwise.
  *
  * usage: ehyb_mtmetis <graph.bin> <where.bin>
- *   graph.bin : u32 magic 'EHYG', u32 nvtxs, u32 nparts, u32 nthreads, f32 ubvec,
+ *   graph.bin : u32 magic 'EHYG' | 'EHYW', u32 nvtxs, u32 nparts, u32 nthreads, f32 ubvec,
  *               u32 xadj[nvtxs+1], u32 adjncy[xadj[nvtxs]]
+ *               'EHYW' only (coarsened graphs: the level-1 partition into GPU blocks):
+ *               i32 vwgt[nvtxs], i32 adjwgt[xadj[nvtxs]]
  *   where.bin : i32 edgecut, u32 where[nvtxs]
  */
 #include <stdio.h>
@@ -18,6 +20,7 @@
 #include "mtmetis_abi.h"
 
 #define EHYG_MAGIC 0x47594845u
+#define EHYW_MAGIC 0x57594845u
 
 static int read_all(FILE *f, void *p, size_t bytes)
 {
@@ -34,7 +37,7 @@ int main(int argc, char **argv)
     if (!f) { perror(argv[1]); return 1; }
     uint32_t hdr[4];
     float ub;
-    if (read_all(f, hdr, sizeof hdr) || read_all(f, &ub, sizeof ub) || hdr[0] != EHYG_MAGIC) {
+    if (read_all(f, hdr, sizeof hdr) || read_all(f, &ub, sizeof ub) || (hdr[0] != EHYG_MAGIC && hdr[0] != EHYW_MAGIC)) {
         fprintf(stderr, "ehyb_mtmetis: bad header\n");
         return 1;
     }
@@ -44,6 +47,12 @@ int main(int argc, char **argv)
     size_t nadj = xadj[n];
     uint32_t *adj = (uint32_t *)malloc((nadj ? nadj : 1) * sizeof(uint32_t));
     if (!adj || read_all(f, adj, nadj * sizeof(uint32_t))) return 1;
+    ehyb_mtm_wgt *vwgt = NULL, *adjwgt = NULL;
+    if (hdr[0] == EHYW_MAGIC) {
+        vwgt = (ehyb_mtm_wgt *)malloc((n ? n : 1) * sizeof(ehyb_mtm_wgt));
+        adjwgt = (ehyb_mtm_wgt *)malloc((nadj ? nadj : 1) * sizeof(ehyb_mtm_wgt));
+        if (!vwgt || !adjwgt || read_all(f, vwgt, (size_t)n * sizeof(ehyb_mtm_wgt)) || read_all(f, adjwgt, nadj * sizeof(ehyb_mtm_wgt))) return 1;
+    }
     fclose(f);
 
     uint32_t *where = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t));
@@ -51,7 +60,7 @@ int main(int argc, char **argv)
     options[EHYB_MTMETIS_OPTION_NTHREADS] = (double)nthreads;
     ehyb_mtm_vtx ncon = 1;
     ehyb_mtm_wgt cut = 0;
-    int rc = MTMETIS_PartGraphKway(&n, &ncon, xadj, adj, NULL, NULL, NULL, &nparts, NULL, &ub,
+    int rc = MTMETIS_PartGraphKway(&n, &ncon, xadj, adj, vwgt, NULL, adjwgt, &nparts, NULL, &ub,
                                    options, &cut, where);
     if (rc != EHYB_MTMETIS_SUCCESS) {
         fprintf(stderr, "ehyb_mtmetis: MTMETIS_PartGraphKway returned %d\n", rc);

@@ -181,6 +181,138 @@ class DistributedBlock:
             self.h = C.c_void_p()
 
 
+class GridDecomp:
+    """27-point stencil grid cut into bricks, bricks assigned to ranks (ehyb_grid_decomp)."""
+
+    def __init__(self, grid, brick, world, owner=None):
+        self.lib = L.load()
+        self.grid, self.brick, self.world = tuple(grid), tuple(brick), world
+        self.h = C.c_void_p()
+        ow = np.ascontiguousarray(owner, np.uint32) if owner is not None else None
+        check(self.lib, self.lib.ehyb_grid_decomp_create(*self.grid, *self.brick, world, ow.ctypes.data_as(L.c_u32_p) if ow is not None else None,
+                                                         C.byref(self.h)), "ehyb_grid_decomp_create")
+        nb = C.c_int64(); rs = L.c_i64_p(); own = C.POINTER(C.c_int32)()
+        check(self.lib, self.lib.ehyb_grid_decomp_info(self.h, C.byref(nb), C.byref(rs), C.byref(own)), "ehyb_grid_decomp_info")
+        self.nBricks = nb.value
+        self.rowStarts = api._np(rs, world + 1, np.int64)
+        self.owner = api._np(own, self.nBricks, np.int32)
+
+    @staticmethod
+    def brick_graph(grid, brick):
+        lib = L.load()
+        nb = C.c_int64(); xadj = L.c_u32_p(); adj = L.c_u32_p(); vw = C.POINTER(C.c_int32)(); aw = C.POINTER(C.c_int32)()
+        check(lib, lib.ehyb_grid_brick_graph(*grid, *brick, C.byref(nb), C.byref(xadj), C.byref(adj), C.byref(vw), C.byref(aw)),
+              "ehyb_grid_brick_graph")
+        xa = api._np(xadj, nb.value + 1, np.uint32)
+        out = xa, api._np(adj, int(xa[-1]), np.uint32), api._np(vw, nb.value, np.int32), api._np(aw, int(xa[-1]), np.int32)
+        for q in (xadj, adj, vw, aw):
+            lib.ehyb_free_host(q)
+        return out
+
+    @staticmethod
+    def level1_metis(grid, brick, world, nthreads=1, ubvec=1.001):
+        """owner[brick] = mt-metis k = world partition of the weighted brick graph (the reference's
+        call, reordering.c:270-293, on the coarsened graph)."""
+        lib = L.load()
+        xa, ad, vw, aw = GridDecomp.brick_graph(grid, brick)
+        where = np.zeros(len(vw), np.uint32)
+        check(lib, lib.ehyb_partition_graph_weighted(C.c_uint32(len(vw)), xa.ctypes.data_as(L.c_u32_p), ad.ctypes.data_as(L.c_u32_p),
+                                                     vw.ctypes.data_as(C.POINTER(C.c_int32)), aw.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     C.c_uint32(world), C.c_uint32(nthreads), C.c_float(ubvec),
+                                                     where.ctypes.data_as(L.c_u32_p)), "ehyb_partition_graph_weighted")
+        return where
+
+    def rows(self, rank):
+        """All rows of a rank (level-1 order and column ids) + partVec = brick ordinal: the general path's input."""
+        rp = L.c_i64_p(); col = L.c_i64_p(); val = L.c_dbl_p(); pv = L.c_u32_p()
+        check(self.lib, self.lib.ehyb_grid_rows(self.h, rank, C.byref(rp), C.byref(col), C.byref(val), C.byref(pv)), "ehyb_grid_rows")
+        n = int(self.rowStarts[rank + 1] - self.rowStarts[rank])
+        rowPtr = api._np(rp, n + 1, np.int64)
+        out = rowPtr, api._np(col, int(rowPtr[-1]), np.int64), api._np(val, int(rowPtr[-1]), np.float64), api._np(pv, n, np.uint32)
+        for q in (rp, col, val, pv):
+            self.lib.ehyb_free_host(q)
+        return out
+
+    def natural_ids(self, level1):
+        level1 = np.ascontiguousarray(level1, np.int64)
+        out = np.empty(len(level1), np.int64)
+        check(self.lib, self.lib.ehyb_grid_natural_ids(self.h, C.c_int64(len(level1)), level1.ctypes.data_as(L.c_i64_p),
+                                                       out.ctypes.data_as(L.c_i64_p)), "ehyb_grid_natural_ids")
+        return out
+
+    def free(self):
+        if self.h:
+            self.lib.ehyb_grid_decomp_free(self.h)
+            self.h = C.c_void_p()
+
+
+class GridBlock(DistributedBlock):
+    """A rank's block of a brick-decomposed stencil grid, streamed into the tuned layout
+    (ehyb_mg_grid_build): no matrixCOO exists; x and y live in permuted local order and
+    natural_ids() tells which grid cell every entry belongs to."""
+
+    def __init__(self, decomp: GridDecomp, rank, er_fill=0.0, exchange="p2p", chunk_bricks=0):
+        self.lib = L.load()
+        self.decomp = decomp
+        self.rank, self.world = rank, decomp.world
+        self.rowStarts = decomp.rowStarts.copy()
+        self.n = int(self.rowStarts[rank + 1] - self.rowStarts[rank])
+        self.exchange = exchange
+        self.h = C.c_void_p()
+        check(self.lib, self.lib.ehyb_mg_grid_build(decomp.h, rank, C.c_double(er_fill), EXCHANGES[exchange], chunk_bricks, C.byref(self.h)),
+              "ehyb_mg_grid_build")
+        nh = C.c_int64(); hg = L.c_i64_p(); rc = L.c_i64_p()
+        check(self.lib, self.lib.ehyb_mg_local_halo(self.h, C.byref(nh), C.byref(hg), C.byref(rc)), "ehyb_mg_local_halo")
+        self.nHalo = nh.value
+        self.haloGlobal = api._np(hg, self.nHalo, np.int64)
+        self.recvCount = api._np(rc, self.world, np.int64)
+        self.session = None
+        self.coo = None
+        self._view()
+
+    def _view(self):
+        coo = C.POINTER(MatrixCOO)(); lay = C.c_void_p(); ns = C.c_int64(); si = C.POINTER(C.c_int32)(); sc = L.c_i64_p()
+        check(self.lib, self.lib.ehyb_mg_local_view(self.h, C.byref(coo), C.byref(lay), C.byref(ns), C.byref(si), C.byref(sc)),
+              "ehyb_mg_local_view")
+        self.sendIdx = api._np(si, ns.value, np.int32) if ns.value else np.zeros(0, np.int32)
+        v = api.LayoutView()
+        check(self.lib, self.lib.ehyb_layout_get(lay, C.byref(v)), "ehyb_layout_get")
+        self.stats = {k: getattr(v, k) for k in ("n", "ncols", "nnz", "nParts", "W", "nSlices", "nOverflow", "nnzEll",
+                                                 "nnzRemInSlice", "nnzOverflow", "algBytes", "formatBytes", "cacheMax",
+                                                 "haloInOverflow")}
+        self.layout = lay
+
+    def set_send(self, all_needs):
+        super().set_send(all_needs)
+        self._view()  # the send list in permuted local numbering exists now
+
+    def natural_ids(self):
+        out = np.empty(self.n, np.int64)
+        check(self.lib, self.lib.ehyb_mg_local_natural_ids(self.h, out.ctypes.data_as(L.c_i64_p)), "ehyb_mg_local_natural_ids")
+        return out
+
+    def halo_natural_ids(self):
+        return self.decomp.natural_ids(self.haloGlobal)
+
+
+def setup_grid(rank, world, grid, brick, dist, level1="metis", exchange="p2p", er_fill=0.0):
+    """Rank's block of the 27-point stencil on `grid` cut into `brick`s: level 1 = mt-metis on the
+    brick graph (rank 0 runs it, every rank gets the owner vector) or contiguous runs of bricks."""
+    owner = None
+    if level1 == "metis" and world > 1:
+        box = [GridDecomp.level1_metis(grid, brick, world) if rank == 0 else None]
+        if dist is not None:
+            dist.broadcast_object_list(box, src=0)
+        owner = box[0]
+    dec = GridDecomp(grid, brick, world, owner)
+    blk = GridBlock(dec, rank, er_fill=er_fill, exchange=exchange)
+    if world > 1:
+        blk.exchange_lists(dist)
+    else:
+        blk.set_send([[np.zeros(0, np.int64)]])
+    return blk, dec
+
+
 EXCHANGES = {"nccl": 0, "p2p": 1}  # EHYB_MG_NCCL, EHYB_MG_P2P
 P2P_BLOB_BYTES = 128               # EHYB_MG_P2P_BLOB_BYTES
 

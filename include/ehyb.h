@@ -199,6 +199,21 @@ int ehyb_layout_get(const ehyb_layout *L, ehyb_layout_view *view);
 int ehyb_layout_to_reference(const ehyb_layout *L, matrixEHYB *out, int *sizeBlockELL, int *sizeER);
 void ehyb_layout_free(ehyb_layout *L);
 
+/* Streamed build (BASELINE.json config 5: 3.6 G entries never exist as one COO): the permuted
+ * matrix arrives a few consecutive partitions at a time - rows [partBoundary[0],
+ * partBoundary[nParts]) as CSR with rowPtr relative to the chunk (rowPtr[0] == 0) and absolute
+ * local column numbers - and the slices are appended to one blob; peak memory = the layout + one
+ * chunk.  Same layout as ehyb_layout_build_csr of the whole matrix, byte for byte, for
+ * er_fill >= 0 (er_fill < 0 decides per chunk); opts->W must be set; the all-overflow fallback
+ * (min_coverage) does not apply.  Layouts of more than 64 M rows drop the per-row bookkeeping
+ * that only ehyb_layout_to_reference and the cache file need. */
+typedef struct ehyb_layout_builder ehyb_layout_builder;
+int ehyb_layout_builder_begin(int64_t n, const ehyb_layout_opts *opts, ehyb_layout_builder **out);
+int ehyb_layout_builder_add(ehyb_layout_builder *B, int nParts, const int32_t *partBoundary, const int64_t *rowPtr,
+                            const int32_t *col, const double *val);
+int ehyb_layout_builder_finish(ehyb_layout_builder *B, ehyb_layout **out); /* releases B */
+void ehyb_layout_builder_abort(ehyb_layout_builder *B);
+
 /* Binary cache (the reference re-runs reader, mt-metis, reorder and COO2EHYB on
  * every invocation).  ehyb_layout_save/load move a layout alone.  ehyb_cache_save/load move the
  * whole result of the pipeline for a source file: the layout plus - all optional together - the
@@ -374,6 +389,33 @@ void ehyb_mg_session_free(ehyb_mg_session *s);
  * columns ascending): a rank's slab of BASELINE.json config 5, generated in place. */
 int ehyb_gen_stencil27_rows(int nx, int ny, int64_t nz, int64_t z0, int64_t z1, int64_t **rowPtr,
                             int64_t **col, double **val);
+
+/* ---- BASELINE.json config 5: the 27-point stencil on nx x ny x nz, sharded (csrc/host/grid.c) ----
+ * The grid is cut into bricks of bx x by x bz cells.  Level 1 assigns bricks to GPUs (owner[]:
+ * the mt-metis k = nranks partition of ehyb_grid_brick_graph - the call of reordering.c:270-293
+ * on the coarsened graph, with vertex and edge weights - or NULL for contiguous runs of bricks);
+ * level 2: every brick is one EHYB partition.  ehyb_mg_grid_build streams a rank's block into the
+ * tuned layout without ever holding its COO (peak: the layout + 4 B per row + one chunk) and
+ * returns it finished: ehyb_mg_local_halo -> exchange -> ehyb_mg_local_set_send -> session.
+ * Level-1 ids (what the halo and send lists carry) are rank-major, then brick, then cell. */
+typedef struct ehyb_grid_decomp ehyb_grid_decomp;
+int ehyb_grid_brick_graph(int nx, int ny, int nz, int bx, int by, int bz, int64_t *nBricks, uint32_t **xadj, uint32_t **adjncy,
+                          int32_t **vwgt, int32_t **adjwgt);
+/* weighted k-way partition by the pinned mt-metis binary (through bin/ehyb_mtmetis) */
+int ehyb_partition_graph_weighted(uint32_t nvtxs, const uint32_t *xadj, const uint32_t *adjncy, const int32_t *vwgt,
+                                  const int32_t *adjwgt, uint32_t nparts, uint32_t nthreads, float ubvec, uint32_t *where);
+int ehyb_grid_decomp_create(int nx, int ny, int nz, int bx, int by, int bz, int nranks, const uint32_t *owner, ehyb_grid_decomp **out);
+int ehyb_grid_decomp_info(const ehyb_grid_decomp *D, int64_t *nBricks, const int64_t **rowStarts, const int32_t **owner);
+void ehyb_grid_decomp_free(ehyb_grid_decomp *D);
+/* er_fill, exchange: as ehyb_mg_local_finish; chunkBricks bricks per builder call (0 = 64). */
+int ehyb_mg_grid_build(const ehyb_grid_decomp *D, int rank, double er_fill, int exchange, int chunkBricks, ehyb_mg_local **out);
+/* natural grid index (z*ny + y)*nx + x of every local row in permuted order (to fill x, check y) */
+int ehyb_mg_local_natural_ids(const ehyb_mg_local *L, int64_t *out);
+/* natural grid index of level-1 ids (e.g. of a halo list) */
+int ehyb_grid_natural_ids(const ehyb_grid_decomp *D, int64_t count, const int64_t *level1, int64_t *out);
+/* all rows of a rank at once, level-1 order and ids, partVec = brick of the row: the input of
+ * the general path (ehyb_mg_local_build + ehyb_mg_local_finish) - small grids, parity tests */
+int ehyb_grid_rows(const ehyb_grid_decomp *D, int rank, int64_t **rowPtr, int64_t **col, double **val, uint32_t **partVec);
 
 /* pinned host memory for asynchronous host-vector products */
 int ehyb_host_alloc_pinned(size_t bytes, void **out);
