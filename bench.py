@@ -4,14 +4,20 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-A step is one y = A x product.  Workload at every N: BASELINE.json configs[1], the 3-D
-27-point stencil 128^3 (n 2 097 152, nnz 55 742 968, fp64) PER GPU: at N > 1 the global grid
-is 128 x 128 x 128N, rank r owns z-slab r (weak scaling) and the x halo planes are exchanged
-every product INSIDE the main kernel (stores into the neighbours' memory over NVLink, CUDA IPC;
-EHYB_MG_EXCHANGE=nccl selects the NCCL send/recv baseline).  Inputs are resident in HBM when the
-timed region starts; the matrix data (~600 MB) is larger than L2 (126 MB).
-EHYB_BENCH_GRID=NXxNYxNZ [EHYB_BENCH_SCALING=strong] runs other grids / one global grid cut into
-slabs (BASELINE.json configs[4] at a size the host pipeline holds).
+A step is one y = A x product.
+  N = 1  BASELINE.json configs[1]: 3-D 27-point stencil 128^3 (n 2 097 152, nnz 55 742 968, fp64) on one
+         GPU - the configuration the metric is quoted on.
+  N > 1  BASELINE.json configs[4]: 3-D 27-point stencil 512^3 (n 134 217 728, nnz 3 609 741 304) sharded
+         over the N GPUs (strong scaling: the global problem is fixed).  The grid is cut into 16^3
+         bricks; level 1 = the pinned mt-metis k = N partition of the weighted brick graph (metis row
+         blocks -> GPUs), level 2 = one EHYB partition per brick; every rank streams its block into the
+         tuned layout without ever holding a COO (csrc/host/grid.c).  The x halo is exchanged every
+         product INSIDE the persistent kernel (stores into the neighbours' memory over NVLink, CUDA
+         IPC; EHYB_MG_EXCHANGE=nccl selects the NCCL send/recv baseline).
+Inputs are resident in HBM when the timed region starts; the matrix data per GPU (>= 580 MB) is
+larger than L2 (126 MB).  EHYB_BENCH_GRID=NXxNYxNZ sets another global grid (also at N = 1: the same
+brick pipeline on one GPU), EHYB_BENCH_BRICK the brick, EHYB_BENCH_LEVEL1=runs contiguous runs of
+bricks instead of mt-metis; EHYB_BENCH_MG=slab runs round 1's weak-scaling z-slab case (128^3 per GPU).
 
 The JSON line carries: value (GFLOP/s = 2 nnz / t, all ranks), roofline (algorithmic bytes of
 the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json; traffic = DRAM bytes
@@ -39,14 +45,12 @@ sys.path.insert(0, str(ROOT))
 os.environ.setdefault("EHYB_MTMETIS_BIN", str(ROOT / "bin" / "ehyb_mtmetis"))
 
 GRID = (128, 128, 128)  # BASELINE.json configs[1]
-WORKLOAD = "3D 27-point stencil 128^3 (n 2097152, nnz 55742968) fp64, EHYB, per GPU"
-# Other shapes (not the driver's default): EHYB_BENCH_GRID=NXxNYxNZ sets the grid; with
-# EHYB_BENCH_SCALING=strong that grid is the GLOBAL one and rank r owns z-slab r of NZ/N planes
-# (BASELINE.json configs[4], the sharded big stencil), else it is the per-GPU grid (weak).
+WORKLOAD = "3D 27-point stencil 128^3 (n 2097152, nnz 55742968) fp64, EHYB, single B200 (BASELINE.json configs[1])"
+GRID5 = (512, 512, 512)  # BASELINE.json configs[4]
+BRICK = tuple(int(v) for v in os.environ.get("EHYB_BENCH_BRICK", "16x16x16").lower().split("x"))
+SLAB = os.environ.get("EHYB_BENCH_MG") == "slab"  # round 1's weak-scaling case: 128^3 per GPU, z-slabs
 if os.environ.get("EHYB_BENCH_GRID"):
-    GRID = tuple(int(v) for v in os.environ["EHYB_BENCH_GRID"].lower().split("x"))
-    WORKLOAD = "3D 27-point stencil %dx%dx%d fp64, EHYB, %s" % (
-        GRID + ("global grid (strong scaling)" if os.environ.get("EHYB_BENCH_SCALING") == "strong" else "per GPU",))
+    GRID = GRID5 = tuple(int(v) for v in os.environ["EHYB_BENCH_GRID"].lower().split("x"))
 STRONG = os.environ.get("EHYB_BENCH_SCALING") == "strong"
 
 
@@ -193,13 +197,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
 
-    if world > 1:
+    if world > 1 and SLAB:
         grid = GRID
         if STRONG:
             if GRID[2] % world:
                 raise SystemExit("bench.py: strong scaling needs NZ divisible by the number of GPUs")
             grid = (GRID[0], GRID[1], GRID[2] // world)
-        return run_ours_multi(args, rank, world, local, grid, WORKLOAD, "strong" if STRONG else "weak")
+        wl = "3D 27-point stencil %dx%dx%d fp64, EHYB, %s" % (GRID + ("global grid cut into z-slabs" if STRONG else "per GPU (z-slabs)",))
+        return run_ours_multi(args, rank, world, local, grid, wl, "strong" if STRONG else "weak")
+    if world > 1 or os.environ.get("EHYB_BENCH_GRID"):
+        return run_ours_grid(args, rank, world, local)
 
     with stdout_to_stderr():
         m, lay, x, pl, t_prep = build_matrix(GRID)
@@ -427,6 +434,171 @@ def run_ours_multi(args, rank, world, local, grid, workload, scaling="weak"):
     blk.free()
     dist.barrier()
     dist.destroy_process_group()
+
+
+class _NoDist:
+    """world == 1: the collectives of the set-up degenerate"""
+
+    @staticmethod
+    def all_gather_object(out, obj):
+        out[0] = obj
+
+    @staticmethod
+    def barrier():
+        pass
+
+    @staticmethod
+    def broadcast_object_list(box, src=0):
+        pass
+
+
+def run_ours_grid(args, rank, world, local):
+    """BASELINE.json configs[4]: the 27-point stencil on GRID5 sharded over `world` GPUs by mt-metis
+    blocks of bricks, streamed format build, halo exchange inside the persistent kernel.  The oracle
+    (closed-form check vector) is used only for the parity check of one product."""
+    import torch
+    import torch.distributed as tdist
+    from ehyb_spmv_gpu_b200 import _lib as L
+    from ehyb_spmv_gpu_b200._lib import check
+    from ehyb_spmv_gpu_b200.multigpu import p2p_supported, setup_grid, unique_id, x_of_global
+
+    dist = tdist if world > 1 else _NoDist
+    lib = L.load()
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    threads = max(1, cores // world)   # torchrun exports OMP_NUM_THREADS=1: the format build is OpenMP code
+    lib.ehyb_set_host_threads(threads)
+    t0 = time.time()
+    exchange = os.environ.get("EHYB_MG_EXCHANGE", "p2p")
+    if exchange == "p2p" and world > 1:
+        ok = torch.tensor([1 if p2p_supported(local, world) else 0], device="cuda")
+        tdist.all_reduce(ok, op=tdist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            raise SystemExit("bench.py: the GPUs of this box have no peer access; set EHYB_MG_EXCHANGE=nccl")
+    level1 = os.environ.get("EHYB_BENCH_LEVEL1", "metis")
+    with stdout_to_stderr():
+        blk, dec = setup_grid(rank, world, GRID5, BRICK, dist, level1, exchange)
+        t_build = time.time() - t0
+        if exchange == "p2p":
+            blk.create_session_p2p(local, dist)
+        else:
+            ids = [unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            blk.create_session(local, ids[0])
+    t_prep = time.time() - t0
+    nat = blk.natural_ids()
+    x_perm = x_of_global(nat)
+    blk.set_x(x_perm)
+
+    # parity of one distributed product: the closed-form check vector of the stencil (oracle), every row
+    blk.spmv()
+    y = blk.get_y()
+    if blk.timed_out():
+        raise SystemExit("bench.py: rank %d: a neighbour did not deliver its halo" % rank)
+    from oracle import oracle as O
+    orc = O.Oracle()
+    y_ref, absAx = orc.stencil27_rows_product(GRID5, nat)
+    gate_fail = int(np.count_nonzero(~(np.abs(y - y_ref) <= 1e-12 * absAx)))
+    max_err = float(np.abs(y - y_ref).max())
+    del y_ref, absAx, nat
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = blk.time_spmv(args.warmup, args.steps)
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = sampler.stop()
+    peers = int(np.count_nonzero(blk.recvCount))
+    stats = torch.tensor([ms, blk.stats["algBytes"], peers, -peers, blk.nHalo, t_prep], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([blk.stats["nnz"], blk.stats["algBytes"], gate_fail, blk.nHalo, blk.stats["nnzOverflow"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tdist.all_reduce(stats, op=tdist.ReduceOp.MAX)
+        tdist.all_reduce(tot, op=tdist.ReduceOp.SUM)
+    ms_max, alg_max, peers_max, neg_peers_min, halo_max, prep_max = (float(v) for v in stats.tolist())
+    nnz_all, alg_all, gate_all, halo_all, ovf_all = (float(v) for v in tot.tolist())
+
+    # end to end: host x -> device, distributed product, y -> host, every step, pipelined (pinned buffers)
+    pin = []
+    def pinned(count):
+        p = C.c_void_p()
+        check(lib, lib.ehyb_host_alloc_pinned(C.c_size_t(count * 8), C.byref(p)), "ehyb_host_alloc_pinned")
+        pin.append(p)
+        return np.ctypeslib.as_array((C.c_double * count).from_address(p.value))
+    nbuf = 2
+    xs = [pinned(blk.n) for _ in range(nbuf)]
+    ys = [pinned(blk.n) for _ in range(nbuf)]
+    for b in xs:
+        b[:] = x_perm
+    def host_batch(count):
+        xp = (C.c_void_p * count)(*[xs[i % nbuf].ctypes.data for i in range(count)])
+        yp = (C.c_void_p * count)(*[ys[i % nbuf].ctypes.data for i in range(count)])
+        check(lib, lib.ehyb_mg_spmv_host_batch(blk.session, xp, yp, count), "ehyb_mg_spmv_host_batch")
+    host_batch(3)
+    e2e_steps = min(args.steps, 50)
+    dist.barrier()
+    te = time.perf_counter()
+    host_batch(e2e_steps)
+    dist.barrier()
+    te = time.perf_counter() - te
+    e2e_ok = bool(np.array_equal(np.asarray(ys[(e2e_steps - 1) % nbuf]), y)) if blk.stats["nOverflow"] == 0 else True
+    tt = torch.tensor([te], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tdist.all_reduce(tt, op=tdist.ReduceOp.MAX)
+    te = float(tt.item())
+
+    ms_per_step = ms_max / args.steps
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = alg_max / (ms_per_step * 1e6)
+        n_all = int(np.prod(GRID5))
+        is5 = GRID5 == (512, 512, 512)
+        out = {
+            "metric": "fp64 SpMV GFLOP/s (2*nnz/t), EHYB format", "value": round(2.0 * nnz_all / (ms_per_step * 1e6), 2),
+            "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 6), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D 27-point stencil %dx%dx%d (n %d, nnz %d) fp64, EHYB, sharded over %d B200%s"
+                                   % (GRID5 + (n_all, int(nnz_all), world, " (BASELINE.json configs[4])" if is5 else "")),
+                       "global_grid": list(GRID5), "brick": list(BRICK),
+                       "decomposition": ("level 1: mt-metis k=%d partition of the weighted brick graph (bricks -> GPUs); " % world if level1 == "metis" and world > 1
+                                         else "level 1: contiguous runs of bricks; ") + "level 2: one EHYB partition per brick",
+                       "n_per_gpu_rank0": blk.n, "nnz_total": int(nnz_all), "halo_x_entries_total": int(halo_all),
+                       "halo_x_entries_max_per_gpu": int(halo_max), "peers_per_gpu_min": int(-neg_peers_min), "peers_per_gpu_max": int(peers_max),
+                       "partitions_rank0": blk.stats["nParts"], "window": blk.stats["W"],
+                       "exchange": EXCHANGE_TEXT[exchange] if world > 1 else "none (one GPU)", "nnz_overflow_total": int(ovf_all),
+                       "remainder_cache_max": blk.stats["cacheMax"],
+                       "l2": "matrix data per GPU (%.1f GB on rank 0) larger than L2 (126 MB), no flush" % (blk.stats["formatBytes"] / 1e9),
+                       "host_prep_s": round(prep_max, 1), "host_format_build_s_rank0": round(t_build, 1), "host_threads_per_rank": threads},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "kernel": blk.kernel_name(), "frac_of_nominal_8TBs": round(achieved / 8000.0, 4),
+                         "algorithmic_bytes_per_launch": int(alg_max),
+                         "note": "largest per-GPU algorithmic bytes / whole-step time (max over ranks); the step is one launch of "
+                                 "the main kernel with the exchange inside it" if exchange == "p2p" else
+                                 "largest per-GPU algorithmic bytes / whole-step time (main kernel + exchange + overflow)"},
+            "e2e": {"value": round(2.0 * nnz_all * e2e_steps / te / 1e9, 2), "unit": "GFLOP/s",
+                    "h2d_bytes_per_step": 8 * n_all, "d2h_bytes_per_step": 8 * n_all, "steps": e2e_steps,
+                    "api": "ehyb_mg_spmv_host_batch per rank (pinned host x/y of the rank's rows, copies pipelined with the products)",
+                    "bit_identical_to_device_resident_product": e2e_ok},
+            "gpu_launches": args.steps * blk.launches_per_spmv(),
+            "clocks": clocks,
+            "parity": {"rows_outside_1e-12_gate_all_ranks": int(gate_all), "max_abs_err_rank0": max_err,
+                       "checked": "every row of every rank against the closed-form check vector (oracle)"},
+        }
+        print(json.dumps(out), flush=True)
+    for p in pin:
+        lib.ehyb_host_free_pinned(p)
+    dist.barrier()
+    blk.free()
+    dec.free()
+    dist.barrier()
+    if world > 1:
+        tdist.destroy_process_group()
 
 
 def run_reference(args):

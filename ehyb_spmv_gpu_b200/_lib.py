@@ -115,7 +115,7 @@ EXPORTS = [
     "mm_write_mtx_crd_size", "mm_write_mtx_array_size", "mm_is_valid", "mm_typecode_to_str",
     "mm_read_mtx_crd_entry", "mm_read_mtx_crd_data", "mm_write_mtx_crd", "mm_read_unsymmetric_sparse",
     # ehyb.h
-    "ehyb_last_error", "ehyb_version", "ehyb_device_count", "ehyb_device_query", "ehyb_device_info_b200",
+    "ehyb_last_error", "ehyb_version", "ehyb_set_host_threads", "ehyb_get_host_threads", "ehyb_device_count", "ehyb_device_query", "ehyb_device_info_b200",
     "ehyb_plan", "ehyb_plan_kernel", "ehyb_plan_reference", "ehyb_build_graph", "ehyb_set_partitioner", "ehyb_partition_graph",
     "ehyb_reorder_with_partition", "ehyb_reorder", "ehyb_partition_blocks", "ehyb_free_host",
     "ehyb_layout_build", "ehyb_layout_build_csr", "ehyb_layout_get", "ehyb_layout_to_reference",
@@ -127,7 +127,7 @@ EXPORTS = [
     "ehyb_read_mtx", "ehyb_write_mtx", "ehyb_coo_free",
     "ehyb_mg_local_build", "ehyb_mg_local_halo", "ehyb_mg_local_set_send", "ehyb_mg_local_graph",
     "ehyb_mg_local_finish", "ehyb_mg_local_view", "ehyb_mg_local_free", "ehyb_mg_unique_id",
-    "ehyb_mg_session_create", "ehyb_mg_session_handle", "ehyb_mg_spmv", "ehyb_mg_time_spmv",
+    "ehyb_mg_session_create", "ehyb_mg_session_handle", "ehyb_mg_spmv", "ehyb_mg_time_spmv", "ehyb_mg_spmv_host_batch",
     "ehyb_mg_p2p_supported", "ehyb_mg_session_create_p2p", "ehyb_mg_p2p_export", "ehyb_mg_p2p_connect",
     "ehyb_mg_status", "ehyb_mg_launches_per_spmv",
     "ehyb_mg_session_free", "ehyb_gen_stencil27_rows", "ehyb_host_alloc_pinned", "ehyb_host_free_pinned",

@@ -1236,6 +1236,39 @@ extern "C" int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d)
     return s->exchange == EHYB_MG_P2P ? mg_spmv_p2p(s, x_d, y_d) : mg_spmv_nccl(s, x_d, y_d);
 }
 
+/* Pipelined stream of distributed products with HOST vectors: for i in [0, count): y_h[i] =
+ * A_block [x_h[i] | halo], x_h[i] / y_h[i] the n local entries in (pinned) host memory.  As
+ * ehyb_spmv_host_batch: the H2D of product i+1 and the D2H of product i-1 overlap the kernel of
+ * product i (two buffer pairs, three streams); the halo travels between the GPUs inside the
+ * products.  Collective: every rank calls it with the same count. */
+extern "C" int ehyb_mg_spmv_host_batch(ehyb_mg_session *s, const double *const *x_h, double *const *y_h, int count)
+{
+    if (!s || !x_h || !y_h || count < 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv_host_batch: bad argument");
+    ehyb_handle *h = s->h;
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_pipeline(h);
+    if (rc) return rc;
+    for (int i = 0; i < count; ++i) {
+        const int b = i & 1;
+        if (i >= 2) CU(cudaStreamWaitEvent(h->h2d, h->evK[b], 0));
+        CU(cudaMemcpyAsync(h->xb[b], x_h[i], sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->h2d));
+        CU(cudaEventRecord(h->evX[b], h->h2d));
+        CU(cudaStreamWaitEvent(h->stream, h->evX[b], 0));
+        if (i >= 2) CU(cudaStreamWaitEvent(h->stream, h->evY[b], 0));
+        rc = s->exchange == EHYB_MG_P2P ? mg_spmv_p2p(s, h->xb[b], h->yb[b]) : mg_spmv_nccl(s, h->xb[b], h->yb[b]);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->evK[b], h->stream));
+        CU(cudaStreamWaitEvent(h->d2h, h->evK[b], 0));
+        CU(cudaMemcpyAsync(y_h[i], h->yb[b], sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->d2h));
+        CU(cudaEventRecord(h->evY[b], h->d2h));
+    }
+    CU(cudaStreamSynchronize(h->h2d));
+    CU(cudaStreamSynchronize(h->stream));
+    if (s->commStream) CU(cudaStreamSynchronize(s->commStream));
+    CU(cudaStreamSynchronize(h->d2h));
+    return peer_check(h);
+}
+
 extern "C" int ehyb_mg_session_handle(ehyb_mg_session *s, ehyb_handle **h)
 {
     if (!s || !h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_session_handle: NULL");

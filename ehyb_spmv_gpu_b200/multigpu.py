@@ -146,6 +146,9 @@ class DistributedBlock:
     def launches_per_spmv(self):
         return int(self.lib.ehyb_mg_launches_per_spmv(self.session))
 
+    def kernel_name(self):
+        return self.lib.ehyb_session_kernel(self.handle).decode()
+
     def timed_out(self):
         t = C.c_int()
         check(self.lib, self.lib.ehyb_mg_status(self.session, C.byref(t)), "ehyb_mg_status")

@@ -42,6 +42,10 @@ typedef enum ehyb_status {
 
 const char *ehyb_last_error(void);
 const char *ehyb_version(void);
+/* threads of the host-side OpenMP code (format build, reorder, generators); n <= 0: unchanged.
+ * Process launchers tend to export OMP_NUM_THREADS=1 to their workers. */
+void ehyb_set_host_threads(int n);
+int ehyb_get_host_threads(void);
 
 /* ------------------------------------------------------------------------------------ */
 /* device query and partition-parameter plan                                              */
@@ -381,6 +385,11 @@ int ehyb_mg_session_handle(ehyb_mg_session *s, ehyb_handle **h);
  * number of times; asynchronous on the session stream. */
 int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d);
 int ehyb_mg_time_spmv(ehyb_mg_session *s, int warmup, int iters, float *ms_total);
+/* Pipelined stream of distributed products with HOST vectors (the n local entries of x and y, in
+ * pinned memory for true overlap): y_h[i] = A_block [x_h[i] | halo]; the copies of products i+1
+ * and i-1 overlap the kernel of product i, the halo travels between the GPUs inside the products.
+ * Collective: every rank calls it with the same count. */
+int ehyb_mg_spmv_host_batch(ehyb_mg_session *s, const double *const *x_h, double *const *y_h, int count);
 /* Kernel launches one distributed product issues. */
 int ehyb_mg_launches_per_spmv(const ehyb_mg_session *s);
 /* Every rank must have finished its products before any rank frees its session (barrier). */

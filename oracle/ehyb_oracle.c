@@ -608,3 +608,57 @@ int orc_compare(const double *yResult, const double *y, double threshold, int n,
     out[0] = avgdiff; out[1] = avgampl;
     return k;
 }
+
+/* ------------------------------------------------------------------------- */
+/* BASELINE.json config 5 (27-point stencil 512^3): the matrix is too large to   */
+/* hold as a CSR next to the product under test, and the reference cannot run it */
+/* at all, so the check vector is evaluated in closed form  */
+/* from the generator's definition (diag 26, off -1, 27-point      */
+/* neighbourhood clipped at the boundary; same matrix as gen_stencil27_lower +   */
+/* solver_test.c:127-265's symmetric expansion, checked against each other in    */
+/* tests/test_oracle_pinned.py) for x a fixed hash of the natural row index.     */
+/* ------------------------------------------------------------------------- */
+
+/* x(i): splitmix-style hash of the natural index, in (-0.1, 0.1); the same
+ * function as multigpu.x_of_global (numpy), bit for bit */
+static inline double orc_x_of_global(unsigned long long i)
+{
+    unsigned long long z = i * 0x9E3779B97F4A7C15ULL + 0x632BE59BD9B4E019ULL;
+    z ^= z >> 29;
+    z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 32;
+    return ((double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 0.2;
+}
+
+void orc_x_of_global_fill(long long count, const long long *ids, double scale, double shift, double *x)
+{
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < count; ++k) x[k] = orc_x_of_global((unsigned long long)ids[k]) * scale + shift;
+}
+
+/* y_ref and |A||x| of the rows `ids` (natural indices (z*ny + y)*nx + x) for
+ * x_j = orc_x_of_global(j) * scale + shift; entries summed in ascending column
+ * order like the CSR baseline. */
+void orc_stencil27_rows_product(int nx, int ny, int nz, long long count, const long long *ids, double scale, double shift,
+                                double *yref, double *absAx)
+{
+    const long long plane = (long long)nx * ny;
+#pragma omp parallel for schedule(static)
+    for (long long k = 0; k < count; ++k) {
+        const long long g = ids[k];
+        const int x = (int)(g % nx), y = (int)((g / nx) % ny), z = (int)(g / plane);
+        double s = 0.0, a = 0.0;
+        for (int dz = -1; dz <= 1; ++dz)
+            for (int dy = -1; dy <= 1; ++dy)
+                for (int dx = -1; dx <= 1; ++dx) {
+                    if (x + dx < 0 || x + dx >= nx || y + dy < 0 || y + dy >= ny || z + dz < 0 || z + dz >= nz) continue;
+                    const long long c = g + dz * plane + (long long)dy * nx + dx;
+                    const double v = c == g ? 26.0 : -1.0;
+                    const double xv = orc_x_of_global((unsigned long long)c) * scale + shift;
+                    s += v * xv;
+                    a += fabs(v) * fabs(xv);
+                }
+        yref[k] = s;
+        absAx[k] = a;
+    }
+}

@@ -359,6 +359,22 @@ class Oracle:
         return float(self.L.orc_csr_spmv_timed(n, _p(rowIdx, c_int_p), _p(J, c_int_p), _p(V, c_dbl_p),
                                                _p(x, c_dbl_p), _p(y, c_dbl_p), warmup, iters)), y
 
+    def x_of_global(self, ids, scale=1.0, shift=0.0):
+        """x_j = hash(j) * scale + shift for natural indices j (the function multigpu.x_of_global)."""
+        ids = np.ascontiguousarray(ids, np.int64)
+        x = np.empty(len(ids))
+        self.L.orc_x_of_global_fill(C.c_longlong(len(ids)), _p(ids, C.POINTER(C.c_longlong)), C.c_double(scale), C.c_double(shift), _p(x, c_dbl_p))
+        return x
+
+    def stencil27_rows_product(self, grid, ids, scale=1.0, shift=0.0):
+        """(y_ref, |A||x|) of the rows `ids` (natural indices) of the 27-point stencil on `grid`, in
+        closed form, for x_j = hash(j) * scale + shift: the check vector of BASELINE.json config 5."""
+        ids = np.ascontiguousarray(ids, np.int64)
+        y = np.empty(len(ids)); a = np.empty(len(ids))
+        self.L.orc_stencil27_rows_product(int(grid[0]), int(grid[1]), int(grid[2]), C.c_longlong(len(ids)), _p(ids, C.POINTER(C.c_longlong)),
+                                          C.c_double(scale), C.c_double(shift), _p(y, c_dbl_p), _p(a, c_dbl_p))
+        return y, a
+
     def vector_reorder(self, v, lst):
         out = np.empty_like(v)
         self.L.orc_vector_reorder(C.c_int(len(v)), _p(v, c_dbl_p), _p(out, c_dbl_p), _p(lst, c_int_p))

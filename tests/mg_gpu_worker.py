@@ -45,6 +45,77 @@ def setup_oneway(rank, world, dist, exchange, n_local=6000):
     return blk, rowStarts
 
 
+def run_grid(rank, world, dist, exchange, grid, level1, products):
+    """BASELINE.json config 5's pipeline at a small size: GLOBAL grid cut into bricks, level 1 by
+    mt-metis on the brick graph (or scattered owners: every rank neighbours every other), streamed
+    format build, products checked against the closed-form check vector of the stencil (oracle)."""
+    import torch
+    from ehyb_spmv_gpu_b200 import _lib as L
+    from ehyb_spmv_gpu_b200 import multigpu as mg
+    from oracle import oracle as O
+    brick = (8, 8, 4)
+    if level1 == "scatter":
+        nb = int(np.prod([-(-g // b) for g, b in zip(grid, brick)]))
+        dec = mg.GridDecomp(grid, brick, world, np.random.default_rng(7).integers(0, world, nb).astype(np.uint32))
+        blk = mg.GridBlock(dec, rank, exchange=exchange, chunk_bricks=5)
+        blk.exchange_lists(dist)
+        assert int(np.count_nonzero(blk.recvCount)) == world - 1
+    else:
+        blk, dec = mg.setup_grid(rank, world, grid, brick, dist, "metis", exchange)
+    if exchange == "p2p":
+        blk.create_session_p2p(rank, dist)
+        assert blk.launches_per_spmv() == 1 + (1 if blk.stats["nOverflow"] else 0)
+    else:
+        ids = [mg.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        blk.create_session(rank, ids[0])
+    orc = O.Oracle()
+    nat = blk.natural_ids()
+    lib = blk.lib
+    for k in range(products):           # host-synchronised products, a different x every time
+        blk.set_x(orc.x_of_global(nat, k + 1.0, 0.01 * k))
+        blk.spmv()
+        y = blk.get_y()
+        y_ref, absAx = orc.stencil27_rows_product(grid, nat, k + 1.0, 0.01 * k)
+        bad = np.flatnonzero(~(np.abs(y - y_ref) <= 1e-12 * absAx))
+        assert bad.size == 0, "rank %d product %d: %d rows outside the gate, first %s" % (rank, k, bad.size, bad[:5])
+    # queued products without host synchronisation, every one with its own x (see main())
+    K = 6
+    xs = torch.zeros((K, blk.n + blk.nHalo), dtype=torch.float64, device="cuda")
+    ys = torch.full((K, blk.n), float("nan"), dtype=torch.float64, device="cuda")
+    for k in range(K):
+        xs[k, :blk.n] = torch.from_numpy(orc.x_of_global(nat, 0.5 + k, -0.02 * k))
+    torch.cuda.synchronize()
+    dist.barrier()
+    for k in range(K):
+        L.check(lib, lib.ehyb_mg_spmv(blk.session, C.c_void_p(xs[k].data_ptr()), C.c_void_p(ys[k].data_ptr())), "ehyb_mg_spmv")
+    L.check(lib, lib.ehyb_sync(blk.handle), "ehyb_sync")
+    torch.cuda.synchronize()
+    for k in range(K):
+        y_ref, absAx = orc.stencil27_rows_product(grid, nat, 0.5 + k, -0.02 * k)
+        bad = np.flatnonzero(~(np.abs(ys[k].cpu().numpy() - y_ref) <= 1e-12 * absAx))
+        assert bad.size == 0, "rank %d queued product %d: %d rows outside the gate" % (rank, k, bad.size)
+    # pipelined host-vector products (ehyb_mg_spmv_host_batch): y_i of x_i, every i
+    xh = [orc.x_of_global(nat, 1.0 + 0.25 * i, 0.003 * i) for i in range(5)]
+    yh = [np.full(blk.n, np.nan) for _ in range(5)]
+    xp = (C.c_void_p * 5)(*[a.ctypes.data for a in xh])
+    yp = (C.c_void_p * 5)(*[a.ctypes.data for a in yh])
+    dist.barrier()
+    L.check(lib, lib.ehyb_mg_spmv_host_batch(blk.session, xp, yp, 5), "ehyb_mg_spmv_host_batch")
+    for i in range(5):
+        y_ref, absAx = orc.stencil27_rows_product(grid, nat, 1.0 + 0.25 * i, 0.003 * i)
+        assert np.all(np.abs(yh[i] - y_ref) <= 1e-12 * absAx), "rank %d host batch product %d outside the gate" % (rank, i)
+    assert not blk.timed_out()
+    ms = blk.time_spmv(3, 50)
+    kname = blk.kernel_name()
+    dist.barrier()
+    blk.free()
+    dec.free()
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank %d ok (grid path, kernel %s, %d peers, %.1f us/product)" % (rank, kname, int(np.count_nonzero(blk.recvCount)), ms / 50 * 1e3))
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -60,6 +131,8 @@ def main():
     dist.init_process_group("gloo", rank=rank, world_size=world)
     if exchange == "p2p":
         assert mg.p2p_supported(rank, world), "no peer access between the GPUs of this box"
+    if partition.startswith("grid"):
+        return run_grid(rank, world, dist, exchange, grid, partition.split("-")[1], min(products, 4))
     if partition == "oneway":
         blk, rowStarts = setup_oneway(rank, world, dist, exchange)
     else:

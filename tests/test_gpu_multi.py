@@ -37,6 +37,11 @@ CASES = [
     ("nccl", "oneway", "-"),
     ("nccl", "metis", "24x20x9"),
     ("nccl", "blocks", "64x64x24"),
+    # BASELINE.json config 5's pipeline (GLOBAL grid, bricks, level-1 owners, streamed build, closed-form check)
+    ("p2p", "grid-metis", "48x40x36"),
+    ("p2p", "grid-scatter", "40x40x24"),    # every rank neighbours every other
+    ("nccl", "grid-metis", "48x40x36"),
+    ("p2p", "grid-metis", "160x160x96"),    # 2.4 M rows: hundreds of partitions per GPU, many per CTA
 ]
 
 
@@ -46,7 +51,7 @@ CASES = [
 def test_distributed_product_on_gpus(world, exchange, partition, grid, kernel):
     if _gpus() < world:
         pytest.skip("needs %d GPUs" % world)
-    if partition == "metis" and not (ROOT / "bin" / "ehyb_mtmetis").exists():
+    if "metis" in partition and not (ROOT / "bin" / "ehyb_mtmetis").exists():
         pytest.skip("bin/ehyb_mtmetis not built")
     port = _free_port()
     procs = []
