@@ -45,7 +45,8 @@ struct ehyb_handle {
     double *ovfVal;
     int32_t *cacheCols;
     int32_t *order;      /* CTA slot -> partition (NULL: identity), see ehyb_staged_kernel */
-    int32_t *ctaTab;     /* persistent kernel: partition table in CTA-slot order (8 ints per slot) */
+    int32_t *ctaTab;     /* persistent kernel: work items in CTA order (8 ints each), see build_cta_tab */
+    int32_t *ctaStart;   /* persistent kernel: [grid + 1] first item of every CTA */
     unsigned long long *trace; /* development: per-CTA timeline of the last product (EHYB_TRACE=1) */
     int cacheCap;        /* elements of the shared-memory remainder cache */
     int smCount;
@@ -142,27 +143,100 @@ static main_kernel_t persistent_kernel(int threads, bool peer)
 }
 constexpr int kPeerPersistWarps = 20;
 
-/* The persistent kernel's partition table: slot s = c + grid*j is the j-th partition of CTA c;
- * row = {rowStart, rowEnd, sliceStart, sliceEnd, cacheStart, cacheCount, flags, 0}, flags bit 0 =
- * the partition's cache list reaches into the halo columns (>= n).  order == NULL: identity. */
+static int env_int_early(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return s && s[0] ? atoi(s) : dflt;
+}
+
+/* The persistent kernel's work list.  seq = the partitions in `order` (NULL: identity).
+ *   full rounds  CTA c takes whole partitions seq[c + G*j]: at any time the G CTAs stream G
+ *                CONSECUTIVE partitions - one moving region of the blob and of x.  (Measured: giving
+ *                every CTA its own contiguous run of the sequence instead, 148 streams spread over
+ *                the whole blob, costs 7 % at 256^3 and 14 % at 512^3 / 2 GPUs.)
+ *   tail         a whole number of partitions per CTA leaves SMs idle at the end (4 096 partitions
+ *                on 148 SMs: 48 SMs idle for the last 1/28 of the product), and partitions differ in
+ *                size.  The last partitions (the incomplete round; with >= 8 rounds also the last
+ *                full one) are therefore cut by BYTES: CTA c gets a run of consecutive slices that
+ *                tops its total up to the average, parts of at most a few partitions it shares
+ *                with its neighbours.
+ * Item = {rowStart, rowEnd, first slice, end slice (of the run inside the partition), cacheStart,
+ * cacheCount, flags (bit 0: the cache list has halo columns), row of the item's first slice};
+ * ctaStart[c] = first item of CTA c.  Multi-GPU sessions pass an order with the partitions that
+ * have halo columns last: every CTA meets them at the end of its list. */
 static int build_cta_tab(ehyb_handle *h, const ehyb_layout_view *v, const int32_t *order)
 {
-    const size_t P = (size_t)h->nParts;
-    int32_t *tab = (int32_t *)malloc(P * 8 * sizeof(int32_t));
-    if (!tab) return ehyb_fail(EHYB_ERR_NOMEM, "partition table: out of memory");
-    for (size_t s = 0; s < P; ++s) {
-        const ehyb_part_desc *d = &v->parts[order ? order[s] : (int32_t)s];
-        int32_t *t = tab + 8 * s;
-        t[0] = d->rowStart; t[1] = d->rowEnd; t[2] = d->sliceStart; t[3] = d->sliceEnd;
+    const int P = h->nParts, G = h->grid;
+    const int balance = env_int_early("EHYB_PERSIST_BALANCE", 1);
+    int rounds = P / G;
+    /* the tail: the P mod G partitions of the last, incomplete round - and the last full round as
+     * well when a CTA has many rounds, to even out partitions of different sizes.  (A shared
+     * partition is staged once per CTA that has a part of it: with 3 partitions per CTA - config 2,
+     * 444 partitions - cutting a whole round of them cost 2.8 %, measured.) */
+    if (balance && rounds >= 8) rounds -= 1;
+    if (!balance) rounds = (P + G - 1) / G;           /* (experiments: whole partitions only) */
+    const int tail0 = rounds * G < P ? rounds * G : P; /* first partition (sequence position) of the tail */
+    const size_t maxItems = (size_t)P + 3 * (size_t)G + 1;
+    int32_t *tab = (int32_t *)malloc(maxItems * 8 * sizeof(int32_t));
+    int32_t *start = (int32_t *)malloc(((size_t)G + 1) * sizeof(int32_t));
+    double *full = (double *)calloc((size_t)G, sizeof(double));
+    if (!tab || !start || !full) { free(tab); free(start); free(full); return ehyb_fail(EHYB_ERR_NOMEM, "work list: out of memory"); }
+    auto sliceCost = [&](int s2) { /* bytes streamed for the slice + its fixed cost (descriptor, y rows, chunk bookkeeping) */
+        const ehyb_slice_desc &d = v->slices[s2];
+        return (double)d.w * 512.0 + (double)((d.w + 3) / 4) * 512.0 + (double)d.wr * 512.0 + (double)((d.wr + 3) / 4) * 512.0 + 768.0;
+    };
+    auto partOf = [&](int i) { return &v->parts[order ? order[i] : i]; };
+    auto emit = [&](int32_t *t, const ehyb_part_desc *d, int s0, int s1) {
+        t[0] = d->rowStart; t[1] = d->rowEnd; t[2] = s0; t[3] = s1;
         t[4] = d->cacheStart; t[5] = d->cacheCount;
         t[6] = d->cacheCount > 0 && v->cacheCols[d->cacheStart + d->cacheCount - 1] >= v->n ? 1 : 0;
-        t[7] = 0;
+        t[7] = d->rowStart + (s0 - d->sliceStart) * EHYB_SLICE_ROWS;
+    };
+    double total = 0.0;
+    for (int i = 0; i < P; ++i) {
+        const ehyb_part_desc *d = partOf(i);
+        double b = 0.0;
+        for (int s2 = d->sliceStart; s2 < d->sliceEnd; ++s2) b += sliceCost(s2);
+        total += b;
+        if (i < tail0) full[i % G] += b;
     }
+    const double avg = total / (double)G;
+    size_t k = 0;
+    int ti = tail0;                                        /* tail partition being cut */
+    int sNext = ti < P ? partOf(ti)->sliceStart : 0;       /* its next unassigned slice */
+    for (int c = 0; c < G; ++c) {
+        start[c] = (int32_t)k;
+        for (int j = 0; j < rounds && c + G * j < tail0; ++j) {
+            const ehyb_part_desc *d = partOf(c + G * j);
+            emit(tab + 8 * k, d, d->sliceStart, d->sliceEnd);
+            ++k;
+        }
+        double have = full[c];
+        while (ti < P) {
+            const ehyb_part_desc *d = partOf(ti);
+            if (sNext >= d->sliceEnd) { /* (also skips partitions without slices) */
+                if (++ti < P) sNext = partOf(ti)->sliceStart;
+                continue;
+            }
+            if (have >= avg && c + 1 < G) break;
+            int sEnd = sNext;
+            while (sEnd < d->sliceEnd && (c + 1 == G || have < avg)) have += sliceCost(sEnd++);
+            emit(tab + 8 * k, d, sNext, sEnd);
+            ++k;
+            sNext = sEnd;
+        }
+    }
+    start[G] = (int32_t)k;
+    free(full);
     cudaError_t e = cudaSuccess;
-    if (!h->ctaTab) e = cudaMalloc(&h->ctaTab, P * 8 * sizeof(int32_t));
-    if (e == cudaSuccess) e = cudaMemcpy(h->ctaTab, tab, P * 8 * sizeof(int32_t), cudaMemcpyHostToDevice);
-    free(tab);
-    if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "partition table: %s", cudaGetErrorString(e));
+    cudaFree(h->ctaTab); cudaFree(h->ctaStart);
+    h->ctaTab = NULL; h->ctaStart = NULL;
+    e = cudaMalloc(&h->ctaTab, (k ? k : 1) * 8 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&h->ctaStart, ((size_t)G + 1) * sizeof(int32_t));
+    if (e == cudaSuccess && k) e = cudaMemcpy(h->ctaTab, tab, k * 8 * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->ctaStart, start, ((size_t)G + 1) * sizeof(int32_t), cudaMemcpyHostToDevice);
+    free(tab); free(start);
+    if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "work list: %s", cudaGetErrorString(e));
     return EHYB_OK;
 }
 
@@ -179,7 +253,7 @@ extern "C" void ehyb_free(ehyb_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     cudaFree(h->parts); cudaFree(h->slices); cudaFree(h->blob);
-    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->ctaTab); cudaFree(h->trace);
+    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->ctaTab); cudaFree(h->ctaStart); cudaFree(h->trace);
     cudaFree(h->x); cudaFree(h->y);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->xb[i]); cudaFree(h->yb[i]);
@@ -222,7 +296,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
         /* one CTA per SM over all of its partitions, {window, cache} double-buffered: needs one CTA
          * per partition and room for >= 8 warps of staging next to the two buffers (16 to be chosen
          * by default); otherwise the staged kernel */
-        const int grid = h->nParts < prop.multiProcessorCount ? h->nParts : prop.multiProcessorCount;
+        const int grid = h->nSlices < prop.multiProcessorCount ? (h->nSlices > 0 ? h->nSlices : 1) : prop.multiProcessorCount;
         const size_t fixed = (size_t)kPersistHeader + 2 * (winBytes + cacheBytes);
         const size_t perWarp = (size_t)kSlotsPerWarp * slot_bytes(4);
         int nw = fixed + perWarp <= prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - fixed) / perWarp) : 0;
@@ -344,8 +418,9 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     h->winPiece = env_int("EHYB_WIN_PIECE", 32768) & ~15;
     if (h->winPiece < 16) h->winPiece = 32768;
     if (env_int("EHYB_TRACE", 0)) {
-        CU(cudaMalloc(&h->trace, sizeof(unsigned long long) * 8 * (size_t)h->nParts * (size_t)h->kpp));
-        CU(cudaMemset(h->trace, 0, sizeof(unsigned long long) * 8 * (size_t)h->nParts * (size_t)h->kpp));
+        const size_t traceCtas = (size_t)h->nParts * (size_t)h->kpp > (size_t)h->grid ? (size_t)h->nParts * (size_t)h->kpp : (size_t)h->grid;
+        CU(cudaMalloc(&h->trace, sizeof(unsigned long long) * 8 * traceCtas));
+        CU(cudaMemset(h->trace, 0, sizeof(unsigned long long) * 8 * traceCtas));
     }
     h->l2_persist = 0;
     if (o->l2_persist_x && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
@@ -422,6 +497,7 @@ static MainArgs main_args(const ehyb_handle *h, const double *x_d, double *y_d, 
     a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = h->dbgSkip; a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
     a.order = h->order;
     a.ctaTab = h->ctaTab;
+    a.ctaStart = h->ctaStart;
     a.nPartsTotal = h->nParts;
     a.l2hint = h->l2hint;
     a.dynamicDeal = h->dynamicDeal;
@@ -681,7 +757,7 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
 extern "C" int ehyb_trace_read(ehyb_handle *h, unsigned long long *out, int *ctas)
 {
     if (!h || !ctas) return ehyb_fail(EHYB_ERR_ARG, "ehyb_trace_read: NULL");
-    *ctas = h->trace ? h->nParts * h->kpp : 0;
+    *ctas = h->trace ? (h->nParts * h->kpp > h->grid ? h->nParts * h->kpp : h->grid) : 0;
     if (!h->trace || !out) return EHYB_OK;
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
@@ -1027,9 +1103,9 @@ extern "C" int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int 
          *     columns - these CTAs push, nobody in them waits -, then the partitions that need halo
          *     values, by which time the neighbours' push has arrived, then the rest, so that the
          *     tail of the kernel is made of ordinary partitions;
-         *   persistent kernel (slot c + grid*j = j-th partition of CTA c): all the partitions
-         *     without halo columns first, the others last - every CTA meets them at the end of its
-         *     list, when the neighbours have long delivered. */
+         *   persistent kernel (CTA c takes the partitions order[c + grid*j], build_cta_tab): all the
+         *     partitions without halo columns first, the others last - every CTA meets them at the
+         *     end of its list, when the neighbours have long delivered. */
         ehyb_layout_view v;
         int rc2 = ehyb_layout_get(layout, &v);
         if (rc2) return rc2;
@@ -1039,12 +1115,11 @@ extern "C" int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int 
         const int reorder = env_int("EHYB_P2P_ORDER", 1);
         int firstWave = h->smCount * h->ctasPerSM / h->kpp;
         if (firstWave < 1) firstWave = 1;
-        if (h->kernel == EHYB_KERNEL_PERSISTENT) firstWave = h->nParts;
         int nPlain = 0;
         for (int p = 0; p < h->nParts; ++p) {
             const int cnt = v.parts[p].cacheCount;
             const int halo = reorder && cnt > 0 && v.cacheCols[v.parts[p].cacheStart + cnt - 1] >= v.n;
-            cls[p] = halo ? 1 : (nPlain++ < firstWave ? 0 : 2);
+            cls[p] = halo ? 1 : (h->kernel == EHYB_KERNEL_PERSISTENT || nPlain++ < firstWave ? 0 : 2);
         }
         int k = 0;
         for (int pass = 0; pass < 3; ++pass)

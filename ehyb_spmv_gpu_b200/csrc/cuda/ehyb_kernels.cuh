@@ -75,7 +75,8 @@ struct MainArgs {
     const int32_t *cacheCols; /* per-partition remainder cache lists (permuted columns) */
     int cacheCap;             /* shared-memory cache capacity in elements (>= longest list) */
     const int32_t *order;     /* CTA slot -> partition (NULL: identity) */
-    const int32_t *ctaTab;    /* persistent kernel: the partition table in CTA order, 8 ints per slot (see there) */
+    const int32_t *ctaTab;    /* persistent kernel: work items in CTA order, 8 ints each (see there) */
+    const int32_t *ctaStart;  /* persistent kernel: [grid + 1] first work item of every CTA */
     int prologueBarrier;      /* staged kernel, experiments: CTA barrier after window + cache staging */
     int dynamicDeal;          /* staged kernel: slices beyond the first nw are taken on demand (shared-memory counter) */
     int l2hint;               /* staged kernel: L2 eviction hints on the TMA copies (stream evict-first, x evict-last) */
@@ -1023,10 +1024,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
  *     longest-job-first); a warp's chunk stream does not know partition boundaries: when the
  *     next slice it is dealt lies in a later partition, a "switch" marker per boundary goes down
  *     its two-slot pipeline where the consumer has to change buffers;
- *   - the CTA's partitions are rows of a table in GLOBAL memory (a.ctaTab, 32 bytes per
- *     partition, built by the session: slot c + grid*j = the j-th partition of CTA c), read
- *     through L1/L2 one slice ahead of their use: any number of partitions per CTA
- *     (27-point 512^3 on one GPU: 32 768 partitions, 222 per CTA);
+ *   - the work of a CTA is a list of ITEMS in GLOBAL memory (a.ctaTab, 32 bytes each, CTA c owns
+ *     items ctaStart[c] .. ctaStart[c+1]), an item = a run of consecutive slices of one partition.
+ *     The session cuts the sequence of all slices into one run per CTA of equal BYTES, so the
+ *     CTAs finish together whatever the number and the sizes of the partitions (a whole number of
+ *     partitions per CTA left 48 of 148 SMs idle for the last 1/28 of a 4 096-partition product);
+ *     a CTA's first and last items are parts of partitions it shares with its neighbours.  Items
+ *     are read through L1/L2 one slice ahead of their use: any number per CTA (27-point 512^3 on
+ *     one GPU: 32 768 partitions, 222 per CTA);
  *   - no CTA-wide barrier after the start-up; warps are at most one partition apart.
  *
  * PEER: the multi-GPU build.  The last warp of the first pushCtas CTAs (all of them are
@@ -1036,7 +1041,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
  * neighbours' flags and reads the halo buffer; the session orders every CTA's partitions so that
  * those with halo columns come last, when the neighbours' push has long arrived.
  *
- * grid = min(#SMs, nParts), block = NW*32, one CTA per SM.
+ * grid = min(#SMs, nSlices), block = NW*32, one CTA per SM.
  * smem = 512 B header (mbarriers, sequence counter) + 2 * (align128((W+2)*8) +
  * align128(cacheCap*8)) + NW * 2 * slot.  Requires ctasPerPart == 1.
  */
@@ -1078,12 +1083,12 @@ struct PMeta {
 /* issue side of a warp: walks the slices it is dealt out of the CTA's sequence */
 template <int KCE>
 struct PWalker {
-    const int4 *tab;           /* this CTA's rows of the partition table: row j at tab[strideJ * j] */
+    const int4 *tab;           /* this CTA's work items: item j at tab[2 * j] */
     int *counter;              /* shared: next undealt slice of the CTA's sequence */
     const uint2 *slices;       /* global slice descriptors */
     const unsigned char *blob;
     const unsigned char *base; /* current slice */
-    int strideJ, nj;
+    int nj;
     int j;                     /* partition of the current slice */
     int t;                     /* current slice, local index in partition j */
     int qn, jn;                /* next slice of this warp (sequence number) and its partition */
@@ -1114,7 +1119,7 @@ struct PWalker {
             baseN += nslN;
             jn += 1;
             if (jn < nj) {
-                const int4 e = __ldg(tab + static_cast<size_t>(strideJ) * jn);
+                const int4 e = __ldg(tab + 2 * jn);
                 sliceStartN = e.z;
                 nslN = e.w - e.z;
             }
@@ -1141,9 +1146,9 @@ struct PWalker {
         live = true;
     }
 
-    __device__ __forceinline__ void start(const int4 *tab_, int strideJ_, int *counter_, const uint2 *slices_, const unsigned char *blob_, int nj_, int lane)
+    __device__ __forceinline__ void start(const int4 *tab_, int *counter_, const uint2 *slices_, const unsigned char *blob_, int nj_, int lane)
     {
-        tab = tab_; strideJ = strideJ_; counter = counter_; slices = slices_; blob = blob_; nj = nj_;
+        tab = tab_; counter = counter_; slices = slices_; blob = blob_; nj = nj_;
         j = 0; jn = 0; baseN = 0; switchesOwed = 0; live = false;
         const int4 e = __ldg(tab);
         sliceStartN = e.z;
@@ -1238,12 +1243,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     constexpr uint32_t kSlotValBytes = static_cast<uint32_t>(slot_val_bytes(KCE));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nw = blockDim.x >> 5;
-    const int G = gridDim.x;
-    const int nj = (a.nPartsTotal - static_cast<int>(blockIdx.x) + G - 1) / G; /* partitions of this CTA (>= 1: grid <= nParts) */
-    /* row j of this CTA in the partition table: {rowStart, rowEnd, sliceStart, sliceEnd},
-     * {cacheStart, cacheCount, flags (1: the cache list has halo columns), -} */
-    const int4 *tab = reinterpret_cast<const int4 *>(a.ctaTab) + 2 * static_cast<size_t>(blockIdx.x);
-    const int strideJ = 2 * G;
+    /* this CTA's work items: {rowStart, rowEnd, sliceStart, sliceEnd} of the partition - the slices
+     * restricted to the CTA's run -, {cacheStart, cacheCount, flags (1: the cache list has halo
+     * columns), row of the run's first slice} */
+    const int item0 = __ldg(a.ctaStart + blockIdx.x);
+    const int nj = __ldg(a.ctaStart + blockIdx.x + 1) - item0;
+    const int4 *tab = reinterpret_cast<const int4 *>(a.ctaTab) + 2 * static_cast<size_t>(item0);
 
     /* header: [0,16) window bars, [16,32) cache bars, [32,48) empty bars, [64,448) slot bars,
      * [448,452) sequence counter */
@@ -1269,6 +1274,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     }
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (nj <= 0) { /* fewer slices than CTAs: nothing but this CTA's share of the halo push */
+        if (PEER && pusher) {
+            const bool ok = peer_push_check(a.peer);
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            peer_push_all(a.peer, a.x, lane, ok);
+        }
+        return;
+    }
     if (tid == 0) {
         *seqCounter = 0;
         for (int b = 0; b < 2; ++b) {
@@ -1286,7 +1299,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     if (a.l2hint) keepPolicy = make_evict_last_policy();
     else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(keepPolicy));
     PWalker<KCE> wk;
-    wk.start(tab, strideJ, seqCounter, reinterpret_cast<const uint2 *>(a.slices), a.blob, nj, lane);
+    wk.start(tab, seqCounter, reinterpret_cast<const uint2 *>(a.slices), a.blob, nj, lane);
     PMeta meta[2];
     meta[0] = issue_pchunk(wk, slot0, slotBar0, lane, streamPolicy);
     meta[1] = issue_pchunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane, streamPolicy);
@@ -1317,15 +1330,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
      * Inlined at two places only (start-up and one site in the loop): the code size of this kernel
      * matters (a polled, non-blocking variant with checks in every iteration measured slower). */
     int dutyState = 0, dutyJ = 0; /* dutyState 1: partition dutyJ still has to be staged by this warp */
-    int nxtPs = 0, nxtPe = 0;     /* rows of the partition staged last = the one the consumer enters next */
+    int nxtPs = 0, nxtPe = 0, nxtRow0 = 0; /* partition staged last = the one the consumer enters next: rows, row of the item's first slice */
     bool haloReady = false;       /* PEER: this warp has seen the neighbours' flags of this product */
     auto duty_begin = [&](int jj) { dutyState = 1; dutyJ = jj; };
     auto duty_run = [&]() {
         const int b = dutyJ & 1;
-        const int4 e0 = __ldg(tab + static_cast<size_t>(strideJ) * dutyJ);
-        const int4 e1 = __ldg(tab + static_cast<size_t>(strideJ) * dutyJ + 1);
+        const int4 e0 = __ldg(tab + 2 * dutyJ);
+        const int4 e1 = __ldg(tab + 2 * dutyJ + 1);
         const int cacheStart = e1.x, cacheCount = e1.y;
-        nxtPs = e0.x; nxtPe = e0.y;
+        nxtPs = e0.x; nxtPe = e0.y; nxtRow0 = e1.w;
         if (dutyJ >= 2) mbar_wait_bounded(hdr + 32u + 8u * b, static_cast<uint32_t>(((dutyJ - 2) >> 1) & 1));
         if (warp == 0) {
             const int ps_ = e0.x;
@@ -1387,7 +1400,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     duty_run();
     if (PEER && pushPending) peer_push_all(a.peer, a.x, lane, pushOk);
     if (PEER && tr && pusher && lane == 0) tr[2] = global_timer_ns();
-    int ps = nxtPs, pe = nxtPe;
+    int ps = nxtPs, pe = nxtPe, row0 = nxtRow0;
     uint32_t xsAddr = smem_u32(buf0) + static_cast<uint32_t>(ps - (ps & ~1)) * 8u;
     uint32_t cacheAddr = smem_u32(buf0) + winBytes;
     if (nj > 1) duty_begin(1);
@@ -1413,7 +1426,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
             if (lane == 0) mbar_arrive(hdr + 32u + 8u * static_cast<uint32_t>(jC & 1));
             jC += 1;
             const uint32_t b = static_cast<uint32_t>(jC & 1), par = static_cast<uint32_t>((jC >> 1) & 1);
-            ps = nxtPs; pe = nxtPe; /* (the staging of partition jC by this warp came last) */
+            ps = nxtPs; pe = nxtPe; row0 = nxtRow0; /* (the staging of partition jC by this warp came last) */
             xsAddr = smem_u32(buf0) + b * bufBytes + static_cast<uint32_t>(ps - (ps & ~1)) * 8u;
             cacheAddr = smem_u32(buf0) + b * bufBytes + winBytes;
             cacheReady = false;
@@ -1472,7 +1485,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
                 }
             }
             if (m.flags & 2) {
-                const int r = ps + m.t * EHYB_SLICE_ROWS + lane;
+                const int r = row0 + m.t * EHYB_SLICE_ROWS + lane;
                 if (r < pe) a.y[r] = acc0 + r0;
                 if (r + 32 < pe) a.y[r + 32] = acc1 + r1;
                 acc0 = acc1 = r0 = r1 = 0.0;

@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r2_t2.log 2>&1; tail -15 gpurun_out/r2_t2.log
-EHYB_BENCH_GRID=256x256x256 timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/r2_grid256_n1.json 2> gpurun_out/r2_grid256_n1.err; tail -c 2500 gpurun_out/r2_grid256_n1.json; tail -5 gpurun_out/r2_grid256_n1.err
-EHYB_BENCH_GRID=256x256x256 timeout 600 $TR --master-port 29531 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/r2_grid256_n2.json 2> gpurun_out/r2_grid256_n2.err; tail -c 2500 gpurun_out/r2_grid256_n2.json; grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/r2_grid256_n2.err | tail -5
-timeout 900 $TR --master-port 29532 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/r2_grid512_n2.json 2> gpurun_out/r2_grid512_n2.err; tail -c 2500 gpurun_out/r2_grid512_n2.json; grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/r2_grid512_n2.err | tail -5
+P='import json,sys; t=sys.stdin.read(); d=json.loads(t[t.index("{\"metric"):]); print(d["ms_per_step"], d["value"], d["roofline"]["frac"])'
+echo "== C2 B"; timeout 300 python bench.py --steps 200 --warmup 10 2>/dev/null | python -c "$P"
+echo "== 200^3 B"; EHYB_BENCH_GRID=192x192x192 timeout 600 python bench.py --steps 100 --warmup 5 2>/dev/null | python -c "$P"
+echo "== 256^3 B"; EHYB_BENCH_GRID=256x256x256 timeout 600 python bench.py --steps 200 --warmup 5 2>/dev/null | python -c "$P"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_c2.csv python bench.py --steps 20 --warmup 3 > gpurun_out/ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:persistent -s 5 -c 1 -f -o gpurun_out/r2_c2_persistent_full python bench.py --steps 10 --warmup 3 > gpurun_out/ncu2.log 2>&1
+EHYB_BENCH_GRID=256x256x256 ncu --set full --clock-control none --import-source on -k regex:persistent -s 3 -c 1 -f -o gpurun_out/r2_256_persistent_full python bench.py --steps 5 --warmup 3 > gpurun_out/ncu3.log 2>&1
+ls -la gpurun_out/*.ncu-rep
