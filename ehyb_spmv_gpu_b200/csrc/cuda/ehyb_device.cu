@@ -36,7 +36,7 @@ struct ehyb_handle {
     int device;
     cudaStream_t stream, h2d, d2h;
     int64_t n, ncols, nnz, nOvf, blobBytes, algBytes;
-    int nParts, W, kpp, nSlices, threads, ctasPerSM, kernel, kcEll, kcRem, grid;
+    int nParts, W, kpp, nSlices, threads, ctasPerSM, kernel, kcEll, kcRem, grid, slotsPerWarp;
     size_t smemBytes;
     ehyb_part_desc *parts;
     ehyb_slice_desc *slices;
@@ -113,6 +113,12 @@ extern "C" void ehyb_session_opts_default(ehyb_session_opts *o)
     o->kernel = 0;
 }
 
+static int env_int_early(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return s && s[0] ? atoi(s) : dflt;
+}
+
 /* kernel variants: register budget follows the number of resident threads per SM */
 typedef void (*main_kernel_t)(const MainArgs);
 static main_kernel_t pick_kernel(int kernel, int threads, int ctasPerSM)
@@ -132,22 +138,21 @@ static main_kernel_t staged_kernel(int threads, bool peer)
 }
 
 /* persistent, double-buffered variant (ehyb_persistent_kernel): 4-column chunks only */
-static main_kernel_t persistent_kernel(int threads, bool peer)
+static main_kernel_t persistent_kernel(int threads, bool peer, int slots)
 {
-    /* register budgets: 128 at <= 512 threads, 102 at <= 640, 80 at 768.  The multi-GPU build keeps a
-     * few more values live (calls into the exchange code): it spills at 80 registers, so peer
-     * sessions run at most kPeerPersistWarps = 20 warps (measured at config 2: 20 warps already
-     * stream at 99 % of the copy peak) */
-    if (peer) return threads <= 512 ? ehyb_persistent_kernel<512, 4, true> : ehyb_persistent_kernel<640, 4, true>;
-    return threads <= 512 ? ehyb_persistent_kernel<512, 4, false> : threads <= 640 ? ehyb_persistent_kernel<640, 4, false> : ehyb_persistent_kernel<768, 4, false>;
+    /* register budgets: 128 at <= 512 threads, 112 at <= 576, 96 at <= 640, 80 at 768.  The
+     * multi-GPU build keeps a few more values live (calls into the exchange code): it spills at 80
+     * registers, so peer sessions run at most kPeerPersistWarps = 20 warps.  Three staging slots
+     * per warp exist for the 512-thread builds only (16 warps x 3 x 2.5 KB = 120 KB).
+     * $EHYB_PERSIST_BUILD (experiments) forces a build with a larger thread bound. */
+    int b = env_int_early("EHYB_PERSIST_BUILD", 0);
+    if (b < threads) b = threads;
+    if (slots == 3) return peer ? ehyb_persistent_kernel<512, 4, true, 3> : ehyb_persistent_kernel<512, 4, false, 3>;
+    if (peer) return b <= 512 ? ehyb_persistent_kernel<512, 4, true, 2> : b <= 576 ? ehyb_persistent_kernel<576, 4, true, 2> : ehyb_persistent_kernel<640, 4, true, 2>;
+    return b <= 512 ? ehyb_persistent_kernel<512, 4, false, 2> : b <= 576 ? ehyb_persistent_kernel<576, 4, false, 2>
+           : b <= 640 ? ehyb_persistent_kernel<640, 4, false, 2> : ehyb_persistent_kernel<768, 4, false, 2>;
 }
 constexpr int kPeerPersistWarps = 20;
-
-static int env_int_early(const char *name, int dflt)
-{
-    const char *s = getenv(name);
-    return s && s[0] ? atoi(s) : dflt;
-}
 
 /* The persistent kernel's work list.  seq = the partitions in `order` (NULL: identity).
  *   full rounds  CTA c takes whole partitions seq[c + G*j]: at any time the G CTAs stream G
@@ -298,11 +303,25 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
          * by default); otherwise the staged kernel */
         const int grid = h->nSlices < prop.multiProcessorCount ? (h->nSlices > 0 ? h->nSlices : 1) : prop.multiProcessorCount;
         const size_t fixed = (size_t)kPersistHeader + 2 * (winBytes + cacheBytes);
-        const size_t perWarp = (size_t)kSlotsPerWarp * slot_bytes(4);
-        int nw = fixed + perWarp <= prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - fixed) / perWarp) : 0;
+        /* Warps and staging slots (2.5 KB each), measured on 27-point grids (profiles/r2_notes.md):
+         * what decides is the register budget of the consumer loop, not the bytes in flight -
+         * 16 warps x 2 slots in the 128-register build (512 threads) stream 256^3 in 785 us, 20 x 2
+         * at 96 registers in 828 us, 16 x 2 at 96 registers in 864 us, 16 x 3 slots in 802 us.  So:
+         * 16 warps wherever more than 20 would fit; where the two buffers leave room for 17..20
+         * (config 2: 20) all of them, which there is 1.5 % ahead of 16.  A third slot per warp is an
+         * experiment switch ($EHYB_PERSIST_SLOTS=3, 512-thread builds only). */
+        int slots = env_int("EHYB_PERSIST_SLOTS", 2);
+        const size_t room = fixed < prop.sharedMemPerBlockOptin ? prop.sharedMemPerBlockOptin - fixed : 0;
+        if (slots != 3 || room < (size_t)16 * 3 * slot_bytes(4) || (threads > 0 && threads != 512)) slots = 2;
+        const size_t perWarp = (size_t)slots * slot_bytes(4);
+        int nw = (int)(room / perWarp);
+        if (nw > 20 && env_int("EHYB_PERSIST_WARPS", 0) <= 0) nw = 16;
+        if (env_int("EHYB_PERSIST_WARPS", 0) > 0 && nw > env_int("EHYB_PERSIST_WARPS", 0)) nw = env_int("EHYB_PERSIST_WARPS", 0);
         if (nw > kMaxStageWarps) nw = kMaxStageWarps;
+        if (slots == 3 && nw > 16) nw = 16;
         if ((peerSession || env_int("EHYB_FORCE_PEER_BUILD", 0) || env_int("EHYB_TRACE", 0)) && nw > kPeerPersistWarps) nw = kPeerPersistWarps;
         if (threads > 0 && threads / 32 < nw) nw = threads / 32 > 0 ? threads / 32 : 1;
+        h->slotsPerWarp = slots;
         if (h->kpp != 1 || nw < (autoKernel ? 16 : 8)) {
             kernel = EHYB_KERNEL_STAGED;
         } else {
@@ -379,11 +398,12 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(ehyb_main_kernel<1024, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    for (int t = 512; t <= 768; t += 128)
-        for (int peer = 0; peer < 2; ++peer) {
-            CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-            CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        }
+    for (int t = 512; t <= 768; t += 64)
+        for (int peer = 0; peer < 2; ++peer)
+            for (int sl = 2; sl <= 3; ++sl) {
+                CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0, sl), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+                CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0, sl), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            }
     if (kernel == EHYB_KERNEL_PERSISTENT) {
         int rcTab = build_cta_tab(h, v, NULL);
         if (rcTab) return rcTab;
@@ -476,7 +496,7 @@ static int upload_session(const ehyb_layout *L, const ehyb_session_opts *opts, b
 /* peer: the launch carries a halo exchange, or the session records a per-CTA trace */
 static main_kernel_t main_kernel_of(const ehyb_handle *h, bool peer)
 {
-    if (h->kernel == EHYB_KERNEL_PERSISTENT) return persistent_kernel(h->threads, peer || h->trace != NULL || h->forcePeerBuild);
+    if (h->kernel == EHYB_KERNEL_PERSISTENT) return persistent_kernel(h->threads, peer || h->trace != NULL || h->forcePeerBuild, h->slotsPerWarp);
     if (h->kernel == EHYB_KERNEL_STAGED) return staged_kernel(h->threads, peer || h->trace != NULL);
     return pick_kernel(h->kernel, h->threads, h->ctasPerSM);
 }

@@ -658,6 +658,22 @@ __device__ __forceinline__ int2 lds_s32x2(uint32_t addr)
     return v;
 }
 
+/* shared-memory address of x[idx] for the two 16-bit indices packed in c: base + 8 * index.  Written
+ * as extract + multiply-add (2 instructions per gather; left to itself the compiler shifts, masks
+ * and adds: 3) - the index arithmetic is a third of the consumer loop's instructions. */
+__device__ __forceinline__ uint32_t xaddr_lo(uint32_t c, uint32_t base)
+{
+    uint32_t r;
+    asm("{\n.reg .u32 t;\nand.b32 t, %1, 0xffff;\nmad.lo.u32 %0, t, 8, %2;\n}" : "=r"(r) : "r"(c), "r"(base));
+    return r;
+}
+__device__ __forceinline__ uint32_t xaddr_hi(uint32_t c, uint32_t base)
+{
+    uint32_t r;
+    asm("{\n.reg .u32 t;\nshr.u32 t, %1, 16;\nmad.lo.u32 %0, t, 8, %2;\n}" : "=r"(r) : "r"(c), "r"(base));
+    return r;
+}
+
 /* Walks the chunks of the slices of one warp; every member is warp-uniform.  Chunk sizes are
  * compile-time powers of two so that the per-chunk bookkeeping is a handful of shifts (ncu on
  * the first version showed the consumers spending most of their issue slots on this
@@ -1042,8 +1058,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
  * those with halo columns come last, when the neighbours' push has long arrived.
  *
  * grid = min(#SMs, nSlices), block = NW*32, one CTA per SM.
- * smem = 512 B header (mbarriers, sequence counter) + 2 * (align128((W+2)*8) +
- * align128(cacheCap*8)) + NW * 2 * slot.  Requires ctasPerPart == 1.
+ * smem = 1 KB header (mbarriers, sequence counter) + 2 * (align128((W+2)*8) +
+ * align128(cacheCap*8)) + NW * NS * slot.  Requires ctasPerPart == 1.
  */
 /* mbarrier wait with a time limit: a protocol error between the warps must abort the kernel
  * (trap: the launch fails with an error), never leave the GPU spinning */
@@ -1072,7 +1088,7 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-constexpr int kPersistHeader = 512;
+constexpr int kPersistHeader = 1024;
 
 struct PMeta {
     int kc;    /* columns in the chunk */
@@ -1235,7 +1251,11 @@ __device__ __noinline__ bool stage_halo_columns(const MainArgs &a, const int32_t
     return true;
 }
 
-template <int kMaxThreads, int KCE, bool PEER>
+/* NS = staging slots per warp (2 or 3): the depth of a warp's chunk pipeline.  16 warps x 3 slots with
+ * the 128-register budget of a 512-thread CTA beat 20 x 2 at 96 registers wherever the two buffers
+ * leave 120 KB (27-point 256^3: 795 -> see profiles/r2_notes.md); measured: the register budget
+ * matters as much as the bytes in flight - the consumer's LDS chains decide how fast a slot turns around. */
+template <int kMaxThreads, int KCE, bool PEER, int NS>
 __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const __grid_constant__ MainArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1250,16 +1270,16 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     const int nj = __ldg(a.ctaStart + blockIdx.x + 1) - item0;
     const int4 *tab = reinterpret_cast<const int4 *>(a.ctaTab) + 2 * static_cast<size_t>(item0);
 
-    /* header: [0,16) window bars, [16,32) cache bars, [32,48) empty bars, [64,448) slot bars,
-     * [448,452) sequence counter */
+    /* header: [0,16) window bars, [16,32) cache bars, [32,48) empty bars, [64,640) slot bars,
+     * [960,964) sequence counter */
     const uint32_t hdr = smem_u32(smem);
-    int *seqCounter = reinterpret_cast<int *>(smem + 448);
+    int *seqCounter = reinterpret_cast<int *>(smem + 960);
     const uint32_t winBytes = (static_cast<uint32_t>(a.W + 2) * 8u + 127u) & ~127u;
     const uint32_t cacheBytes = (static_cast<uint32_t>(a.cacheCap) * 8u + 127u) & ~127u;
     const uint32_t bufBytes = winBytes + cacheBytes;
     unsigned char *buf0 = smem + kPersistHeader;
-    const uint32_t slotBar0 = hdr + 64u + static_cast<uint32_t>(warp * kSlotsPerWarp) * 8u;
-    const uint32_t slot0 = smem_u32(buf0) + 2u * bufBytes + static_cast<uint32_t>(warp * kSlotsPerWarp) * kSlotBytes;
+    const uint32_t slotBar0 = hdr + 64u + static_cast<uint32_t>(warp * NS) * 8u;
+    const uint32_t slot0 = smem_u32(buf0) + 2u * bufBytes + static_cast<uint32_t>(warp * NS) * kSlotBytes;
     const bool pusher = PEER && a.peer.flags != nullptr && static_cast<int>(blockIdx.x) < a.peer.pushCtas && warp == nw - 1;
     /* development (EHYB_TRACE=1, PEER build): 8 stamps per CTA - start, previous grid complete, push
      * done, first window staged, last warp done, SM, longest wait for the neighbours' flags (ns),
@@ -1289,7 +1309,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
             mbar_init(hdr + 16u + 8u * b, static_cast<uint32_t>(nw * 32)); /* cache: every lane arrives (through cp.async) */
             mbar_init(hdr + 32u + 8u * b, static_cast<uint32_t>(nw)); /* empty: one arrival per warp */
         }
-        for (int i = 0; i < nw * kSlotsPerWarp; ++i) mbar_init(hdr + 64u + i * 8u, 1);
+        for (int i = 0; i < nw * NS; ++i) mbar_init(hdr + 64u + i * 8u, 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -1300,9 +1320,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(keepPolicy));
     PWalker<KCE> wk;
     wk.start(tab, seqCounter, reinterpret_cast<const uint2 *>(a.slices), a.blob, nj, lane);
-    PMeta meta[2];
-    meta[0] = issue_pchunk(wk, slot0, slotBar0, lane, streamPolicy);
-    meta[1] = issue_pchunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane, streamPolicy);
+    PMeta meta0, meta1, meta2; /* chunk in slot 0, 1, 2 (named, not an array: the slot index is dynamic) */
+    meta0 = issue_pchunk(wk, slot0, slotBar0, lane, streamPolicy);
+    meta1 = issue_pchunk(wk, slot0 + kSlotBytes, slotBar0 + 8u, lane, streamPolicy);
+    meta2.kc = 0; meta2.flags = 0; meta2.t = 0;
+    if (NS > 2) meta2 = issue_pchunk(wk, slot0 + 2u * kSlotBytes, slotBar0 + 16u, lane, streamPolicy);
     uint32_t phases = 0;
 
     /* multi-GPU, pushing warp: everything of the halo push that does not need x */
@@ -1412,7 +1434,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     int s = 0;
 #pragma unroll 1
     for (;;) {
-        const PMeta m = s ? meta[1] : meta[0];
+        const PMeta m = s == 0 ? meta0 : (s == 1 || NS == 2) ? meta1 : meta2;
         if (!(m.flags & 4)) break;
         const uint32_t slot = slot0 + static_cast<uint32_t>(s) * kSlotBytes;
         const uint32_t bar = slotBar0 + static_cast<uint32_t>(s) * 8u;
@@ -1454,10 +1476,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
                         const double2 v1 = lds_f64x2(vAddr + (4 * g + 1) * 512u);
                         const double2 v2 = lds_f64x2(vAddr + (4 * g + 2) * 512u);
                         const double2 v3 = lds_f64x2(vAddr + (4 * g + 3) * 512u);
-                        const double x00 = lds_f64(xb + (c.x & 0xffffu) * 8u), x01 = lds_f64(xb + (c.z & 0xffffu) * 8u);
-                        const double x10 = lds_f64(xb + (c.x >> 16) * 8u), x11 = lds_f64(xb + (c.z >> 16) * 8u);
-                        const double x20 = lds_f64(xb + (c.y & 0xffffu) * 8u), x21 = lds_f64(xb + (c.w & 0xffffu) * 8u);
-                        const double x30 = lds_f64(xb + (c.y >> 16) * 8u), x31 = lds_f64(xb + (c.w >> 16) * 8u);
+                        const double x00 = lds_f64(xaddr_lo(c.x, xb)), x01 = lds_f64(xaddr_lo(c.z, xb));
+                        const double x10 = lds_f64(xaddr_hi(c.x, xb)), x11 = lds_f64(xaddr_hi(c.z, xb));
+                        const double x20 = lds_f64(xaddr_lo(c.y, xb)), x21 = lds_f64(xaddr_lo(c.w, xb));
+                        const double x30 = lds_f64(xaddr_hi(c.y, xb)), x31 = lds_f64(xaddr_hi(c.w, xb));
                         s0 = fma(v0.x, x00, s0);
                         s1 = fma(v0.y, x01, s1);
                         s0 = fma(v1.x, x10, s0);
@@ -1494,8 +1516,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
         }
         __syncwarp();
         const PMeta mn = issue_pchunk(wk, slot, bar, lane, streamPolicy);
-        if (s) meta[1] = mn; else meta[0] = mn;
-        s ^= 1;
+        if (s == 0) meta0 = mn; else if (s == 1 || NS == 2) meta1 = mn; else meta2 = mn;
+        s = s + 1 == NS ? 0 : s + 1;
     }
     if (PEER && tr && lane == 0) atomicMax(tr + 4, global_timer_ns());
     /* (every warp has passed all nj-1 switch markers here: the walker always ends in the last
