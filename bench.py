@@ -179,6 +179,56 @@ def gpu_comparisons(m, xr, y_ref, absAx):
     return out
 
 
+def reference_gpu_row(iters=100):
+    """The reference's OWN device path on this GPU (reported row): reference kernel.cu +
+    convert.c, unmodified, compiled in place for sm_100a (oracle/_ref/ref_gpu_bench, built by
+    `make -C oracle refgpu`), at the reference's own partition parameters (82-SM heuristic), timed with
+    CUDA events as shipped (the remainder phase only runs in the first launch) and with the
+    remainder counter reset before every launch.  Outside the timed region; absent if not built."""
+    exe = ROOT / "oracle" / "_ref" / "ref_gpu_bench"
+    if not exe.exists():
+        return {"unavailable": "oracle/_ref/ref_gpu_bench not built (needs /root/reference at build time)"}
+    import subprocess
+    import tempfile
+    from oracle import oracle as O
+    try:
+        orc = O.Oracle()
+        n, li, lj, lv = O.gen_stencil27_lower(*GRID)
+        x = orc.x_reference(n)
+        m = orc.read_sym(n, li, lj, lv, x)
+        P, W, kpp = orc.heuristic_ref(n, True)
+        xadj, adj = orc.graph(m)
+        part = O.mtmetis_partition(xadj, adj, P, nthreads=1)
+        r = orc.reorder(m, P, W, part)
+        xr = orc.vector_reorder(x, r["reorderList"])
+        with tempfile.TemporaryDirectory() as d:
+            fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+            with open(fin, "wb") as f:
+                f.write(np.array([n, m["nnz"], P, W, max(kpp, 1)], np.int32).tobytes())
+                for k in ("I", "J"):
+                    f.write(r[k].tobytes())
+                f.write(r["V"].tobytes())
+                for k in ("rowIdx", "numInRow", "numInRow2", "partBoundary"):
+                    f.write(r[k].astype(np.int32).tobytes())
+                f.write(xr.tobytes())
+            res = subprocess.run([str(exe), fin, fout, str(iters)], capture_output=True, text=True, timeout=300)
+            line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+            if res.returncode or not line:
+                return {"error": (res.stdout + res.stderr)[-400:]}
+            row = json.loads(line[-1])["reference_gpu"]
+            yy = np.fromfile(fout, dtype=np.float64)
+        y_ref = orc.csr_spmv(r["rowIdx"], r["J"], r["V"], xr)
+        absAx = orc.csr_abs_spmv(r["rowIdx"], r["J"], r["V"], xr)
+        row["rows_outside_1e-12_gate_as_shipped"] = int(np.count_nonzero(~(np.abs(yy[:n] - y_ref) <= 1e-12 * absAx)))
+        row["rows_outside_1e-12_gate_repaired"] = int(np.count_nonzero(~(np.abs(yy[n:] - y_ref) <= 1e-12 * absAx)))
+        row["partitions"], row["window"] = P, W
+        row["what"] = ("reference kernel.cu:110-195 + convert.c, unmodified, nvcc -arch=sm_100a, same GPU, same matrix, the reference's "
+                       "own partition parameters; 'as_shipped' = remainder work only in launch 1 (B-1), 'repaired' = every launch complete")
+        return row
+    except Exception as e:  # a comparison row must never take the bench down
+        return {"error": repr(e)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -273,6 +323,8 @@ def run_ours(args):
     gate_fail = int(np.count_nonzero(~(np.abs(s.get_y() - y_cpu) <= 1e-12 * absAx)))
 
     comparisons = gpu_comparisons(m, xr, y_cpu, absAx)
+    if GRID == (128, 128, 128) and os.environ.get("EHYB_BENCH_REFERENCE_GPU", "1") != "0":
+        comparisons["reference_kernel_sm100a"] = reference_gpu_row()
 
     peaks, peak_src = measured_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))

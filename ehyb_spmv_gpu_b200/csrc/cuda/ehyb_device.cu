@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../host/common.h"
+#include "../host/ovfstream.h"
 #include "ehyb_kernels.cuh"
 
 using namespace ehyb;
@@ -60,6 +61,13 @@ struct ehyb_handle {
     /* multi-GPU, peer-memory exchange: word in mapped pinned host memory that a kernel sets when a
      * wait on a neighbour ran into the time limit (sticky); NULL for single-GPU sessions */
     volatile uint32_t *peerStatus_h;
+    /* large overflow lists: the CSR-like stream format (host/ovfstream.c) instead of the COO list */
+    int ovfStream, ovfHubs, ovfGroups, ovfTiles;
+    uint32_t *ovfColEnc;
+    uint2 *ovfGrp;
+    int32_t *ovfRowOfSeg, *ovfHubCols, *ovfCarryRow;
+    double *ovfCarryVal;
+    int64_t ovfDeviceBytes, ovfHubRefs;
     int forcePeerBuild; /* development ($EHYB_FORCE_PEER_BUILD): single-GPU sessions run the multi-GPU build of the kernel */
 };
 
@@ -258,7 +266,8 @@ extern "C" void ehyb_free(ehyb_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     cudaFree(h->parts); cudaFree(h->slices); cudaFree(h->blob);
-    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->ctaTab); cudaFree(h->ctaStart); cudaFree(h->trace);
+    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->ovfColEnc); cudaFree(h->ovfGrp); cudaFree(h->ovfRowOfSeg);
+    cudaFree(h->ovfHubCols); cudaFree(h->ovfCarryRow); cudaFree(h->ovfCarryVal); cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->ctaTab); cudaFree(h->ctaStart); cudaFree(h->trace);
     cudaFree(h->x); cudaFree(h->y);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->xb[i]); cudaFree(h->yb[i]);
@@ -380,7 +389,41 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     CU(cudaMemcpyAsync(h->blob, v->blob, (size_t)h->blobBytes, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMalloc(&h->cacheCols, sizeof(int32_t) * (size_t)(v->cacheTotal ? v->cacheTotal : 1)));
     if (v->cacheTotal) CU(cudaMemcpyAsync(h->cacheCols, v->cacheCols, sizeof(int32_t) * (size_t)v->cacheTotal, cudaMemcpyHostToDevice, h->stream));
-    if (h->nOvf > 0) {
+    /* Overflow list.  Short lists (what the slices could not hold, halo entries) stay a COO reduced
+     * with one atomic per row segment; long ones - >= $EHYB_OVF_STREAM_MIN entries, default 2^20, or
+     * any length with $EHYB_DETERMINISTIC=1 - become the CSR-like stream of host/ovfstream.c: 12.25
+     * instead of 16 bytes per entry, hub columns in shared memory, no atomics (bit-reproducible y).
+     * Not for peer-memory sessions: there the overflow kernel waits for the neighbours' flags. */
+    h->ovfStream = 0;
+    if (h->nOvf > 0 && !peerSession &&
+        (env_int("EHYB_DETERMINISTIC", 0) || h->nOvf >= (int64_t)env_int("EHYB_OVF_STREAM_MIN", 1 << 20)) && env_int("EHYB_OVF_STREAM", 1)) {
+        ehyb_ovfstream st;
+        int hubCap = env_int("EHYB_OVF_HUBS", 16384);
+        const int hubMax = (int)((prop.sharedMemPerBlockOptin - 1024) / sizeof(double));
+        if (hubCap > hubMax) hubCap = hubMax;
+        if (hubCap < 0) hubCap = 0;
+        int rcS = ehyb_ovfstream_build(h->nOvf, v->ovfRow, v->ovfCol, h->ncols, hubCap, &st);
+        if (rcS) return rcS;
+        h->ovfStream = 1;
+        h->ovfHubs = st.nHub; h->ovfGroups = (int)st.nGroups; h->ovfDeviceBytes = st.deviceBytes; h->ovfHubRefs = st.hubRefs;
+        h->ovfTiles = (int)((st.nGroups + kStreamTileGroups - 1) / kStreamTileGroups);
+        cudaError_t e = cudaMalloc(&h->ovfVal, sizeof(double) * (size_t)h->nOvf);
+        if (e == cudaSuccess) e = cudaMalloc(&h->ovfColEnc, sizeof(uint32_t) * (size_t)h->nOvf);
+        if (e == cudaSuccess) e = cudaMalloc(&h->ovfGrp, sizeof(uint2) * (size_t)st.nGroups);
+        if (e == cudaSuccess) e = cudaMalloc(&h->ovfRowOfSeg, sizeof(int32_t) * (size_t)st.nSeg);
+        if (e == cudaSuccess) e = cudaMalloc(&h->ovfHubCols, sizeof(int32_t) * (size_t)(st.nHub ? st.nHub : 1));
+        if (e == cudaSuccess) e = cudaMalloc(&h->ovfCarryRow, sizeof(int32_t) * 2 * (size_t)h->ovfTiles);
+        if (e == cudaSuccess) e = cudaMalloc(&h->ovfCarryVal, sizeof(double) * 2 * (size_t)h->ovfTiles);
+        if (e == cudaSuccess) e = cudaMemcpy(h->ovfVal, v->ovfVal, sizeof(double) * (size_t)h->nOvf, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->ovfColEnc, st.col, sizeof(uint32_t) * (size_t)h->nOvf, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->ovfGrp, st.grp, sizeof(uint2) * (size_t)st.nGroups, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->ovfRowOfSeg, st.rowOfSeg, sizeof(int32_t) * (size_t)st.nSeg, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && st.nHub) e = cudaMemcpy(h->ovfHubCols, st.hubCols, sizeof(int32_t) * (size_t)st.nHub, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(h->ovfCarryRow, 0xff, sizeof(int32_t) * 2 * (size_t)h->ovfTiles);
+        ehyb_ovfstream_free(&st);
+        if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "overflow stream upload: %s", cudaGetErrorString(e));
+        CU(cudaFuncSetAttribute(ehyb_ovfstream_kernel<kStreamTileGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    } else if (h->nOvf > 0) {
         CU(cudaMalloc(&h->ovfRow, sizeof(int32_t) * (size_t)h->nOvf));
         CU(cudaMalloc(&h->ovfCol, sizeof(int32_t) * (size_t)h->nOvf));
         CU(cudaMalloc(&h->ovfVal, sizeof(double) * (size_t)h->nOvf));
@@ -573,6 +616,26 @@ static int overflow_per_warp(const ehyb_handle *h)
 static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s, const PeerArgs *pa)
 {
     if (h->nOvf <= 0) return EHYB_OK;
+    if (h->ovfStream) {
+        /* the CSR-like stream: one persistent CTA per SM, then the carry fix-up; plain launches (the
+         * stream kernel reads x through the read-only path: it must not start before its predecessor
+         * is complete) */
+        if (pa != NULL && pa->flags != NULL) return ehyb_fail(EHYB_ERR_ARG, "the overflow stream does not carry the peer-memory exchange");
+        OvfStreamArgs a;
+        a.val = h->ovfVal; a.col = h->ovfColEnc; a.grp = h->ovfGrp; a.rowOfSeg = h->ovfRowOfSeg; a.hubCols = h->ovfHubCols;
+        a.nHub = h->ovfHubs; a.count = h->nOvf; a.nGroups = h->ovfGroups; a.nTiles = h->ovfTiles;
+        a.x = x_d; a.y = y_d; a.carryRow = h->ovfCarryRow; a.carryVal = h->ovfCarryVal;
+        a.accumulate = h->skipMain ? 0 : 1;
+        const int64_t tilesPerCta = 32;
+        int grid = h->smCount;
+        if ((int64_t)grid * tilesPerCta > h->ovfTiles) grid = (int)((h->ovfTiles + tilesPerCta - 1) / tilesPerCta);
+        ehyb_ovfstream_kernel<kStreamTileGroups><<<grid, 1024, sizeof(double) * (size_t)h->ovfHubs, s>>>(a);
+        CU(cudaGetLastError());
+        const int64_t n2 = 2 * (int64_t)h->ovfTiles;
+        ehyb_ovfstream_fixup<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(h->ovfCarryRow, h->ovfCarryVal, n2, y_d, a.accumulate);
+        CU(cudaGetLastError());
+        return EHYB_OK;
+    }
     OverflowArgs o;
     o.row = h->ovfRow; o.col = h->ovfCol; o.val = h->ovfVal; o.count = h->nOvf; o.x = x_d; o.y = y_d;
     o.perWarp = overflow_per_warp(h);
@@ -610,7 +673,7 @@ static int launch_product(ehyb_handle *h, const double *x_d, double *y_d, cudaSt
     return rc ? rc : launch_overflow(h, x_d, y_d, s, NULL);
 }
 
-extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h) { return h ? (h->nOvf > 0 ? 2 : 1) - (h->skipMain ? 1 : 0) : 0; }
+extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h) { return h ? (h->nOvf > 0 ? (h->ovfStream ? 3 : 2) : 1) - (h->skipMain ? 1 : 0) : 0; }
 
 extern "C" int ehyb_spmv(ehyb_handle *h, const double *x_d, double *y_d)
 {
@@ -788,7 +851,7 @@ extern "C" int ehyb_trace_read(ehyb_handle *h, unsigned long long *out, int *cta
 extern "C" const char *ehyb_session_kernel(const ehyb_handle *h)
 {
     if (!h) return "";
-    if (h->skipMain) return "ehyb_overflow_kernel";
+    if (h->skipMain) return h->ovfStream ? "ehyb_ovfstream_kernel" : "ehyb_overflow_kernel";
     return h->kernel == EHYB_KERNEL_PERSISTENT ? "ehyb_persistent_kernel" : h->kernel == EHYB_KERNEL_STAGED ? "ehyb_staged_kernel" : "ehyb_main_kernel";
 }
 

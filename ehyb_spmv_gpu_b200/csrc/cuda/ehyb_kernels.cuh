@@ -189,6 +189,20 @@ __device__ __forceinline__ uint4 ld_stream_u32x4(const uint4 *p, uint64_t pol)
     return v;
 }
 
+__device__ __forceinline__ int ld_stream_s32(const int *p, uint64_t pol)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ double ld_stream_f64(const double *p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 __device__ __forceinline__ int2 ld_stream_s32x2(const int2 *p, uint64_t pol)
 {
     int2 v;
@@ -1606,4 +1620,149 @@ __global__ void __launch_bounds__(256) ehyb_overflow_kernel(const OverflowArgs a
     if (a.lateTrigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+/* ---------------------------------------------------------------- overflow stream --- */
+
+/*
+ * Large overflow lists (power-law graphs: the list is the matrix) in the CSR-like stream format of
+ * host/ovfstream.c: 12 bytes per entry + 8 per 32 entries, hub columns in shared memory, no
+ * atomics.  One persistent CTA of 1 024 threads per SM; a warp takes tiles of TG x 32 consecutive
+ * entries (tile t -> warp t mod #warps: neighbouring warps stream neighbouring tiles).
+ *
+ *   - the x values of the hub columns (the <= 16 384 most referenced ones) are gathered into shared
+ *     memory once per CTA; an entry with the top bit of its column set reads there (LDS) instead of
+ *     occupying one 32-byte L1TEX sector per lane;
+ *   - all the streaming loads of a tile first (column + value of TG groups), then all the gathers;
+ *   - row segments: lane j of a group belongs to segment seg0 + popc(mask & bits 1..j); products
+ *     are summed per segment with a warp-shuffle segmented scan, carried from group to group
+ *     inside the tile in registers;
+ *   - a segment that lies inside the tile is stored by the lane at its end: y[row] = sum (or +=
+ *     when the main kernel has written the row's slice part);
+ *   - the tile's first segment if it continues a row of the previous tile, and its last one if the
+ *     row goes on in the next tile, go to the tile's two CARRY slots instead; ehyb_ovfstream_fixup
+ *     adds the slots of a row in tile order.  Who adds what, and in which order, is fixed by the
+ *     data: y is bit-reproducible (the COO kernel's atomics are not).
+ */
+struct OvfStreamArgs {
+    const double *val;
+    const uint32_t *col;       /* column, or 0x80000000 | hub index */
+    const uint2 *grp;          /* per 32 entries: {segment of the first entry, new-row mask} */
+    const int32_t *rowOfSeg;
+    const int32_t *hubCols;
+    int nHub;
+    int64_t count;
+    int nGroups, nTiles;
+    const double *x;
+    double *y;
+    int32_t *carryRow;         /* [2 * nTiles]: head and tail slot of every tile, -1 = unused */
+    double *carryVal;
+    int accumulate;            /* 1: y[row] += sum (the main kernel wrote y), 0: y[row] = sum (y was zeroed) */
+};
+
+constexpr int kStreamTileGroups = 4; /* 128 entries per tile */
+
+template <int TG>
+__global__ void __launch_bounds__(1024, 1) ehyb_ovfstream_kernel(const __grid_constant__ OvfStreamArgs a)
+{
+    extern __shared__ __align__(16) double hub[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory"); /* x, and y as the main kernel / the memset left it */
+    for (int i = tid; i < a.nHub; i += blockDim.x) hub[i] = ld_gather_f64(a.x + __ldg(a.hubCols + i));
+    __syncthreads();
+    const uint64_t pol = make_evict_first_policy();
+    const int nwarps = blockDim.x >> 5;
+    const int W = gridDim.x * nwarps;
+    const uint32_t lanemaskLe = (2u << lane) - 1u; /* bits 0..lane */
+    for (int tile = static_cast<int>(blockIdx.x) * nwarps + (tid >> 5); tile < a.nTiles; tile += W) {
+        const int g0 = tile * TG;
+        uint2 gm[TG];
+        uint32_t c[TG];
+        double v[TG], xv[TG];
+#pragma unroll
+        for (int u = 0; u < TG; ++u) {
+            const int gi = g0 + u;
+            gm[u] = gi < a.nGroups ? __ldg(a.grp + gi) : make_uint2(0u, 0u);
+            const int64_t i = static_cast<int64_t>(gi) * 32 + lane;
+            const bool live = i < a.count;
+            c[u] = live ? static_cast<uint32_t>(ld_stream_s32(reinterpret_cast<const int *>(a.col) + i, pol)) : 0x80000000u;
+            v[u] = live ? ld_stream_f64(a.val + i, pol) : 0.0;
+        }
+        const bool nextStartsNew = g0 + TG < a.nGroups ? (__ldg(&a.grp[g0 + TG].y) & 1u) != 0 : true;
+#pragma unroll
+        for (int u = 0; u < TG; ++u) xv[u] = (c[u] & 0x80000000u) ? (a.nHub ? hub[c[u] & 0x7fffffffu] : 0.0) : __ldg(a.x + c[u]); /* (plain launch: x is constant while this grid lives) */
+        /* the tile's first and last segment */
+        const int liveGroups = min(TG, a.nGroups - g0);
+        const bool headCont = (gm[0].y & 1u) == 0u;
+        const int headSeg = static_cast<int>(gm[0].x);
+        const bool tailCont = !nextStartsNew;
+        int tailSeg;
+        {
+            const int64_t left = a.count - static_cast<int64_t>(g0 + liveGroups - 1) * 32; /* live lanes of the last live group */
+            const uint32_t liveMask = left >= 32 ? 0xffffffffu : ((1u << static_cast<int>(left)) - 1u);
+            uint2 last = gm[0];
+#pragma unroll
+            for (int u = 1; u < TG; ++u)
+                if (u < liveGroups) last = gm[u];
+            tailSeg = static_cast<int>(last.x) + __popc(last.y & liveMask & ~1u);
+        }
+        if (lane == 0) { /* slots nobody will write this product */
+            if (!headCont) a.carryRow[2 * tile] = -1;
+            if (!tailCont) a.carryRow[2 * tile + 1] = -1;
+        }
+        auto store = [&](int seg, double sum) {
+            const int row = __ldg(a.rowOfSeg + seg);
+            const bool isHead = headCont && seg == headSeg, isTail = tailCont && seg == tailSeg;
+            if (isHead) {
+                a.carryRow[2 * tile] = row;
+                a.carryVal[2 * tile] = sum;
+                if (isTail) { a.carryRow[2 * tile + 1] = row; a.carryVal[2 * tile + 1] = 0.0; } /* the whole tile inside one row */
+            } else if (isTail) {
+                a.carryRow[2 * tile + 1] = row;
+                a.carryVal[2 * tile + 1] = sum;
+            } else if (a.accumulate) {
+                a.y[row] += sum;
+            } else {
+                a.y[row] = sum;
+            }
+        };
+        int carrySeg = -1;
+        double carry = 0.0;
+#pragma unroll
+        for (int u = 0; u < TG; ++u) {
+            if (u >= liveGroups) break; /* warp-uniform */
+            const bool live = static_cast<int64_t>(g0 + u) * 32 + lane < a.count;
+            const int seg = live ? static_cast<int>(gm[u].x) + __popc(gm[u].y & lanemaskLe & ~1u) : -2 - lane;
+            double prod = v[u] * xv[u];
+            if (lane == 0 && seg == carrySeg) prod += carry;              /* continue the carried segment */
+            if (lane == 0 && carrySeg >= 0 && seg != carrySeg) store(carrySeg, carry); /* it ended with the previous group */
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, prod, off);
+                const int ss = __shfl_up_sync(0xffffffffu, seg, off);
+                if (lane >= off && ss == seg) prod += t;
+            }
+            const int snext = __shfl_down_sync(0xffffffffu, seg, 1);
+            const bool tailOfSeg = live && (lane == 31 || snext != seg);
+            const bool carries = lane == 31 && live && u + 1 < liveGroups; /* may continue in the next group of this tile */
+            if (tailOfSeg && !carries) store(seg, prod);
+            carrySeg = __shfl_sync(0xffffffffu, carries ? seg : -1, 31);
+            carry = __shfl_sync(0xffffffffu, prod, 31);
+        }
+    }
+}
+
+/* adds the carry slots of every row that spans tiles, in tile order (one thread per run of equal rows) */
+__global__ void __launch_bounds__(256) ehyb_ovfstream_fixup(const int32_t *__restrict__ carryRow, const double *__restrict__ carryVal, int64_t n2,
+                                                          double *__restrict__ y, int accumulate)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    const int r = carryRow[i];
+    if (r < 0 || (i > 0 && carryRow[i - 1] == r)) return;
+    double sum = 0.0;
+    for (int64_t j = i; j < n2 && carryRow[j] == r; ++j) sum += carryVal[j];
+    y[r] = accumulate ? y[r] + sum : sum;
+}
+
 } /* namespace ehyb */
+

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""BASELINE.json config 4 (R-MAT) timing of the overflow paths on one layout: the CSR-like stream with and
+without hub columns, the COO list with atomics, cuSPARSE CSR on the same matrix.
+  python scripts/rmat_variants.py --scale 24 [--iters 30]"""
+import argparse, ctypes as C, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ehyb_spmv_gpu_b200 import api
+from oracle import oracle as O
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scale", type=int, default=22)
+ap.add_argument("--iters", type=int, default=30)
+a = ap.parse_args()
+t = time.time()
+n, fi, fj, fv = api.gen_rmat(a.scale, 16, seed=1, add_diagonal=False)
+x = np.random.default_rng(0).uniform(-0.1, 0.1, n)
+m = api.CooMatrix.from_general(n, fi, fj, fv, x)
+del fi, fj, fv
+pl = api.plan(n)
+m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
+m.reorder_with_partition((np.arange(n, dtype=np.int64) * pl.nParts // n).astype(np.uint32))
+lay = api.Layout(m)
+st = lay.stats()
+print(f"rmat scale {a.scale}: n={n} nnz={st['nnz']} host {time.time()-t:.1f}s; overflow {st['nnzOverflow']} algBytes {st['algBytes']} COO formatBytes {st['formatBytes']}", flush=True)
+xr = m.vector_reorder(x)
+orc = O.Oracle()
+arr = m.arrays()
+y_ref = orc.csr_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
+absAx = orc.csr_abs_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
+for name, env in (("stream + 16384 hubs", {}), ("stream + 8192 hubs", {"EHYB_OVF_HUBS": "8192"}), ("stream, no hubs", {"EHYB_OVF_HUBS": "0"}),
+                  ("COO list + atomics (round 1)", {"EHYB_OVF_STREAM": "0"})):
+    for k in ("EHYB_OVF_HUBS", "EHYB_OVF_STREAM"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    s = api.Session(lay)
+    y = s.spmv_host(xr)
+    bad = int(np.count_nonzero(~(np.abs(y - y_ref) <= 1e-12 * absAx)))
+    same = bool(np.array_equal(s.spmv_host(xr), y))
+    s.set_x(xr)
+    ms = s.time_spmv(5, a.iters)
+    ms = ms[0] if isinstance(ms, tuple) else ms
+    per = ms / a.iters
+    print(f"{name:32s} {per*1e3:8.1f} us  {2*st['nnz']/(per*1e6):7.1f} GFLOP/s  {st['algBytes']/(per*1e6):7.1f} GB/s alg  gate fails {bad}  bit-reproducible {same}  kernel {s.kernel_name()}", flush=True)
+    s.free()
+cus = os.path.join(ROOT, "ehyb_spmv_gpu_b200", "lib", "libehyb_cusparse.so")
+if os.path.exists(cus):
+    lib = C.CDLL(cus)
+    for alg in (1, 2):
+        us = C.c_float(); yc = np.empty(n)
+        if lib.ehyb_cusparse_spmv(C.byref(m.c), xr.ctypes.data_as(C.POINTER(C.c_double)), yc.ctypes.data_as(C.POINTER(C.c_double)), 3, 20, alg, C.byref(us)) == 0:
+            print(f"cuSPARSE CSR ALG{alg}: {us.value:.1f} us per product, {2*st['nnz']/(us.value*1e3):.1f} GFLOP/s", flush=True)

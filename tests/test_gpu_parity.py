@@ -189,3 +189,52 @@ def test_persistent_kernel_bit_exact_and_gate(orc, kind, dims, P, W):
     ms, kms = s3.time_spmv(3, 20, kernel_only=True)
     assert ms > 0 and np.array_equal(s3.get_y(), y3) or st["nOverflow"] > 0
     s2.free(); s3.free(); lay.free(); m.free()
+
+
+@pytest.mark.parametrize("case", ["rmat_all_overflow", "rmat_slices_plus_stream", "stencil_no_cache", "one_long_row"])
+def test_overflow_stream_is_deterministic(orc, case, monkeypatch):
+    """Large overflow lists run as a CSR-like stream (host/ovfstream.c, ehyb_ovfstream_kernel): hub columns
+    in shared memory, row segments summed by warp shuffles, rows that span warp tiles through carry slots
+    and a fix-up kernel - no atomics.  EHYB_DETERMINISTIC=1 selects it for lists of any length.  Bars: the
+    accuracy gate, and y BIT-IDENTICAL between products and between sessions (the COO kernel's atomics do
+    not give that)."""
+    monkeypatch.setenv("EHYB_DETERMINISTIC", "1")
+    if case.startswith("rmat"):
+        n, fi, fj, fv = api.gen_rmat(14, 16, seed=5, add_diagonal=False)
+        m = api.CooMatrix.from_general(n, fi, fj, fv, util.x_random(n, 1))
+        pl = api.plan(n)
+        m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
+        m.reorder_with_partition((np.arange(n, dtype=np.int64) * pl.nParts // n).astype(np.uint32))
+        lay = api.Layout(m, min_coverage=0.9 if case == "rmat_all_overflow" else -1.0)
+    elif case == "stencil_no_cache":
+        m = util.product_pipeline("st27", (40, 40, 40), 20, 3264, 1, x=util.x_random(64000, 1))
+        n = m.n
+        lay = api.Layout(m, cache_cap=-1)       # every entry outside the window goes to the list
+    else:
+        # a matrix whose first row is dense (n entries: spans hundreds of warp tiles) + a tridiagonal rest
+        n = 40000
+        fi = np.concatenate([np.zeros(n, np.int32), np.arange(1, n, dtype=np.int32), np.arange(1, n, dtype=np.int32)])
+        fj = np.concatenate([np.arange(n, dtype=np.int32), np.arange(1, n, dtype=np.int32), np.arange(0, n - 1, dtype=np.int32)])
+        fv = util.x_random(len(fi), 3)
+        m = api.CooMatrix.from_general(n, fi, fj, fv, util.x_random(n, 1))
+        m.set_plan(8, 5056, 1)
+        m.reorder_with_partition((np.arange(n, dtype=np.int64) * 8 // n).astype(np.uint32))
+        lay = api.Layout(m)
+    st = lay.stats()
+    assert st["nOverflow"] > 0
+    s = api.Session(lay)
+    assert s.launches_per_spmv() == (2 if st["nnzEll"] + st["nnzRemInSlice"] == 0 else 3)
+    a = m.arrays()
+    ys = []
+    for seed in (7, 8):
+        xr = m.vector_reorder(util.x_random(n, seed))
+        y = s.spmv_host(xr)
+        util.assert_within_gate(y, orc.csr_spmv(a["rowIdx"], a["J"], a["V"], xr), orc.csr_abs_spmv(a["rowIdx"], a["J"], a["V"], xr))
+        assert np.array_equal(s.spmv_host(xr), y), "a second product of the same x changed bits"
+        ys.append((xr, y))
+    s.set_x(ys[0][0])
+    s.time_spmv(2, 10)
+    assert np.array_equal(s.get_y(), ys[0][1]), "back-to-back products changed bits"
+    s2 = api.Session(lay)
+    assert np.array_equal(s2.spmv_host(ys[1][0]), ys[1][1]), "another session gives other bits"
+    s.free(); s2.free(); lay.free(); m.free()
