@@ -144,6 +144,12 @@ def build_matrix(grid, x=None):
     except Exception:
         dev = api.device_info_b200()
     pl = api.plan(n, dev, kernel=api.KERNEL_PERSISTENT)  # single GPU: partitions sized for the persistent kernel
+    # partition stage: deterministic and parallel (hierpart.c: 8 single-threaded mt-metis processes at once)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    api.L.load().ehyb_set_partition_pieces(int(os.environ.get("EHYB_PARTITION_PIECES", min(8, cores))))
     m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
     m.reorder()
     lay = api.Layout(m, er_fill=float(os.environ.get("EHYB_ER_FILL", "-1")))

@@ -128,12 +128,12 @@ EXPORTS = [
     "ehyb_mg_local_build", "ehyb_mg_local_halo", "ehyb_mg_local_set_send", "ehyb_mg_local_graph",
     "ehyb_mg_local_finish", "ehyb_mg_local_view", "ehyb_mg_local_free", "ehyb_mg_unique_id",
     "ehyb_mg_session_create", "ehyb_mg_session_handle", "ehyb_mg_spmv", "ehyb_mg_time_spmv", "ehyb_mg_spmv_host_batch",
-    "ehyb_mg_p2p_supported", "ehyb_mg_session_create_p2p", "ehyb_mg_p2p_export", "ehyb_mg_p2p_connect",
+    "ehyb_mg_p2p_supported", "ehyb_mg_session_create_p2p", "ehyb_mg_p2p_export", "ehyb_mg_p2p_connect", "ehyb_mg_p2p_connect_local",
     "ehyb_mg_status", "ehyb_mg_launches_per_spmv",
     "ehyb_mg_session_free", "ehyb_gen_stencil27_rows", "ehyb_host_alloc_pinned", "ehyb_host_free_pinned",
     "ehyb_session_info",
     "ehyb_layout_builder_begin", "ehyb_layout_builder_add", "ehyb_layout_builder_finish", "ehyb_layout_builder_abort",
-    "ehyb_grid_brick_graph", "ehyb_partition_graph_weighted", "ehyb_grid_decomp_create", "ehyb_grid_decomp_info",
+    "ehyb_grid_brick_graph", "ehyb_partition_graph_weighted", "ehyb_partition_graph_hier", "ehyb_set_partition_pieces", "ehyb_get_partition_pieces", "ehyb_grid_decomp_create", "ehyb_grid_decomp_info",
     "ehyb_grid_decomp_free", "ehyb_mg_grid_build", "ehyb_mg_local_natural_ids", "ehyb_grid_natural_ids", "ehyb_grid_rows",
 ]
 

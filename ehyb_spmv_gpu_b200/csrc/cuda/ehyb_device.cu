@@ -978,7 +978,7 @@ struct ehyb_mg_session {
     uint32_t *status_d;          /* device view of status_h */
     uint32_t *status_h;          /* mapped pinned host word, see ehyb_handle.peerStatus_h */
     uint32_t epoch, recvMask, nbrMask;
-    int nPeers, pushCtas, connected;
+    int nPeers, pushCtas, connected, peerIsLocal;
     unsigned long long timeoutNs;
 };
 
@@ -1010,7 +1010,7 @@ extern "C" void ehyb_mg_session_free(ehyb_mg_session *s)
     if (s->comm && g_nccl.dl) g_nccl.CommDestroy(s->comm);
     if (s->peerBase) {
         for (int g = 0; g < s->nranks; ++g)
-            if (s->peerBase[g]) cudaIpcCloseMemHandle(s->peerBase[g]);
+            if (s->peerBase[g] && !s->peerIsLocal) cudaIpcCloseMemHandle(s->peerBase[g]);
         free(s->peerBase);
     }
     cudaFree(s->shared); cudaFree(s->pushDst_d[0]); cudaFree(s->pushDst_d[1]); cudaFree(s->peerFlag_d);
@@ -1241,14 +1241,16 @@ extern "C" int ehyb_mg_p2p_export(ehyb_mg_session *s, void *blob)
     return EHYB_OK;
 }
 
-extern "C" int ehyb_mg_p2p_connect(ehyb_mg_session *s, const void *blobs, const int64_t *recvOffsetOnPeer)
+/* connect `s` to its neighbours described by B[] (one entry per rank); localBase != NULL: the
+ * neighbours live in THIS process (ehyb_mg_p2p_connect_local) and localBase[g] is rank g's shared
+ * allocation itself, else it is mapped through the CUDA IPC handle of B[g] */
+static int p2p_connect_impl(ehyb_mg_session *s, const P2PBlob *B, const int64_t *recvOffsetOnPeer, void *const *localBase)
 {
-    if (!s || !blobs || !recvOffsetOnPeer || s->exchange != EHYB_MG_P2P) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_connect: bad argument");
     if (s->connected) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_connect: already connected");
     CU(cudaSetDevice(s->h->device));
     const int R = s->nranks;
-    const P2PBlob *B = (const P2PBlob *)blobs;
     s->peerBase = (void **)calloc((size_t)R, sizeof(void *));
+    s->peerIsLocal = localBase != NULL;
     double **dst[2] = {(double **)malloc(sizeof(double *) * (size_t)(s->nSend ? s->nSend : 1)),
                        (double **)malloc(sizeof(double *) * (size_t)(s->nSend ? s->nSend : 1))};
     uint32_t **flagAddr = (uint32_t **)malloc(sizeof(uint32_t *) * (size_t)R);
@@ -1268,10 +1270,17 @@ extern "C" int ehyb_mg_p2p_connect(ehyb_mg_session *s, const void *blobs, const 
             int can = 0;
             CU(cudaDeviceCanAccessPeer(&can, s->h->device, B[g].device));
             if (!can) return ehyb_fail(EHYB_ERR_PEER, "GPU %d cannot access GPU %d (rank %d) directly", s->h->device, B[g].device, g);
-            cudaError_t e = cudaIpcOpenMemHandle(&s->peerBase[g], B[g].handle, cudaIpcMemLazyEnablePeerAccess);
-            if (e != cudaSuccess) {
-                s->peerBase[g] = NULL;
-                return ehyb_fail(EHYB_ERR_PEER, "cudaIpcOpenMemHandle(rank %d): %s", g, cudaGetErrorString(e));
+            if (localBase) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(B[g].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return ehyb_fail(EHYB_ERR_PEER, "cudaDeviceEnablePeerAccess(%d): %s", B[g].device, cudaGetErrorString(e));
+                cudaGetLastError();
+                s->peerBase[g] = localBase[g];
+            } else {
+                cudaError_t e = cudaIpcOpenMemHandle(&s->peerBase[g], B[g].handle, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    s->peerBase[g] = NULL;
+                    return ehyb_fail(EHYB_ERR_PEER, "cudaIpcOpenMemHandle(rank %d): %s", g, cudaGetErrorString(e));
+                }
             }
             unsigned char *base = (unsigned char *)s->peerBase[g];
             for (int64_t k = 0; k < sc; ++k)
@@ -1306,6 +1315,44 @@ extern "C" int ehyb_mg_p2p_connect(ehyb_mg_session *s, const void *blobs, const 
     if (rc) return rc;
     s->connected = 1;
     return EHYB_OK;
+}
+
+extern "C" int ehyb_mg_p2p_connect(ehyb_mg_session *s, const void *blobs, const int64_t *recvOffsetOnPeer)
+{
+    if (!s || !blobs || !recvOffsetOnPeer || s->exchange != EHYB_MG_P2P) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_connect: bad argument");
+    return p2p_connect_impl(s, (const P2PBlob *)blobs, recvOffsetOnPeer, NULL);
+}
+
+/* All the ranks in ONE process (one host thread per GPU, or one thread driving them all): the
+ * sessions reach each other's halo buffers through plain peer access (cudaDeviceEnablePeerAccess)
+ * instead of CUDA IPC mappings, which do not work inside the exporting process.  sessions[r] =
+ * rank r's session (created with ehyb_mg_session_create_p2p on its own device).  This is what the
+ * C driver uses (bin/spmv.out -G N): no launcher, no Python, no torch.distributed. */
+extern "C" int ehyb_mg_p2p_connect_local(ehyb_mg_session *const *sessions, int nranks)
+{
+    if (!sessions || nranks <= 0 || nranks > 32) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_connect_local: bad argument");
+    P2PBlob *B = (P2PBlob *)calloc((size_t)nranks, sizeof(P2PBlob));
+    void **base = (void **)calloc((size_t)nranks, sizeof(void *));
+    int64_t *off = (int64_t *)calloc((size_t)nranks, sizeof(int64_t));
+    if (!B || !base || !off) { free(B); free(base); free(off); return ehyb_fail(EHYB_ERR_NOMEM, "p2p connect: out of memory"); }
+    int rc = EHYB_OK;
+    for (int g = 0; g < nranks && rc == EHYB_OK; ++g) {
+        ehyb_mg_session *s = sessions[g];
+        if (!s || s->exchange != EHYB_MG_P2P || s->nranks != nranks || s->rank != g) { rc = ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_p2p_connect_local: sessions[%d] is not rank %d of %d (peer-memory exchange)", g, g, nranks); break; }
+        B[g].haloStride = (int64_t)s->haloStride; B[g].flagsOffset = (int64_t)(2 * s->haloStride); B[g].nHalo = s->nHalo;
+        B[g].device = s->h->device; B[g].rank = g; B[g].pushCtas = s->pushCtas;
+        base[g] = s->shared;
+    }
+    for (int r = 0; r < nranks && rc == EHYB_OK; ++r) {
+        /* rank r's entries start in rank g's halo list behind those of the ranks below r */
+        for (int g = 0; g < nranks; ++g) {
+            off[g] = 0;
+            for (int q = 0; q < r; ++q) off[g] += sessions[g]->recvCount[q];
+        }
+        rc = p2p_connect_impl(sessions[r], B, off, base);
+    }
+    free(B); free(base); free(off);
+    return rc;
 }
 
 extern "C" int ehyb_mg_status(ehyb_mg_session *s, int *timed_out)

@@ -111,6 +111,23 @@ int ehyb_partition_graph(uint32_t n, const uint32_t *xadj, const uint32_t *adjnc
     return EHYB_OK;
 }
 
+/* The unweighted call through the helper process even when an in-process partitioner is installed:
+ * hierpart.c runs several of these at the same time, and the in-process library call is not
+ * re-entrant. */
+int ehyb_partition_graph_process(uint32_t n, const uint32_t *xadj, const uint32_t *adjncy, uint32_t nparts, uint32_t *where)
+{
+    if (!xadj || !adjncy || !where || nparts == 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_partition_graph: bad argument");
+    if (nparts == 1) {
+        memset(where, 0, (size_t)n * sizeof(uint32_t));
+        return EHYB_OK;
+    }
+    int rc = helper_partition(n, xadj, adjncy, NULL, NULL, nparts, 1, 1.001f, where);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; ++i)
+        if (where[i] >= nparts) return ehyb_fail(EHYB_ERR_PARTITION, "partitioner returned part %u >= %u", where[i], nparts);
+    return EHYB_OK;
+}
+
 /* The same call with vertex and edge weights: the level-1 partition of a COARSENED graph (bricks
  * of a grid, grid.c) into one block per GPU.  Always through the helper binary. */
 int ehyb_partition_graph_weighted(uint32_t n, const uint32_t *xadj, const uint32_t *adjncy, const int32_t *vwgt, const int32_t *adjwgt,

@@ -221,7 +221,11 @@ int ehyb_reorder(matrixCOO *m, int symmetric)
     gettimeofday(&t0, NULL);
     printf("start k-way partition\n"); /* reordering.c:279 */
     /* 1 thread on the symmetric path (reordering.c:274), 6 on the other (:120) */
-    rc = ehyb_partition_graph((uint32_t)m->dimension, xadj, adj, (uint32_t)m->nParts, symmetric ? 1u : 6u, where);
+    const int pieces = ehyb_get_partition_pieces();
+    if (pieces > 1) /* deterministic and parallel: hierpart.c (also on the general path: no threaded mt-metis call) */
+        rc = ehyb_partition_graph_hier((uint32_t)m->dimension, xadj, adj, (uint32_t)m->nParts, pieces, where);
+    else
+        rc = ehyb_partition_graph((uint32_t)m->dimension, xadj, adj, (uint32_t)m->nParts, symmetric ? 1u : 6u, where);
     free(xadj);
     free(adj);
     if (rc == EHYB_OK) {

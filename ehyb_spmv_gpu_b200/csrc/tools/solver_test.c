@@ -13,6 +13,9 @@
  * a .mtx file (permutation, x, golden y, tuned layout) is written to <file>.ehyb and loaded by
  * the next run with the same file and partition parameters, which then skips the reader,
  * mt-metis, the reorder and the format build; -C disables it, the stage times are printed.
+ * -G <gpus> with -g st27:NX:NY:NZ runs the sharded stencil (BASELINE.json config 5) on several GPUs
+ * from this one process: mg_driver.c.  -T <pieces> sets the deterministic parallel partition stage
+ * (hierpart.c; default min(8, cores), 0 = the reference's single mt-metis call).
  */
 #include <math.h>
 #include <stdio.h>
@@ -89,20 +92,25 @@ static int finish(int n, const double *yReorder, const int *reorderList, const d
  * partitioning then costs (config 3: 428 us vs 403 us): those keep the staged plan. */
 static int plan_kernel_for(int64_t n, int64_t nnz) { return nnz <= 40 * n ? EHYB_KERNEL_PERSISTENT : EHYB_KERNEL_STAGED; }
 
+/* mg_driver.c */
+int ehyb_driver_multi_gpu(int G, const char *gen, const char *brickSpec, int iters);
+
 static void usage(void)
 {
     printf("usage: spmv.out -i <iterations> (-m <name> | -M <file.mtx> | -g lap2d:NX:NY | -g st27:NX:NY:NZ | -g elas:NX:NY:NZ)\n"
            "       [-R] reference partition heuristic   [-P <parts> -W <window> -K <ctas per partition>] override\n"
-           "       [-C] do not read or write the binary cache <file>.ehyb\n");
+           "       [-C] do not read or write the binary cache <file>.ehyb\n"
+           "       [-T <pieces>] partition stage: pieces partitioned at the same time, deterministic (0 = one mt-metis call)\n"
+           "       [-G <gpus> [-B BXxBYxBZ]] with -g st27:NX:NY:NZ: the stencil sharded over several GPUs of this box\n");
 }
 
 int main(int argc, char *argv[])
 {
-    int MAXIter = 0, oc, useRefPlan = 0, oP = 0, oW = 0, oK = 0, useCache = 1;
-    char fileName[1024] = "", gen[256] = "";
+    int MAXIter = 0, oc, useRefPlan = 0, oP = 0, oW = 0, oK = 0, useCache = 1, gpus = 0, pieces = -1;
+    char fileName[1024] = "", gen[256] = "", brick[64] = "";
     cb_s cb;
     init_cb(&cb);
-    while ((oc = getopt(argc, argv, "m:M:g:i:r:t:f:p:RP:W:K:C")) != -1) {
+    while ((oc = getopt(argc, argv, "m:M:g:i:r:t:f:p:RP:W:K:CG:B:T:")) != -1) {
         switch (oc) {
         case 'm':
             snprintf(fileName, sizeof fileName, "./read/%s.mtx", optarg); /* solver_test.c:284 */
@@ -119,6 +127,9 @@ int main(int argc, char *argv[])
         case 'W': oW = atoi(optarg); break;
         case 'K': oK = atoi(optarg); break;
         case 'C': useCache = 0; break;
+        case 'G': gpus = atoi(optarg); break;
+        case 'B': snprintf(brick, sizeof brick, "%s", optarg); break;
+        case 'T': pieces = atoi(optarg); break;
         case '?': printf("unrecongnized option\n"); break;
         default: printf("option/arguments error!\n"); return 0;
         }
@@ -133,6 +144,12 @@ int main(int argc, char *argv[])
         return 0;
     }
     ehyb_set_partitioner(mtmetis_direct, NULL);
+    if (gpus > 0) return ehyb_driver_multi_gpu(gpus, gen, brick, MAXIter);
+    {   /* partition stage: deterministic and parallel unless -T 0 / the reference plan asks for the reference's call */
+        long cores = sysconf(_SC_NPROCESSORS_ONLN);
+        if (pieces < 0) pieces = useRefPlan ? 0 : (cores >= 8 ? 8 : (int)cores);
+        ehyb_set_partition_pieces(pieces);
+    }
     if (getenv("EHYB_NO_CACHE")) useCache = 0;
     ehyb_device_info dev;
     int haveDev = ehyb_device_query(0, &dev) == EHYB_OK;

@@ -110,6 +110,18 @@ void ehyb_set_partitioner(ehyb_partition_fn fn, void *user);
 int ehyb_partition_graph(uint32_t nvtxs, const uint32_t *xadj, const uint32_t *adjncy,
                          uint32_t nparts, uint32_t nthreads, uint32_t *where);
 
+/* Deterministic and parallel partition stage (csrc/host/hierpart.c): the rows are
+ * contracted in blocks, ONE single-threaded mt-metis call cuts the block graph into `pieces`
+ * pieces, and every piece is partitioned on its own by a single-threaded mt-metis process, all at
+ * once.  Same partition vector on every run (the reference's threaded call, reordering.c:120, is
+ * not), wall time of the largest piece.  pieces <= 1 or n < 65536: the reference's single call.
+ * ehyb_set_partition_pieces(T) makes ehyb_reorder / matrixReorder* use it ($EHYB_PARTITION_PIECES
+ * overrides; 0 = the reference's call, the default). */
+int ehyb_partition_graph_hier(uint32_t nvtxs, const uint32_t *xadj, const uint32_t *adjncy, uint32_t nparts, int pieces,
+                              uint32_t *where);
+void ehyb_set_partition_pieces(int pieces);
+int ehyb_get_partition_pieces(void);
+
 /* Everything of matrixReorder after the mt-metis call (reordering.c:299-377), for a given
  * partition vector partVec[old row] in [0, nParts).  Same in/out contract as matrixReorder. */
 int ehyb_reorder_with_partition(matrixCOO *m, const uint32_t *partVec);
@@ -376,6 +388,9 @@ int ehyb_mg_p2p_supported(int device, int nranks, int *supported);
 int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int nranks, int device, ehyb_mg_session **out);
 int ehyb_mg_p2p_export(ehyb_mg_session *s, void *blob);
 int ehyb_mg_p2p_connect(ehyb_mg_session *s, const void *blobs, const int64_t *recvOffsetOnPeer);
+/* The same connection when all the ranks live in ONE process (the C driver, bin/spmv.out -G N: one
+ * host thread per GPU): plain peer access instead of CUDA IPC; sessions[r] = rank r's session. */
+int ehyb_mg_p2p_connect_local(ehyb_mg_session *const *sessions, int nranks);
 /* Set when a wait on a neighbour ran into the time limit ($EHYB_P2P_TIMEOUT_MS, default 10 s)
  * since the session was created: the products since then are not valid. */
 int ehyb_mg_status(ehyb_mg_session *s, int *timed_out);

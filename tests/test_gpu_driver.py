@@ -51,3 +51,25 @@ def test_driver_from_mtx_and_cache(tmp_path):
     cache.write_bytes(raw)
     rc, out5 = _run("-i", "5", "-M", str(mtx), "-P", "40", "-W", "2048", "-K", "4")
     assert rc == 0 and "cache not used" in out5 and "start k-way partition" in out5, out5[-2000:]
+
+
+@pytest.mark.parametrize("gpus", [1, 2, 4])
+def test_driver_multi_gpu_mode(gpus):
+    """./spmv.out -G <gpus> -g st27:NX:NY:NZ: BASELINE.json config 5's pipeline from the C driver alone -
+    one process, one host thread per GPU, level 1 by mt-metis on the brick graph, streamed format build,
+    halo exchange inside the persistent kernel over plain peer access; per-GPU lines, the reference's
+    `iter is ...` line for the whole job, exit code from the accuracy gate over every row."""
+    import torch
+    if not (ROOT / "bin" / "spmv.out").exists():
+        pytest.skip("bin/spmv.out not built")
+    if torch.cuda.device_count() < gpus:
+        pytest.skip("needs %d GPUs" % gpus)
+    dims = (96, 80, 64)
+    rc, out = _run("-G", str(gpus), "-g", "st27:%d:%d:%d" % dims, "-B", "16x16x8", "-i", "20")
+    assert rc == 0, out[-3000:]
+    n = dims[0] * dims[1] * dims[2]
+    assert "0 of %d rows fail" % n in out, out[-3000:]
+    for g in range(gpus):
+        assert "GPU %d: " % g in out
+    assert "iter is 20, time is" in out and "EHYB-B200 multi-GPU: %d GPUs" % gpus in out
+    assert out.count("gate 0 rows fail") == gpus
