@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""BASELINE.json config 4 (R-MAT) timing of the overflow paths on one layout: the CSR-like stream with and
-without hub columns, the COO list with atomics, cuSPARSE CSR on the same matrix.
-  python scripts/rmat_variants.py --scale 24 [--iters 30]"""
+"""BASELINE.json config 4 (R-MAT) timing of the overflow paths on one layout: the tile-packed CSR-like
+stream (tile shapes, staging depth, hub columns), the COO list with atomics, cuSPARSE CSR on the same matrix.
+  python scripts/rmat_variants.py --scale 24 [--iters 30] [--variants default,coo] [--no-cusparse]"""
 import argparse, ctypes as C, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,6 +12,8 @@ from oracle import oracle as O
 ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=int, default=22)
 ap.add_argument("--iters", type=int, default=30)
+ap.add_argument("--variants", default="")
+ap.add_argument("--no-cusparse", action="store_true")
 a = ap.parse_args()
 t = time.time()
 n, fi, fj, fv = api.gen_rmat(a.scale, 16, seed=1, add_diagonal=False)
@@ -29,9 +31,18 @@ orc = O.Oracle()
 arr = m.arrays()
 y_ref = orc.csr_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
 absAx = orc.csr_abs_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
-for name, env in (("stream + 16384 hubs", {}), ("stream + 8192 hubs", {"EHYB_OVF_HUBS": "8192"}), ("stream, no hubs", {"EHYB_OVF_HUBS": "0"}),
-                  ("COO list + atomics (round 1)", {"EHYB_OVF_STREAM": "0"})):
-    for k in ("EHYB_OVF_HUBS", "EHYB_OVF_STREAM"):
+VARIANTS = (("default", "stream: 128-entry tiles x 32 warps, 3 slots, 8192 hubs", {}),
+            ("tg8", "stream: 256-entry tiles x 16 warps, 3 slots", {"EHYB_OVF_TG": "8"}),
+            ("slots2", "stream: 128-entry tiles, 2 slots", {"EHYB_OVF_SLOTS": "2"}),
+            ("slots4", "stream: 128-entry tiles, 4 slots, 2048 hubs", {"EHYB_OVF_SLOTS": "4", "EHYB_OVF_HUBS": "2048"}),
+            ("hubs4k", "stream: 4096 hubs", {"EHYB_OVF_HUBS": "4096"}),
+            ("nohubs", "stream: no hubs", {"EHYB_OVF_HUBS": "0"}),
+            ("coo", "COO list + atomics (round 1)", {"EHYB_OVF_STREAM": "0"}))
+want = [w for w in a.variants.split(",") if w]
+for key, name, env in VARIANTS:
+    if want and key not in want:
+        continue
+    for k in ("EHYB_OVF_HUBS", "EHYB_OVF_STREAM", "EHYB_OVF_TG", "EHYB_OVF_SLOTS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     s = api.Session(lay)
@@ -42,10 +53,10 @@ for name, env in (("stream + 16384 hubs", {}), ("stream + 8192 hubs", {"EHYB_OVF
     ms = s.time_spmv(5, a.iters)
     ms = ms[0] if isinstance(ms, tuple) else ms
     per = ms / a.iters
-    print(f"{name:32s} {per*1e3:8.1f} us  {2*st['nnz']/(per*1e6):7.1f} GFLOP/s  {st['algBytes']/(per*1e6):7.1f} GB/s alg  gate fails {bad}  bit-reproducible {same}  kernel {s.kernel_name()}", flush=True)
+    print(f"{name:52s} {per*1e3:8.1f} us  {2*st['nnz']/(per*1e6):7.1f} GFLOP/s  {st['algBytes']/(per*1e6):7.1f} GB/s alg  gate fails {bad}  bit-reproducible {same}  kernel {s.kernel_name()}", flush=True)
     s.free()
 cus = os.path.join(ROOT, "ehyb_spmv_gpu_b200", "lib", "libehyb_cusparse.so")
-if os.path.exists(cus):
+if os.path.exists(cus) and not a.no_cusparse:
     lib = C.CDLL(cus)
     for alg in (1, 2):
         us = C.c_float(); yc = np.empty(n)
