@@ -156,6 +156,39 @@ def build_matrix(grid, x=None):
     return m, lay, x, pl, time.time() - t0
 
 
+def config1_l2_row(device):
+    """BASELINE.json configs[0] (5-point 1024^2: 20 MB of matrix data, L2-resident) with a warm and with
+    a cold L2 (SURVEY.md 8d "Timing"); reported next to the headline, outside its timed region."""
+    from ehyb_spmv_gpu_b200 import api
+    try:
+        n, li, lj, lv = api.gen_lower(api.GEN_LAPLACE2D, 1024, 1024, 1)
+        x = api.x_reference(n)
+        m = api.CooMatrix.from_lower(n, li, lj, lv, x)
+        pl = api.plan(n, api.device_query(device), kernel=api.KERNEL_PERSISTENT)
+        m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
+        m.reorder()
+        lay = api.Layout(m)
+        st = lay.stats()
+        s = api.Session(lay, device=device)
+        xr = m.vector_reorder(x)
+        s.set_x(xr)
+        iters = 200
+        warm = s.time_spmv(10, iters) / iters * 1e3
+        cold = s.time_spmv_flushed(3, 50) / 50 * 1e3
+        ok = bool(np.all(np.abs(m.vector_recover(s.get_y()) - m.y_golden) <= 1e-12 * np.maximum(np.abs(m.y_golden), 1.0)))
+        row = {"workload": "2D 5-point Laplacian 1024^2 (n %d, nnz %d), BASELINE.json configs[0]" % (n, st["nnz"]),
+               "kernel": s.kernel_name(), "format_bytes": st["formatBytes"],
+               "us_per_product_l2_resident": round(warm, 2), "GBs_algorithmic_l2_resident": round(st["algBytes"] / (warm * 1e3), 1),
+               "us_per_product_l2_flushed": round(cold, 2), "GBs_algorithmic_l2_flushed": round(st["algBytes"] / (cold * 1e3), 1),
+               "what": "l2_resident: %d back-to-back products (programmatic dependent launch); l2_flushed: 512 MB of scratch "
+                       "overwritten before every product, each product timed by its own event pair (plain launches)" % iters,
+               "result_inside_gate": ok}
+        s.free(); lay.free(); m.free()
+        return row
+    except Exception as e:  # a comparison row must not take the bench line down
+        return {"error": str(e)[:200]}
+
+
 def gpu_comparisons(m, xr, y_ref, absAx):
     """Other GPU implementations of the same product on the same device, outside the timed region
     (reported rows): cuSPARSE generic-API CSR SpMV through spmvGeneric's library
@@ -331,6 +364,10 @@ def run_ours(args):
     comparisons = gpu_comparisons(m, xr, y_cpu, absAx)
     if GRID == (128, 128, 128) and os.environ.get("EHYB_BENCH_REFERENCE_GPU", "1") != "0":
         comparisons["reference_kernel_sm100a"] = reference_gpu_row()
+
+    if GRID == (128, 128, 128) and os.environ.get("EHYB_BENCH_CONFIG1", "1") != "0":
+        with stdout_to_stderr():
+            comparisons["config1_l2"] = config1_l2_row(local)
 
     peaks, peak_src = measured_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))

@@ -121,7 +121,7 @@ EXPORTS = [
     "ehyb_layout_build", "ehyb_layout_build_csr", "ehyb_layout_get", "ehyb_layout_to_reference",
     "ehyb_layout_free", "ehyb_layout_save", "ehyb_layout_load", "ehyb_cache_save", "ehyb_cache_load",
     "ehyb_session_opts_default", "ehyb_upload", "ehyb_spmv", "ehyb_spmv_host",
-    "ehyb_spmv_host_batch", "ehyb_session_vectors", "ehyb_set_x", "ehyb_get_y", "ehyb_time_spmv",
+    "ehyb_spmv_host_batch", "ehyb_session_vectors", "ehyb_set_x", "ehyb_get_y", "ehyb_time_spmv", "ehyb_time_spmv_flushed",
     "ehyb_launches_per_spmv", "ehyb_pcg_opts_default", "ehyb_pcg_solve", "ehyb_session_size", "ehyb_session_kernel", "ehyb_trace_read", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",
     "ehyb_gen_lower", "ehyb_coo_from_lower", "ehyb_coo_from_general", "ehyb_gen_rmat", "ehyb_x_reference",
     "ehyb_read_mtx", "ehyb_write_mtx", "ehyb_coo_free",
@@ -129,7 +129,8 @@ EXPORTS = [
     "ehyb_mg_local_finish", "ehyb_mg_local_view", "ehyb_mg_local_free", "ehyb_mg_unique_id",
     "ehyb_mg_session_create", "ehyb_mg_session_handle", "ehyb_mg_spmv", "ehyb_mg_time_spmv", "ehyb_mg_spmv_host_batch",
     "ehyb_mg_p2p_supported", "ehyb_mg_session_create_p2p", "ehyb_mg_p2p_export", "ehyb_mg_p2p_connect", "ehyb_mg_p2p_connect_local",
-    "ehyb_mg_status", "ehyb_mg_launches_per_spmv",
+    "ehyb_mg_status", "ehyb_mg_launches_per_spmv", "ehyb_mg_allreduce_sum", "ehyb_mg_spmv_dot_supported", "ehyb_mg_spmv_dot",
+    "ehyb_mg_pcg_solve", "ehyb_mg_session_ranks", "ehyb_spmv_dot_supported", "ehyb_spmv_dot", "ehyb_spmv_dot_host", "ehyb_session_device",
     "ehyb_mg_session_free", "ehyb_gen_stencil27_rows", "ehyb_host_alloc_pinned", "ehyb_host_free_pinned",
     "ehyb_session_info",
     "ehyb_layout_builder_begin", "ehyb_layout_builder_add", "ehyb_layout_builder_finish", "ehyb_layout_builder_abort",

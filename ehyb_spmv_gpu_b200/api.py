@@ -394,6 +394,23 @@ class Session:
               "ehyb_time_spmv")
         return (ms.value, kms.value) if kernel_only else ms.value
 
+    def spmv_dot_supported(self) -> bool:
+        return bool(self.lib.ehyb_spmv_dot_supported(self.h))
+
+    def spmv_dot_host(self, x):
+        """ehyb_spmv_dot_host: (y, x . y) with the dot product computed inside the product kernel."""
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.empty(self.n if hasattr(self, "n") else len(x), np.float64)
+        d = C.c_double()
+        check(self.lib, self.lib.ehyb_spmv_dot_host(self.h, x.ctypes.data_as(L.c_dbl_p), y.ctypes.data_as(L.c_dbl_p), C.byref(d)), "ehyb_spmv_dot_host")
+        return y, d.value
+
+    def time_spmv_flushed(self, warmup: int, iters: int, flush_bytes: int = 512 << 20) -> float:
+        """Sum (ms) of `iters` products each timed alone behind an L2 flush (cold matrix, x and y)."""
+        ms = C.c_float()
+        check(self.lib, self.lib.ehyb_time_spmv_flushed(self.h, warmup, iters, C.c_size_t(flush_bytes), C.byref(ms)), "ehyb_time_spmv_flushed")
+        return ms.value
+
     def pcg_solve(self, b, diag=None, max_iters=1000, rtol=1e-10, check_every=8):
         """ehyb_pcg_solve: A x = b (permuted numbering), Jacobi-preconditioned when diag is given.
         Returns (x, dict(iters, converged, rel_residual, true_rel_residual, ms))."""

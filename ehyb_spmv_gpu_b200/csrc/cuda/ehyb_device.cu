@@ -33,6 +33,8 @@ using namespace ehyb;
             return ehyb_fail(EHYB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+constexpr int kMaxOvfBlocks = 64;
+
 struct ehyb_handle {
     int device;
     cudaStream_t stream, h2d, d2h;
@@ -62,11 +64,14 @@ struct ehyb_handle {
      * wait on a neighbour ran into the time limit (sticky); NULL for single-GPU sessions */
     volatile uint32_t *peerStatus_h;
     /* large overflow lists: the CSR-like stream format (host/ovfstream.c) instead of the COO list */
-    int ovfStream, ovfHubs, ovfGroups, ovfTiles;
-    uint32_t *ovfColEnc;
-    uint2 *ovfGrp;
-    int32_t *ovfRowOfSeg, *ovfHubCols, *ovfCarryRow;
-    double *ovfCarryVal;
+    int ovfStream, ovfHubs, ovfTileGroups, ovfSlots, ovfBlocks; /* ovfHubs: the most any block has */
+    struct OvfBlock { /* one column block = one stream, launched in block order */
+        unsigned char *tiles;
+        int32_t *rowOfSeg, *hubCols, *runs;
+        double *carryVal;
+        int nHub, nTiles;
+        int64_t nRuns, nRunsShort;
+    } ovfBlock[kMaxOvfBlocks];
     int64_t ovfDeviceBytes, ovfHubRefs;
     int forcePeerBuild; /* development ($EHYB_FORCE_PEER_BUILD): single-GPU sessions run the multi-GPU build of the kernel */
 };
@@ -146,15 +151,21 @@ static main_kernel_t staged_kernel(int threads, bool peer)
 }
 
 /* persistent, double-buffered variant (ehyb_persistent_kernel): 4-column chunks only */
-static main_kernel_t persistent_kernel(int threads, bool peer, int slots)
+static main_kernel_t persistent_kernel(int threads, bool peer, int slots, bool dot = false)
 {
     /* register budgets: 128 at <= 512 threads, 112 at <= 576, 96 at <= 640, 80 at 768.  The
      * multi-GPU build keeps a few more values live (calls into the exchange code): it spills at 80
      * registers, so peer sessions run at most kPeerPersistWarps = 20 warps.  Three staging slots
-     * per warp exist for the 512-thread builds only (16 warps x 3 x 2.5 KB = 120 KB).
+     * per warp exist for the 512-thread builds only (16 warps x 3 x 2.5 KB = 120 KB); the builds
+     * with the fused dot product (ehyb_spmv_dot) have two slots.
      * $EHYB_PERSIST_BUILD (experiments) forces a build with a larger thread bound. */
     int b = env_int_early("EHYB_PERSIST_BUILD", 0);
     if (b < threads) b = threads;
+    if (dot) {
+        if (peer) return b <= 512 ? ehyb_persistent_kernel<512, 4, true, 2, true> : b <= 576 ? ehyb_persistent_kernel<576, 4, true, 2, true> : ehyb_persistent_kernel<640, 4, true, 2, true>;
+        return b <= 512 ? ehyb_persistent_kernel<512, 4, false, 2, true> : b <= 576 ? ehyb_persistent_kernel<576, 4, false, 2, true>
+               : b <= 640 ? ehyb_persistent_kernel<640, 4, false, 2, true> : ehyb_persistent_kernel<768, 4, false, 2, true>;
+    }
     if (slots == 3) return peer ? ehyb_persistent_kernel<512, 4, true, 3> : ehyb_persistent_kernel<512, 4, false, 3>;
     if (peer) return b <= 512 ? ehyb_persistent_kernel<512, 4, true, 2> : b <= 576 ? ehyb_persistent_kernel<576, 4, true, 2> : ehyb_persistent_kernel<640, 4, true, 2>;
     return b <= 512 ? ehyb_persistent_kernel<512, 4, false, 2> : b <= 576 ? ehyb_persistent_kernel<576, 4, false, 2>
@@ -266,8 +277,12 @@ extern "C" void ehyb_free(ehyb_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     cudaFree(h->parts); cudaFree(h->slices); cudaFree(h->blob);
-    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal); cudaFree(h->ovfColEnc); cudaFree(h->ovfGrp); cudaFree(h->ovfRowOfSeg);
-    cudaFree(h->ovfHubCols); cudaFree(h->ovfCarryRow); cudaFree(h->ovfCarryVal); cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->ctaTab); cudaFree(h->ctaStart); cudaFree(h->trace);
+    cudaFree(h->ovfRow); cudaFree(h->ovfCol); cudaFree(h->ovfVal);
+    for (int b = 0; b < kMaxOvfBlocks; ++b) {
+        cudaFree(h->ovfBlock[b].tiles); cudaFree(h->ovfBlock[b].rowOfSeg); cudaFree(h->ovfBlock[b].hubCols);
+        cudaFree(h->ovfBlock[b].runs); cudaFree(h->ovfBlock[b].carryVal);
+    }
+    cudaFree(h->cacheCols); cudaFree(h->order); cudaFree(h->ctaTab); cudaFree(h->ctaStart); cudaFree(h->trace);
     cudaFree(h->x); cudaFree(h->y);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->xb[i]); cudaFree(h->yb[i]);
@@ -391,38 +406,68 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
     if (v->cacheTotal) CU(cudaMemcpyAsync(h->cacheCols, v->cacheCols, sizeof(int32_t) * (size_t)v->cacheTotal, cudaMemcpyHostToDevice, h->stream));
     /* Overflow list.  Short lists (what the slices could not hold, halo entries) stay a COO reduced
      * with one atomic per row segment; long ones - >= $EHYB_OVF_STREAM_MIN entries, default 2^20, or
-     * any length with $EHYB_DETERMINISTIC=1 - become the CSR-like stream of host/ovfstream.c: 12.25
-     * instead of 16 bytes per entry, hub columns in shared memory, no atomics (bit-reproducible y).
-     * Not for peer-memory sessions: there the overflow kernel waits for the neighbours' flags. */
+     * any length with $EHYB_DETERMINISTIC=1 - become the tile-packed CSR-like stream of
+     * host/ovfstream.c: 12.4 instead of 16 bytes per entry, staged by bulk copies, hub columns in
+     * shared memory, no atomics (bit-reproducible y).  Not for peer-memory sessions: there the
+     * overflow kernel waits for the neighbours' flags.
+     * Shape: 128-entry tiles x 32 warps (64 registers): 4 096 gathers per SM in flight;
+     * $EHYB_OVF_SLOTS staging slots per warp (default 2) and $EHYB_OVF_HUBS hub columns in shared
+     * memory (default 0).  Both defaults are the SMALLEST shared-memory footprint on purpose: what is
+     * not shared memory is L1, and on a power-law matrix the L1 hits of the hot columns are worth more
+     * than a third slot or an explicit hub cache (R-MAT 24, per product: 2 slots / no hubs 2 011 us,
+     * 2 slots + 8 192 hubs 2 247, 3 slots + 8 192 hubs 3 447; profiles/r2_notes.md). */
     h->ovfStream = 0;
     if (h->nOvf > 0 && !peerSession &&
         (env_int("EHYB_DETERMINISTIC", 0) || h->nOvf >= (int64_t)env_int("EHYB_OVF_STREAM_MIN", 1 << 20)) && env_int("EHYB_OVF_STREAM", 1)) {
-        ehyb_ovfstream st;
-        int hubCap = env_int("EHYB_OVF_HUBS", 16384);
-        const int hubMax = (int)((prop.sharedMemPerBlockOptin - 1024) / sizeof(double));
+        const int tg = 4;
+        int slots = env_int("EHYB_OVF_SLOTS", 2);
+        if (slots < 2) slots = 2;
+        if (slots > kStreamMaxSlots) slots = kStreamMaxSlots;
+        const int warps = tg == 8 ? 16 : 32;
+        const size_t staging = (size_t)kStreamHeader + (size_t)warps * slots * EHYB_OVF_TILE_BYTES(tg);
+        int hubCap = env_int("EHYB_OVF_HUBS", 0);
+        const int hubMax = staging < prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - staging) / sizeof(double)) : 0;
         if (hubCap > hubMax) hubCap = hubMax;
         if (hubCap < 0) hubCap = 0;
-        int rcS = ehyb_ovfstream_build(h->nOvf, v->ovfRow, v->ovfCol, h->ncols, hubCap, &st);
+        /* column blocks ($EHYB_OVF_COLBLOCKS, default 1 = off): the list cut by column range and
+         * streamed block after block, so that a launch's gathers fall into one slice of x.  Measured
+         * on R-MAT 24 (x = 134 MB): 2 011 us with 1 block, 2 134 / 2 349 / 2 522 / 2 735 with 2 / 4 /
+         * 8 / 16 - the gathers already hit L2 (86 %, ncu) and are bound by the L1TEX data pipe (one
+         * wavefront per lane), so blocking only adds a pass over y per block.  Kept as a switch. */
+        int nBlocks = env_int("EHYB_OVF_COLBLOCKS", 1);
+        if (nBlocks > kMaxOvfBlocks) nBlocks = kMaxOvfBlocks;
+        if (nBlocks < 1) nBlocks = 1;
+        const int64_t blockCols = (h->ncols + nBlocks - 1) / nBlocks;
+        ehyb_ovfstream st[kMaxOvfBlocks];
+        int rcS = ehyb_ovfstream_build_blocked(h->nOvf, v->ovfRow, v->ovfCol, v->ovfVal, h->ncols, hubCap, tg, nBlocks, blockCols, st);
         if (rcS) return rcS;
         h->ovfStream = 1;
-        h->ovfHubs = st.nHub; h->ovfGroups = (int)st.nGroups; h->ovfDeviceBytes = st.deviceBytes; h->ovfHubRefs = st.hubRefs;
-        h->ovfTiles = (int)((st.nGroups + kStreamTileGroups - 1) / kStreamTileGroups);
-        cudaError_t e = cudaMalloc(&h->ovfVal, sizeof(double) * (size_t)h->nOvf);
-        if (e == cudaSuccess) e = cudaMalloc(&h->ovfColEnc, sizeof(uint32_t) * (size_t)h->nOvf);
-        if (e == cudaSuccess) e = cudaMalloc(&h->ovfGrp, sizeof(uint2) * (size_t)st.nGroups);
-        if (e == cudaSuccess) e = cudaMalloc(&h->ovfRowOfSeg, sizeof(int32_t) * (size_t)st.nSeg);
-        if (e == cudaSuccess) e = cudaMalloc(&h->ovfHubCols, sizeof(int32_t) * (size_t)(st.nHub ? st.nHub : 1));
-        if (e == cudaSuccess) e = cudaMalloc(&h->ovfCarryRow, sizeof(int32_t) * 2 * (size_t)h->ovfTiles);
-        if (e == cudaSuccess) e = cudaMalloc(&h->ovfCarryVal, sizeof(double) * 2 * (size_t)h->ovfTiles);
-        if (e == cudaSuccess) e = cudaMemcpy(h->ovfVal, v->ovfVal, sizeof(double) * (size_t)h->nOvf, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(h->ovfColEnc, st.col, sizeof(uint32_t) * (size_t)h->nOvf, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(h->ovfGrp, st.grp, sizeof(uint2) * (size_t)st.nGroups, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(h->ovfRowOfSeg, st.rowOfSeg, sizeof(int32_t) * (size_t)st.nSeg, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess && st.nHub) e = cudaMemcpy(h->ovfHubCols, st.hubCols, sizeof(int32_t) * (size_t)st.nHub, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemset(h->ovfCarryRow, 0xff, sizeof(int32_t) * 2 * (size_t)h->ovfTiles);
-        ehyb_ovfstream_free(&st);
+        h->ovfTileGroups = tg; h->ovfSlots = slots; h->ovfBlocks = nBlocks;
+        h->ovfHubs = 0; h->ovfDeviceBytes = 0; h->ovfHubRefs = 0;
+        cudaError_t e = cudaSuccess;
+        for (int b = 0; b < nBlocks && e == cudaSuccess; ++b) {
+            ehyb_handle::OvfBlock &ob = h->ovfBlock[b];
+            ob.nTiles = (int)st[b].nTiles; ob.nHub = st[b].nHub;
+            if (st[b].count == 0) continue;
+            if (st[b].nHub > h->ovfHubs) h->ovfHubs = st[b].nHub;
+            h->ovfDeviceBytes += st[b].deviceBytes; h->ovfHubRefs += st[b].hubRefs;
+            const size_t blobBytes = (size_t)st[b].nTiles * (size_t)st[b].tileBytes;
+            e = cudaMalloc(&ob.tiles, blobBytes);
+            if (e == cudaSuccess) e = cudaMalloc(&ob.rowOfSeg, sizeof(int32_t) * (size_t)st[b].nSeg);
+            if (e == cudaSuccess) e = cudaMalloc(&ob.hubCols, sizeof(int32_t) * (size_t)(st[b].nHub ? st[b].nHub : 1));
+            ob.nRuns = st[b].nRuns; ob.nRunsShort = st[b].nRunsShort;
+            if (e == cudaSuccess) e = cudaMalloc(&ob.runs, sizeof(int32_t) * 3 * (size_t)(st[b].nRuns ? st[b].nRuns : 1));
+            if (e == cudaSuccess) e = cudaMalloc(&ob.carryVal, sizeof(double) * 2 * (size_t)ob.nTiles);
+            if (e == cudaSuccess) e = cudaMemcpy(ob.tiles, st[b].tiles, blobBytes, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(ob.rowOfSeg, st[b].rowOfSeg, sizeof(int32_t) * (size_t)st[b].nSeg, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess && st[b].nHub) e = cudaMemcpy(ob.hubCols, st[b].hubCols, sizeof(int32_t) * (size_t)st[b].nHub, cudaMemcpyHostToDevice);
+            /* the rows of the carry slots are fixed by the data (runs); the sums of unused slots stay 0 */
+            if (e == cudaSuccess && st[b].nRuns) e = cudaMemcpy(ob.runs, st[b].runs, sizeof(int32_t) * 3 * (size_t)st[b].nRuns, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemset(ob.carryVal, 0, sizeof(double) * 2 * (size_t)ob.nTiles);
+        }
+        for (int b = 0; b < nBlocks; ++b) ehyb_ovfstream_free(&st[b]);
         if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "overflow stream upload: %s", cudaGetErrorString(e));
-        CU(cudaFuncSetAttribute(ehyb_ovfstream_kernel<kStreamTileGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+        CU(cudaFuncSetAttribute(ehyb_ovfstream_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     } else if (h->nOvf > 0) {
         CU(cudaMalloc(&h->ovfRow, sizeof(int32_t) * (size_t)h->nOvf));
         CU(cudaMalloc(&h->ovfCol, sizeof(int32_t) * (size_t)h->nOvf));
@@ -446,6 +491,8 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
             for (int sl = 2; sl <= 3; ++sl) {
                 CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0, sl), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
                 CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0, sl), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0, sl, true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+                CU(cudaFuncSetAttribute(persistent_kernel(t, peer != 0, sl, true), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             }
     if (kernel == EHYB_KERNEL_PERSISTENT) {
         int rcTab = build_cta_tab(h, v, NULL);
@@ -537,10 +584,10 @@ static int upload_session(const ehyb_layout *L, const ehyb_session_opts *opts, b
 }
 
 /* peer: the launch carries a halo exchange, or the session records a per-CTA trace */
-static main_kernel_t main_kernel_of(const ehyb_handle *h, bool peer)
+static main_kernel_t main_kernel_of(const ehyb_handle *h, bool peer, bool dot = false)
 {
-    if (h->kernel == EHYB_KERNEL_PERSISTENT) return persistent_kernel(h->threads, peer || h->trace != NULL || h->forcePeerBuild, h->slotsPerWarp);
-    if (h->kernel == EHYB_KERNEL_STAGED) return staged_kernel(h->threads, peer || h->trace != NULL);
+    if (h->kernel == EHYB_KERNEL_PERSISTENT) return persistent_kernel(h->threads, peer || h->trace != NULL || h->forcePeerBuild, h->slotsPerWarp, dot);
+    if (h->kernel == EHYB_KERNEL_STAGED) return staged_kernel(h->threads, peer || h->trace != NULL || dot); /* the staged kernel's dot lives in its multi-GPU build */
     return pick_kernel(h->kernel, h->threads, h->ctasPerSM);
 }
 
@@ -556,6 +603,7 @@ static PeerArgs no_peer(const ehyb_handle *h, const double *x_d)
 static MainArgs main_args(const ehyb_handle *h, const double *x_d, double *y_d, const PeerArgs *pa)
 {
     MainArgs a;
+    a.dot = NULL;
     a.parts = h->parts; a.slices = h->slices; a.blob = h->blob;
     a.x = x_d; a.y = y_d; a.n = (int)h->n; a.W = h->W; a.kpp = h->kpp; a.dbg = h->dbgSkip; a.cacheCols = h->cacheCols; a.cacheCap = h->cacheCap;
     a.order = h->order;
@@ -572,14 +620,15 @@ static MainArgs main_args(const ehyb_handle *h, const double *x_d, double *y_d, 
 }
 
 /* the launches of one product, on `s` */
-static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s, const PeerArgs *pa)
+static int launch_main(ehyb_handle *h, const double *x_d, double *y_d, cudaStream_t s, const PeerArgs *pa, double *dot_d = NULL)
 {
     if (h->skipMain && pa == NULL) { /* (a peer-memory product needs the kernel: it carries the halo push) */
         CU(cudaMemsetAsync(y_d, 0, sizeof(double) * (size_t)h->n, s));
         return EHYB_OK;
     }
-    const MainArgs a = main_args(h, x_d, y_d, pa);
-    main_kernel_t k = main_kernel_of(h, pa != NULL);
+    MainArgs a = main_args(h, x_d, y_d, pa);
+    a.dot = dot_d;
+    main_kernel_t k = main_kernel_of(h, pa != NULL, dot_d != NULL);
     if ((h->kernel == EHYB_KERNEL_STAGED || h->kernel == EHYB_KERNEL_PERSISTENT) && h->pdl) {
         /* programmatic dependent launch: this grid may start while the previous kernel of the
          * stream drains; it orders itself with griddepcontrol.wait before touching x or y */
@@ -621,19 +670,28 @@ static int launch_overflow(ehyb_handle *h, const double *x_d, double *y_d, cudaS
          * stream kernel reads x through the read-only path: it must not start before its predecessor
          * is complete) */
         if (pa != NULL && pa->flags != NULL) return ehyb_fail(EHYB_ERR_ARG, "the overflow stream does not carry the peer-memory exchange");
-        OvfStreamArgs a;
-        a.val = h->ovfVal; a.col = h->ovfColEnc; a.grp = h->ovfGrp; a.rowOfSeg = h->ovfRowOfSeg; a.hubCols = h->ovfHubCols;
-        a.nHub = h->ovfHubs; a.count = h->nOvf; a.nGroups = h->ovfGroups; a.nTiles = h->ovfTiles;
-        a.x = x_d; a.y = y_d; a.carryRow = h->ovfCarryRow; a.carryVal = h->ovfCarryVal;
-        a.accumulate = h->skipMain ? 0 : 1;
-        const int64_t tilesPerCta = 32;
-        int grid = h->smCount;
-        if ((int64_t)grid * tilesPerCta > h->ovfTiles) grid = (int)((h->ovfTiles + tilesPerCta - 1) / tilesPerCta);
-        ehyb_ovfstream_kernel<kStreamTileGroups><<<grid, 1024, sizeof(double) * (size_t)h->ovfHubs, s>>>(a);
-        CU(cudaGetLastError());
-        const int64_t n2 = 2 * (int64_t)h->ovfTiles;
-        ehyb_ovfstream_fixup<<<(unsigned)((n2 + 255) / 256), 256, 0, s>>>(h->ovfCarryRow, h->ovfCarryVal, n2, y_d, a.accumulate);
-        CU(cudaGetLastError());
+        const int tg = h->ovfTileGroups, warps = tg == 8 ? 16 : 32;
+        for (int b = 0; b < h->ovfBlocks; ++b) {
+            const ehyb_handle::OvfBlock &ob = h->ovfBlock[b];
+            if (ob.nTiles == 0) continue;
+            OvfStreamArgs a;
+            a.tiles = ob.tiles; a.rowOfSeg = ob.rowOfSeg; a.hubCols = ob.hubCols;
+            a.nHub = ob.nHub; a.nTiles = ob.nTiles; a.slots = h->ovfSlots;
+            a.x = x_d; a.y = y_d; a.carryVal = ob.carryVal;
+            /* y holds the slice part (main kernel) or zeros (memset); with several column blocks every
+             * block adds to what the blocks before it left */
+            a.accumulate = (h->skipMain && h->ovfBlocks == 1) ? 0 : 1;
+            int grid = h->smCount;
+            if ((int64_t)grid * warps > ob.nTiles) grid = (ob.nTiles + warps - 1) / warps; /* one tile per warp at least */
+            const size_t smem = (size_t)kStreamHeader + (size_t)warps * h->ovfSlots * EHYB_OVF_TILE_BYTES(tg) + sizeof(double) * (size_t)ob.nHub;
+            ehyb_ovfstream_kernel<4, 1024><<<grid, 1024, smem, s>>>(a);
+            CU(cudaGetLastError());
+            if (ob.nRuns > 0) {
+                const int64_t blocks = (ob.nRunsShort + 255) / 256 + (ob.nRuns - ob.nRunsShort + 7) / 8;
+                ehyb_ovfstream_fixup<<<(unsigned)blocks, 256, 0, s>>>(ob.runs, ob.nRunsShort, ob.nRuns, ob.carryVal, y_d, a.accumulate);
+                CU(cudaGetLastError());
+            }
+        }
         return EHYB_OK;
     }
     OverflowArgs o;
@@ -673,7 +731,16 @@ static int launch_product(ehyb_handle *h, const double *x_d, double *y_d, cudaSt
     return rc ? rc : launch_overflow(h, x_d, y_d, s, NULL);
 }
 
-extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h) { return h ? (h->nOvf > 0 ? (h->ovfStream ? 3 : 2) : 1) - (h->skipMain ? 1 : 0) : 0; }
+extern "C" int ehyb_launches_per_spmv(const ehyb_handle *h)
+{
+    if (!h) return 0;
+    int k = h->skipMain ? 0 : 1;
+    if (h->nOvf > 0 && !h->ovfStream) k += 1;
+    if (h->nOvf > 0 && h->ovfStream)
+        for (int b = 0; b < h->ovfBlocks; ++b) /* stream kernel (+ carry fix-up) per column block */
+            k += h->ovfBlock[b].nTiles > 0 ? (h->ovfBlock[b].nRuns > 0 ? 2 : 1) : 0;
+    return k;
+}
 
 extern "C" int ehyb_spmv(ehyb_handle *h, const double *x_d, double *y_d)
 {
@@ -694,6 +761,43 @@ extern "C" int ehyb_spmv(ehyb_handle *h, const double *x_d, double *y_d)
         h->gx = x_d; h->gy = y_d;
     }
     CU(cudaGraphLaunch(h->gexec, h->stream));
+    return EHYB_OK;
+}
+
+/* y = A x and *dot_d += x . y in one launch (the p.Ap of a conjugate-gradient iteration): the rows'
+ * products are taken while y is stored, x[r] from the x window in shared memory.  Only where one
+ * launch is the whole product: staged or persistent kernel, empty overflow list. */
+extern "C" int ehyb_spmv_dot_supported(const ehyb_handle *h)
+{
+    return h && (h->kernel == EHYB_KERNEL_STAGED || h->kernel == EHYB_KERNEL_PERSISTENT) && h->nOvf == 0 && !h->skipMain &&
+           (h->kernel == EHYB_KERNEL_STAGED || h->slotsPerWarp == 2);
+}
+
+extern "C" int ehyb_spmv_dot(ehyb_handle *h, const double *x_d, double *y_d, double *dot_d)
+{
+    if (!h || !x_d || !y_d || !dot_d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_spmv_dot: NULL argument");
+    if (!ehyb_spmv_dot_supported(h)) return ehyb_fail(EHYB_ERR_ARG, "ehyb_spmv_dot: this session's product is not a single staged / persistent launch");
+    CU(cudaSetDevice(h->device));
+    return launch_main(h, x_d, y_d, h->stream, NULL, dot_d);
+}
+
+/* host-vector form (tests, one-off callers): y_h = A x_h, *dot_h = x_h . y_h from the fused kernel */
+extern "C" int ehyb_spmv_dot_host(ehyb_handle *h, const double *x_h, double *y_h, double *dot_h)
+{
+    if (!h || !x_h || !y_h || !dot_h) return ehyb_fail(EHYB_ERR_ARG, "ehyb_spmv_dot_host: NULL argument");
+    CU(cudaSetDevice(h->device));
+    double *dot_d = NULL;
+    CU(cudaMalloc(&dot_d, sizeof(double)));
+    int rc = EHYB_OK;
+    cudaError_t e = cudaMemsetAsync(dot_d, 0, sizeof(double), h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->x, x_h, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) rc = ehyb_spmv_dot(h, h->x, h->y, dot_d);
+    if (e == cudaSuccess && rc == EHYB_OK) e = cudaMemcpyAsync(y_h, h->y, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && rc == EHYB_OK) e = cudaMemcpyAsync(dot_h, dot_d, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dot_d);
+    if (rc) return rc;
+    if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "ehyb_spmv_dot_host: %s", cudaGetErrorString(e));
     return EHYB_OK;
 }
 
@@ -833,6 +937,46 @@ extern "C" int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_t
     return EHYB_OK;
 }
 
+/* Cold-L2 timing (SURVEY.md 8d "Timing": matrices that fit the 126 MB L2 must be reported with and
+ * without a flush): before every product `flush_bytes` of scratch memory are overwritten on the
+ * session stream, which pushes matrix, x and y out of L2; every product has its own event pair (all
+ * of its launches between them) and *ms_sum is the sum over `iters` products.  Launches are plain
+ * here: a programmatic launch would start the product's prologue under the flush. */
+extern "C" int ehyb_time_spmv_flushed(ehyb_handle *h, int warmup, int iters, size_t flush_bytes, float *ms_sum)
+{
+    if (!h || !ms_sum || iters <= 0 || warmup < 0 || flush_bytes == 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_time_spmv_flushed: bad argument");
+    CU(cudaSetDevice(h->device));
+    void *scratch = NULL;
+    CU(cudaMalloc(&scratch, flush_bytes));
+    cudaEvent_t *ev = (cudaEvent_t *)calloc((size_t)iters * 2, sizeof(cudaEvent_t));
+    if (!ev) { cudaFree(scratch); return ehyb_fail(EHYB_ERR_NOMEM, "ehyb_time_spmv_flushed: out of memory"); }
+    for (int i = 0; i < 2 * iters; ++i) cudaEventCreate(&ev[i]);
+    const int pdl = h->pdl;
+    h->pdl = 0;
+    int rc = EHYB_OK;
+    for (int i = -warmup; i < iters && rc == EHYB_OK; ++i) {
+        cudaMemsetAsync(scratch, i & 1, flush_bytes, h->stream);
+        if (i >= 0) cudaEventRecord(ev[2 * i], h->stream);
+        rc = launch_product(h, h->x, h->y, h->stream);
+        if (i >= 0) cudaEventRecord(ev[2 * i + 1], h->stream);
+    }
+    h->pdl = pdl;
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    float sum = 0.f;
+    for (int i = 0; i < iters && e == cudaSuccess && rc == EHYB_OK; ++i) {
+        float t = 0.f;
+        e = cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+        sum += t;
+    }
+    for (int i = 0; i < 2 * iters; ++i) cudaEventDestroy(ev[i]);
+    free(ev);
+    cudaFree(scratch);
+    if (rc) return rc;
+    if (e != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "flushed timing: %s", cudaGetErrorString(e));
+    *ms_sum = sum;
+    return EHYB_OK;
+}
+
 /* Development aid (EHYB_TRACE=1 when the session was created): the staged kernel's per-CTA
  * timeline of the last product - 8 words per CTA: globaltimer ns at CTA start, after the wait
  * for the previous grid, after the halo push, when window + cache are staged, when the last
@@ -920,6 +1064,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t);
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*GroupStart)(void);
     ncclResult_t (*GroupEnd)(void);
     const char *(*GetErrorString)(ncclResult_t);
@@ -942,6 +1087,7 @@ static int nccl_load(void)
     SYM(CommDestroy, "ncclCommDestroy");
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
+    SYM(AllReduce, "ncclAllReduce");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -980,7 +1126,14 @@ struct ehyb_mg_session {
     uint32_t epoch, recvMask, nbrMask;
     int nPeers, pushCtas, connected, peerIsLocal;
     unsigned long long timeoutNs;
+    /* scalar all-reduce over peer memory (ehyb_mg_allreduce_sum): a mailbox in `shared` that EVERY
+     * rank maps - [2 parities][nranks][kMboxVals] doubles, then [2][nranks] epoch words */
+    size_t mboxOffset;
+    unsigned char **mboxPeer_d;  /* device: [nranks] every rank's mailbox (own: local address) */
+    uint32_t arEpoch;
 };
+constexpr int kMboxVals = 4;
+static size_t mbox_bytes(int nranks) { return ((size_t)2 * nranks * kMboxVals * sizeof(double) + (size_t)2 * nranks * sizeof(uint32_t) + 255) & ~(size_t)255; }
 
 __global__ void ehyb_pack_kernel(const double *__restrict__ x, const int32_t *__restrict__ idx, double *__restrict__ out, int64_t n)
 {
@@ -1013,7 +1166,7 @@ extern "C" void ehyb_mg_session_free(ehyb_mg_session *s)
             if (s->peerBase[g] && !s->peerIsLocal) cudaIpcCloseMemHandle(s->peerBase[g]);
         free(s->peerBase);
     }
-    cudaFree(s->shared); cudaFree(s->pushDst_d[0]); cudaFree(s->pushDst_d[1]); cudaFree(s->peerFlag_d);
+    cudaFree(s->shared); cudaFree(s->pushDst_d[0]); cudaFree(s->pushDst_d[1]); cudaFree(s->peerFlag_d); cudaFree(s->mboxPeer_d);
     cudaFree(s->peerPushCtas_d);
     if (s->status_h) { if (s->h) s->h->peerStatus_h = NULL; cudaFreeHost(s->status_h); }
     cudaFree(s->sendIdx_d); cudaFree(s->sendBuf_d);
@@ -1122,7 +1275,8 @@ struct P2PBlob {
     int32_t device, rank;
     int32_t pushCtas;          /* CTAs of this rank that push = flag words it writes on a neighbour */
     int32_t pad32;
-    int64_t pad[3];
+    int64_t mboxOffset;        /* bytes from the base to the all-reduce mailbox */
+    int64_t pad[2];
 };
 static_assert(sizeof(P2PBlob) == EHYB_MG_P2P_BLOB_BYTES, "P2PBlob must match EHYB_MG_P2P_BLOB_BYTES");
 
@@ -1155,8 +1309,9 @@ extern "C" int ehyb_mg_session_create_p2p(const ehyb_mg_local *L, int rank, int 
         /* [halo 0 | halo 1 | flags], every part 256-byte aligned; the allocation is rounded up to
          * 2 MiB so that the IPC handle covers this block and nothing else */
         s->haloStride = (((size_t)s->nHalo + 1) * sizeof(double) + 255) & ~(size_t)255;
-        const size_t flagsBytes = (size_t)nranks * kMaxPushCtas * sizeof(uint32_t);
-        s->sharedBytes = (2 * s->haloStride + flagsBytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        const size_t flagsBytes = ((size_t)nranks * kMaxPushCtas * sizeof(uint32_t) + 255) & ~(size_t)255;
+        s->mboxOffset = 2 * s->haloStride + flagsBytes;
+        s->sharedBytes = (s->mboxOffset + mbox_bytes(nranks) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
         CU(cudaMalloc(&s->shared, s->sharedBytes));
         CU(cudaMemset(s->shared, 0, s->sharedBytes));
         CU(cudaHostAlloc((void **)&s->status_h, 256, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -1237,6 +1392,7 @@ extern "C" int ehyb_mg_p2p_export(ehyb_mg_session *s, void *blob)
     b.device = s->h->device;
     b.rank = s->rank;
     b.pushCtas = s->pushCtas;
+    b.mboxOffset = (int64_t)s->mboxOffset;
     memcpy(blob, &b, sizeof b);
     return EHYB_OK;
 }
@@ -1254,15 +1410,17 @@ static int p2p_connect_impl(ehyb_mg_session *s, const P2PBlob *B, const int64_t 
     double **dst[2] = {(double **)malloc(sizeof(double *) * (size_t)(s->nSend ? s->nSend : 1)),
                        (double **)malloc(sizeof(double *) * (size_t)(s->nSend ? s->nSend : 1))};
     uint32_t **flagAddr = (uint32_t **)malloc(sizeof(uint32_t *) * (size_t)R);
+    unsigned char **mbox = (unsigned char **)calloc((size_t)R, sizeof(unsigned char *));
     int rc = EHYB_OK;
     auto body = [&]() -> int {
-        if (!s->peerBase || !dst[0] || !dst[1] || !flagAddr) return ehyb_fail(EHYB_ERR_NOMEM, "p2p connect: out of memory");
+        if (!s->peerBase || !dst[0] || !dst[1] || !flagAddr || !mbox) return ehyb_fail(EHYB_ERR_NOMEM, "p2p connect: out of memory");
         s->recvMask = s->nbrMask = 0;
         s->nPeers = 0;
         int64_t so = 0;
+        mbox[s->rank] = s->shared + s->mboxOffset;
         for (int g = 0; g < R; ++g) {
             const int64_t sc = s->sendCount[g], rcv = s->recvCount[g];
-            if (g == s->rank || (sc == 0 && rcv == 0)) { so += sc; continue; }
+            if (g == s->rank) { so += sc; continue; }
             if (B[g].rank != g) return ehyb_fail(EHYB_ERR_ARG, "p2p connect: blob %d describes rank %d", g, B[g].rank);
             if (recvOffsetOnPeer[g] < 0 || recvOffsetOnPeer[g] + sc > B[g].nHalo)
                 return ehyb_fail(EHYB_ERR_ARG, "p2p connect: %lld entries at %lld do not fit rank %d's halo of %lld", (long long)sc,
@@ -1283,6 +1441,8 @@ static int p2p_connect_impl(ehyb_mg_session *s, const P2PBlob *B, const int64_t 
                 }
             }
             unsigned char *base = (unsigned char *)s->peerBase[g];
+            mbox[g] = base + B[g].mboxOffset;
+            if (sc == 0 && rcv == 0) continue; /* not a neighbour: mapped for the all-reduce mailbox only */
             for (int64_t k = 0; k < sc; ++k)
                 for (int b = 0; b < 2; ++b)
                     dst[b][so + k] = (double *)(base + (size_t)b * (size_t)B[g].haloStride) + recvOffsetOnPeer[g] + k;
@@ -1307,11 +1467,13 @@ static int p2p_connect_impl(ehyb_mg_session *s, const P2PBlob *B, const int64_t 
         if (e2 != cudaSuccess) return ehyb_fail(EHYB_ERR_CUDA, "p2p connect: %s", cudaGetErrorString(e2));
         CU(cudaMalloc(&s->peerFlag_d, sizeof(uint32_t *) * (size_t)(s->nPeers ? s->nPeers : 1)));
         if (s->nPeers) CU(cudaMemcpy(s->peerFlag_d, flagAddr, sizeof(uint32_t *) * (size_t)s->nPeers, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&s->mboxPeer_d, sizeof(unsigned char *) * (size_t)R));
+        CU(cudaMemcpy(s->mboxPeer_d, mbox, sizeof(unsigned char *) * (size_t)R, cudaMemcpyHostToDevice));
         CU(cudaDeviceSynchronize());
         return EHYB_OK;
     };
     rc = body();
-    free(dst[0]); free(dst[1]); free(flagAddr);
+    free(dst[0]); free(dst[1]); free(flagAddr); free(mbox);
     if (rc) return rc;
     s->connected = 1;
     return EHYB_OK;
@@ -1355,6 +1517,88 @@ extern "C" int ehyb_mg_p2p_connect_local(ehyb_mg_session *const *sessions, int n
     return rc;
 }
 
+/* Scalar all-reduce over peer memory: lane g of one warp stores this rank's `count` partial sums into
+ * rank g's mailbox (slot of this rank, parity of the epoch), releases them with the epoch word
+ * (st.release.sys), then waits for rank g's contribution in its OWN mailbox (ld.acquire.sys) and the
+ * warp adds the contributions in RANK ORDER - the same order on every GPU, so every rank holds the
+ * same bits and takes the same decisions from them.  A mailbox slot of parity b is written again two
+ * all-reduces later; a rank can only be there after it has received everybody's contribution to the
+ * one in between, which every rank sends after it has read this one: two parities are enough.
+ * Bounded like every wait on a peer (status word, ehyb_mg_status). */
+__global__ void __launch_bounds__(32) ehyb_allreduce_kernel(double *vals, int count, unsigned char *const *mboxPeer, int rank, int nranks,
+                                                            uint32_t epoch, unsigned long long timeoutNs, uint32_t *status)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int lane = threadIdx.x;
+    const uint32_t b = epoch & 1u;
+    const size_t valsOff = (static_cast<size_t>(b) * nranks) * kMboxVals * sizeof(double);
+    const size_t flagOff = static_cast<size_t>(2) * nranks * kMboxVals * sizeof(double) + static_cast<size_t>(b) * nranks * sizeof(uint32_t);
+    double mine[kMboxVals];
+#pragma unroll
+    for (int k = 0; k < kMboxVals; ++k) mine[k] = k < count ? __ldcg(vals + k) : 0.0;
+    double got[kMboxVals];
+#pragma unroll
+    for (int k = 0; k < kMboxVals; ++k) got[k] = 0.0;
+    bool ok = true;
+    if (lane < nranks) {
+        unsigned char *peer = mboxPeer[lane];
+        double *dst = reinterpret_cast<double *>(peer + valsOff) + static_cast<size_t>(rank) * kMboxVals;
+#pragma unroll
+        for (int k = 0; k < kMboxVals; ++k) dst[k] = mine[k];
+        st_release_sys_u32(reinterpret_cast<uint32_t *>(peer + flagOff) + rank, epoch);
+        /* rank `lane`'s contribution, in my own mailbox */
+        unsigned char *own = mboxPeer[rank];
+        const uint32_t *flag = reinterpret_cast<const uint32_t *>(own + flagOff) + lane;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned polls = 0;
+        while (ld_acquire_sys_u32(flag) != epoch) {
+            if ((++polls & 255u) == 0 && timeoutNs && global_timer_ns() - t0 > timeoutNs) { ok = false; break; }
+        }
+        const double *src = reinterpret_cast<const double *>(own + valsOff) + static_cast<size_t>(lane) * kMboxVals;
+#pragma unroll
+        for (int k = 0; k < kMboxVals; ++k) got[k] = __ldcg(src + k);
+    }
+    if (!__all_sync(0xffffffffu, ok)) {
+        if (lane == 0) *status = 1u; /* a rank did not show up: the values are left alone, the host reports it */
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < kMboxVals; ++k) {
+        double sum = 0.0;
+        for (int g = 0; g < nranks; ++g) sum += __shfl_sync(0xffffffffu, got[k], g);
+        if (lane == 0 && k < count) vals[k] = sum;
+    }
+}
+
+/* In-stream all-reduce (sum) of `count` <= 4 doubles at vals_d (device memory, replaced by the sum over
+ * the ranks), on the session stream.  Collective: every rank calls it the same number of times.
+ * Peer-memory sessions use the mailbox above; NCCL sessions ncclAllReduce on the session stream. */
+extern "C" int ehyb_mg_allreduce_sum(ehyb_mg_session *s, double *vals_d, int count)
+{
+    if (!s || !vals_d || count < 1 || count > kMboxVals) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_allreduce_sum: bad argument (1..%d values)", kMboxVals);
+    ehyb_handle *h = s->h;
+    CU(cudaSetDevice(h->device));
+    if (s->nranks == 1) return EHYB_OK;
+    if (s->exchange != EHYB_MG_P2P) {
+        NC(g_nccl.AllReduce(vals_d, vals_d, (size_t)count, ncclDouble, ncclSum, s->comm, h->stream));
+        return EHYB_OK;
+    }
+    if (!s->connected) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_allreduce_sum: call ehyb_mg_p2p_connect first");
+    s->arEpoch += 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    CU(cudaLaunchKernelEx(&cfg, ehyb_allreduce_kernel, vals_d, count, (unsigned char *const *)s->mboxPeer_d, s->rank, s->nranks, s->arEpoch,
+                          s->timeoutNs, s->status_d));
+    return EHYB_OK;
+}
+
 extern "C" int ehyb_mg_status(ehyb_mg_session *s, int *timed_out)
 {
     if (!s || !timed_out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_status: NULL");
@@ -1375,7 +1619,7 @@ extern "C" int ehyb_mg_launches_per_spmv(const ehyb_mg_session *s)
 
 /* peer-memory product: ONE launch (plus the overflow kernel if the block has overflow
  * entries); the exchange happens inside the main kernel (ehyb_kernels.cuh, PeerArgs) */
-static int mg_spmv_p2p(ehyb_mg_session *s, double *x_d, double *y_d)
+static int mg_spmv_p2p(ehyb_mg_session *s, double *x_d, double *y_d, double *dot_d = NULL)
 {
     ehyb_handle *h = s->h;
     if (!s->connected) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv: call ehyb_mg_p2p_connect first");
@@ -1398,7 +1642,7 @@ static int mg_spmv_p2p(ehyb_mg_session *s, double *x_d, double *y_d)
     pa.pushCount = (int)s->nSend;
     pa.pushCtas = s->pushCtas;
     pa.nPeers = s->nPeers;
-    int rc = launch_main(h, x_d, y_d, h->stream, &pa);
+    int rc = launch_main(h, x_d, y_d, h->stream, &pa, dot_d);
     return rc ? rc : launch_overflow(h, x_d, y_d, h->stream, &pa);
 }
 
@@ -1439,6 +1683,32 @@ extern "C" int ehyb_mg_spmv(ehyb_mg_session *s, double *x_d, double *y_d)
     if (!s || !x_d || !y_d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv: NULL argument");
     CU(cudaSetDevice(s->h->device));
     return s->exchange == EHYB_MG_P2P ? mg_spmv_p2p(s, x_d, y_d) : mg_spmv_nccl(s, x_d, y_d);
+}
+
+/* The distributed product with the fused dot (ehyb_spmv_dot): *dot_d += x_own . y over this rank's
+ * rows; the sum over the ranks is the caller's (ehyb_mg_allreduce_sum).  Peer-memory sessions whose
+ * block has no overflow entries only (ehyb_mg_spmv_dot_supported). */
+extern "C" int ehyb_mg_spmv_dot_supported(const ehyb_mg_session *s)
+{
+    return s && s->exchange == EHYB_MG_P2P && ehyb_spmv_dot_supported(s->h);
+}
+
+extern "C" int ehyb_mg_spmv_dot(ehyb_mg_session *s, double *x_d, double *y_d, double *dot_d)
+{
+    if (!s || !x_d || !y_d || !dot_d) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv_dot: NULL argument");
+    if (!ehyb_mg_spmv_dot_supported(s)) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_spmv_dot: not a peer-memory session with a single-launch product");
+    CU(cudaSetDevice(s->h->device));
+    return mg_spmv_p2p(s, x_d, y_d, dot_d);
+}
+
+/* device of a session (a solver allocates its vectors there) */
+extern "C" int ehyb_session_device(const ehyb_handle *h) { return h ? h->device : -1; }
+extern "C" int ehyb_mg_session_ranks(const ehyb_mg_session *s, int *rank, int *nranks)
+{
+    if (!s) return ehyb_fail(EHYB_ERR_ARG, "ehyb_mg_session_ranks: NULL");
+    if (rank) *rank = s->rank;
+    if (nranks) *nranks = s->nranks;
+    return EHYB_OK;
 }
 
 /* Pipelined stream of distributed products with HOST vectors: for i in [0, count): y_h[i] =

@@ -82,6 +82,9 @@ struct MainArgs {
     int l2hint;               /* staged kernel: L2 eviction hints on the TMA copies (stream evict-first, x evict-last) */
     uint32_t winPiece;        /* staged kernel: bytes per bulk copy of the x window (multiple of 16) */
     unsigned long long *trace; /* development (EHYB_TRACE=1): 8 globaltimer stamps per CTA, else NULL */
+    double *dot;              /* ehyb_spmv_dot (DOT builds of the persistent kernel, multi-GPU builds of the staged one):
+                                 *dot += sum over the rows of y[r] * x[r], the p.Ap of a CG iteration, x[r] taken
+                                 from the x window in shared memory while y is stored */
     PeerArgs peer;
 };
 
@@ -672,6 +675,24 @@ __device__ __forceinline__ int2 lds_s32x2(uint32_t addr)
     return v;
 }
 
+/* Fused dot product of a CG iteration (MainArgs.dot): rows r and r + 32 of the slice just stored,
+ * y[r] * x[r] with x[r] taken from the partition's window in shared memory (rows of a partition
+ * start at the window's first element; a row beyond the window reads x from global memory). */
+__device__ __forceinline__ double dot_rows(const double *x, uint32_t xsAddr, int ps, int winEnd, int pe, int r, double y0, double y1, double dacc)
+{
+    if (r < pe) dacc = fma(y0, r < winEnd ? lds_f64(xsAddr + static_cast<uint32_t>(r - ps) * 8u) : ld_gather_f64(x + r), dacc);
+    if (r + 32 < pe) dacc = fma(y1, r + 32 < winEnd ? lds_f64(xsAddr + static_cast<uint32_t>(r + 32 - ps) * 8u) : ld_gather_f64(x + r + 32), dacc);
+    return dacc;
+}
+/* end of the warp: one atomic per warp (the sum order over warps is not fixed: like every reduction
+ * of the solver, inside its tolerance, not bit-reproducible) */
+__device__ __forceinline__ void dot_flush(double *dot, double dacc, int lane)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dacc += __shfl_xor_sync(0xffffffffu, dacc, off);
+    if (lane == 0) atomicAdd(dot, dacc);
+}
+
 /* shared-memory address of x[idx] for the two 16-bit indices packed in c: base + 8 * index.  Written
  * as extract + multiply-add (2 instructions per gather; left to itself the compiler shifts, masks
  * and adds: 3) - the index arithmetic is a third of the consumer loop's instructions. */
@@ -961,6 +982,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
     if (tr && tid == 0) tr[3] = global_timer_ns(); /* x window in shared memory */
 
     double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
+    double dacc = 0.0; /* PEER build with a.dot: this warp's share of y.x */
     int s = 0; /* slot in use: chunks alternate between the two slots of the warp */
 #pragma unroll 1
     while (meta[0].flags | meta[1].flags) {
@@ -1026,12 +1048,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_staged_kernel(const MainA
             const int r = ps + m.t * EHYB_SLICE_ROWS + lane;
             if (r < pe) a.y[r] = acc0 + r0; /* y = dot_ell + dot_rem, as kernel.cu:162 + :76 */
             if (r + 32 < pe) a.y[r + 32] = acc1 + r1;
+            if constexpr (PEER) {
+                if (a.dot != nullptr) dacc = dot_rows(a.x, xsAddr, ps, winEnd, pe, r, acc0 + r0, acc1 + r1, dacc);
+            }
             acc0 = acc1 = r0 = r1 = 0.0;
         }
         __syncwarp(); /* every lane is done with the slot before it is refilled */
         const ChunkMeta mn = issue_chunk(wk, slot, bar, lane, streamPolicy);
         if (s) meta[1] = mn; else meta[0] = mn;
         s ^= 1;
+    }
+    if constexpr (PEER) {
+        if (a.dot != nullptr) dot_flush(a.dot, dacc, lane);
     }
     if (tr && lane == 0) atomicMax(tr + 4, global_timer_ns()); /* last warp of the CTA done */
 }
@@ -1269,7 +1297,11 @@ __device__ __noinline__ bool stage_halo_columns(const MainArgs &a, const int32_t
  * the 128-register budget of a 512-thread CTA beat 20 x 2 at 96 registers wherever the two buffers
  * leave 120 KB (27-point 256^3: 795 -> see profiles/r2_notes.md); measured: the register budget
  * matters as much as the bytes in flight - the consumer's LDS chains decide how fast a slot turns around. */
-template <int kMaxThreads, int KCE, bool PEER, int NS>
+/* DOT: the build that also accumulates a.dot += sum_r y[r] * x[r] (ehyb_spmv_dot, the p.Ap of a CG
+ * iteration).  A build of its own, and the warp's partial sum lives in shared memory, not in a
+ * register pair: the consumer loop sits at the register cap of every build (the dot folded into the
+ * 96-register multi-GPU build spilled and cost 19 % of the product, ncu). */
+template <int kMaxThreads, int KCE, bool PEER, int NS, bool DOT = false>
 __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const __grid_constant__ MainArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -1285,7 +1317,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     const int4 *tab = reinterpret_cast<const int4 *>(a.ctaTab) + 2 * static_cast<size_t>(item0);
 
     /* header: [0,16) window bars, [16,32) cache bars, [32,48) empty bars, [64,640) slot bars,
-     * [960,964) sequence counter */
+     * [640,832) DOT builds: one partial sum per warp, [960,964) sequence counter */
     const uint32_t hdr = smem_u32(smem);
     int *seqCounter = reinterpret_cast<int *>(smem + 960);
     const uint32_t winBytes = (static_cast<uint32_t>(a.W + 2) * 8u + 127u) & ~127u;
@@ -1445,6 +1477,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
     bool dutyDue = false; /* set at the end of a slice: stage the next partition at the top of the next iteration */
 
     double acc0 = 0.0, acc1 = 0.0, r0 = 0.0, r1 = 0.0;
+    double *dotAcc = reinterpret_cast<double *>(smem + 640) + warp; /* DOT: this warp's share of y.x (header bytes [640, 832)) */
+    if (DOT && lane == 0) *dotAcc = 0.0;
     int s = 0;
 #pragma unroll 1
     for (;;) {
@@ -1524,6 +1558,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
                 const int r = row0 + m.t * EHYB_SLICE_ROWS + lane;
                 if (r < pe) a.y[r] = acc0 + r0;
                 if (r + 32 < pe) a.y[r + 32] = acc1 + r1;
+                if constexpr (DOT) {
+                    double v = dot_rows(a.x, xsAddr, ps, min(ps + a.W, a.n), pe, r, acc0 + r0, acc1 + r1, 0.0);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    if (lane == 0) *dotAcc += v;
+                }
                 acc0 = acc1 = r0 = r1 = 0.0;
                 dutyDue = true;
             }
@@ -1532,6 +1572,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) ehyb_persistent_kernel(const _
         const PMeta mn = issue_pchunk(wk, slot, bar, lane, streamPolicy);
         if (s == 0) meta0 = mn; else if (s == 1 || NS == 2) meta1 = mn; else meta2 = mn;
         s = s + 1 == NS ? 0 : s + 1;
+    }
+    if constexpr (DOT) {
+        if (lane == 0) atomicAdd(a.dot, *dotAcc);
     }
     if (PEER && tr && lane == 0) atomicMax(tr + 4, global_timer_ns());
     /* (every warp has passed all nj-1 switch markers here: the walker always ends in the last
@@ -1623,145 +1666,199 @@ __global__ void __launch_bounds__(256) ehyb_overflow_kernel(const OverflowArgs a
 /* ---------------------------------------------------------------- overflow stream --- */
 
 /*
- * Large overflow lists (power-law graphs: the list is the matrix) in the CSR-like stream format of
- * host/ovfstream.c: 12 bytes per entry + 8 per 32 entries, hub columns in shared memory, no
- * atomics.  One persistent CTA of 1 024 threads per SM; a warp takes tiles of TG x 32 consecutive
- * entries (tile t -> warp t mod #warps: neighbouring warps stream neighbouring tiles).
+ * Large overflow lists (power-law graphs: the list is the matrix) in the tile-packed CSR-like
+ * stream of host/ovfstream.c: 12.4 bytes per entry, hub columns in shared memory, no atomics.
+ * One persistent CTA per SM; a warp takes tiles of TG x 32 consecutive entries (tile t -> warp
+ * t mod #warps: neighbouring warps stream neighbouring tiles).
  *
- *   - the x values of the hub columns (the <= 16 384 most referenced ones) are gathered into shared
- *     memory once per CTA; an entry with the top bit of its column set reads there (LDS) instead of
+ *   - a tile is ONE record (values, columns, group words, flags) that lane 0 moves into one of the
+ *     warp's staging slots with a bulk copy (UBLKCP, evict-first) `slots` tiles ahead: the matrix
+ *     stream costs no registers and no exposed latency.  The only global loads a warp waits for are
+ *     its x gathers and - issued WITH them - the rows of the segments that end in each lane: one
+ *     memory latency per tile, where plain loads of three arrays walked three dependent ones
+ *     (stream -> gather -> row of the segment; R-MAT 24: 2 278 us, behind the COO list);
+ *   - the x values of the hub columns (the most referenced ones) are gathered into shared memory
+ *     once per CTA; an entry with the top bit of its column set reads there (LDS) instead of
  *     occupying one 32-byte L1TEX sector per lane;
- *   - all the streaming loads of a tile first (column + value of TG groups), then all the gathers;
  *   - row segments: lane j of a group belongs to segment seg0 + popc(mask & bits 1..j); products
- *     are summed per segment with a warp-shuffle segmented scan, carried from group to group
- *     inside the tile in registers;
+ *     are summed per segment with a warp-shuffle segmented scan (a lane knows its distance to the
+ *     head of its segment from the mask: only the sums travel), carried from group to group inside
+ *     the tile in registers;
  *   - a segment that lies inside the tile is stored by the lane at its end: y[row] = sum (or +=
  *     when the main kernel has written the row's slice part);
  *   - the tile's first segment if it continues a row of the previous tile, and its last one if the
- *     row goes on in the next tile, go to the tile's two CARRY slots instead; ehyb_ovfstream_fixup
- *     adds the slots of a row in tile order.  Who adds what, and in which order, is fixed by the
- *     data: y is bit-reproducible (the COO kernel's atomics are not).
+ *     row goes on in the next tile, go to the tile's two CARRY slots instead (their rows are fixed
+ *     by the data and were written at upload); ehyb_ovfstream_fixup adds the slots of a row in tile
+ *     order.  Who adds what, and in which order, is fixed by the data: y is bit-reproducible (the
+ *     COO kernel's atomics are not).
  */
 struct OvfStreamArgs {
-    const double *val;
-    const uint32_t *col;       /* column, or 0x80000000 | hub index */
-    const uint2 *grp;          /* per 32 entries: {segment of the first entry, new-row mask} */
+    const unsigned char *tiles; /* nTiles records of EHYB_OVF_TILE_BYTES(TG) */
     const int32_t *rowOfSeg;
     const int32_t *hubCols;
     int nHub;
-    int64_t count;
-    int nGroups, nTiles;
+    int nTiles;
+    int slots;                 /* staging slots per warp (2..4) */
     const double *x;
     double *y;
-    int32_t *carryRow;         /* [2 * nTiles]: head and tail slot of every tile, -1 = unused */
-    double *carryVal;
+    double *carryVal;          /* [2 * nTiles]: head and tail slot of every tile */
     int accumulate;            /* 1: y[row] += sum (the main kernel wrote y), 0: y[row] = sum (y was zeroed) */
 };
 
-constexpr int kStreamTileGroups = 4; /* 128 entries per tile */
+constexpr int kStreamHeader = 1024; /* mbarriers: warps x slots x 8 bytes */
+constexpr int kStreamMaxSlots = 4;
 
-template <int TG>
-__global__ void __launch_bounds__(1024, 1) ehyb_ovfstream_kernel(const __grid_constant__ OvfStreamArgs a)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
-    extern __shared__ __align__(16) double hub[];
-    const int tid = threadIdx.x, lane = tid & 31;
-    asm volatile("griddepcontrol.wait;" ::: "memory"); /* x, and y as the main kernel / the memset left it */
-    for (int i = tid; i < a.nHub; i += blockDim.x) hub[i] = ld_gather_f64(a.x + __ldg(a.hubCols + i));
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+template <int TG, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) ehyb_ovfstream_kernel(const __grid_constant__ OvfStreamArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr uint32_t E = 32u * TG;
+    constexpr uint32_t kTileBytes = EHYB_OVF_TILE_BYTES(TG);
+    constexpr uint32_t kColOff = 8u * E, kGrpOff = 12u * E, kFlagOff = 12u * E + 8u * TG;
+    constexpr int kWarps = kThreads / 32;
+    static_assert(kWarps * kStreamMaxSlots * 8 <= kStreamHeader, "barrier header too small");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slots = a.slots;
+    const uint32_t bar0 = smem_u32(smem) + static_cast<uint32_t>(warp * slots) * 8u;
+    const uint32_t slot0 = smem_u32(smem) + kStreamHeader + static_cast<uint32_t>(warp * slots) * kTileBytes;
+    double *hub = reinterpret_cast<double *>(smem + kStreamHeader + static_cast<size_t>(kWarps * slots) * kTileBytes);
+    if (tid == 0) {
+        for (int i = 0; i < kWarps * slots; ++i) mbar_init(smem_u32(smem) + 8u * i, 1);
+        fence_mbar_init();
+    }
     __syncthreads();
     const uint64_t pol = make_evict_first_policy();
-    const int nwarps = blockDim.x >> 5;
-    const int W = gridDim.x * nwarps;
+    const int Wt = static_cast<int>(gridDim.x) * kWarps;
+    const int first = static_cast<int>(blockIdx.x) * kWarps + warp;
+    /* the first `slots` tiles of this warp: constant data, on their way while the hubs are gathered */
+    if (lane == 0) {
+        for (int q = 0; q < slots; ++q) {
+            const int64_t t = static_cast<int64_t>(first) + static_cast<int64_t>(q) * Wt;
+            if (t < a.nTiles) {
+                mbar_expect_tx(bar0 + 8u * q, kTileBytes);
+                tma_bulk_g2s_hint(slot0 + static_cast<uint32_t>(q) * kTileBytes, a.tiles + static_cast<size_t>(t) * kTileBytes, kTileBytes, bar0 + 8u * q, pol);
+            }
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory"); /* x, and y as the main kernel / the memset left it */
+    for (int i = tid; i < a.nHub; i += kThreads) hub[i] = ld_gather_f64(a.x + __ldg(a.hubCols + i));
+    __syncthreads();
+    const uint32_t hubAddr = smem_u32(hub);
     const uint32_t lanemaskLe = (2u << lane) - 1u; /* bits 0..lane */
-    for (int tile = static_cast<int>(blockIdx.x) * nwarps + (tid >> 5); tile < a.nTiles; tile += W) {
-        const int g0 = tile * TG;
-        uint2 gm[TG];
-        uint32_t c[TG];
-        double v[TG], xv[TG];
+    uint32_t phases = 0;
+    int s = 0;
+#pragma unroll 1
+    for (int64_t tile = first; tile < a.nTiles; tile += Wt) {
+        const uint32_t slot = slot0 + static_cast<uint32_t>(s) * kTileBytes, bar = bar0 + static_cast<uint32_t>(s) * 8u;
+        mbar_wait_bounded(bar, (phases >> s) & 1u);
+        phases ^= 1u << s;
+        uint32_t c[TG], m[TG];
+        int seg[TG], row[TG];
+        double prod[TG];
 #pragma unroll
         for (int u = 0; u < TG; ++u) {
-            const int gi = g0 + u;
-            gm[u] = gi < a.nGroups ? __ldg(a.grp + gi) : make_uint2(0u, 0u);
-            const int64_t i = static_cast<int64_t>(gi) * 32 + lane;
-            const bool live = i < a.count;
-            c[u] = live ? static_cast<uint32_t>(ld_stream_s32(reinterpret_cast<const int *>(a.col) + i, pol)) : 0x80000000u;
-            v[u] = live ? ld_stream_f64(a.val + i, pol) : 0.0;
+            c[u] = lds_u32(slot + kColOff + (static_cast<uint32_t>(u) * 32u + lane) * 4u);
+            const int2 gm = lds_s32x2(slot + kGrpOff + static_cast<uint32_t>(u) * 8u);
+            m[u] = static_cast<uint32_t>(gm.y);
+            seg[u] = gm.x + __popc(m[u] & lanemaskLe & ~1u);
         }
-        const bool nextStartsNew = g0 + TG < a.nGroups ? (__ldg(&a.grp[g0 + TG].y) & 1u) != 0 : true;
+        const uint32_t flags = lds_u32(slot + kFlagOff);
+        /* the gathers of the whole tile, then the rows of the segments that end in this lane (lane 31
+         * always: its sum may be carried into the next group): all in flight together */
 #pragma unroll
-        for (int u = 0; u < TG; ++u) xv[u] = (c[u] & 0x80000000u) ? (a.nHub ? hub[c[u] & 0x7fffffffu] : 0.0) : __ldg(a.x + c[u]); /* (plain launch: x is constant while this grid lives) */
-        /* the tile's first and last segment */
-        const int liveGroups = min(TG, a.nGroups - g0);
-        const bool headCont = (gm[0].y & 1u) == 0u;
-        const int headSeg = static_cast<int>(gm[0].x);
-        const bool tailCont = !nextStartsNew;
-        int tailSeg;
-        {
-            const int64_t left = a.count - static_cast<int64_t>(g0 + liveGroups - 1) * 32; /* live lanes of the last live group */
-            const uint32_t liveMask = left >= 32 ? 0xffffffffu : ((1u << static_cast<int>(left)) - 1u);
-            uint2 last = gm[0];
+        for (int u = 0; u < TG; ++u)
+            prod[u] = (c[u] & EHYB_OVF_HUB_BIT) ? lds_f64(hubAddr + (c[u] & 0x7fffffffu) * 8u) : __ldg(a.x + c[u]); /* (plain launch: x is constant while this grid lives) */
 #pragma unroll
-            for (int u = 1; u < TG; ++u)
-                if (u < liveGroups) last = gm[u];
-            tailSeg = static_cast<int>(last.x) + __popc(last.y & liveMask & ~1u);
+        for (int u = 0; u < TG; ++u) {
+            const bool tailOfSeg = lane == 31 || ((m[u] >> (lane + 1)) & 1u) != 0u;
+            row[u] = tailOfSeg ? __ldg(a.rowOfSeg + seg[u]) : -1;
         }
-        if (lane == 0) { /* slots nobody will write this product */
-            if (!headCont) a.carryRow[2 * tile] = -1;
-            if (!tailCont) a.carryRow[2 * tile + 1] = -1;
-        }
-        auto store = [&](int seg, double sum) {
-            const int row = __ldg(a.rowOfSeg + seg);
-            const bool isHead = headCont && seg == headSeg, isTail = tailCont && seg == tailSeg;
-            if (isHead) {
-                a.carryRow[2 * tile] = row;
-                a.carryVal[2 * tile] = sum;
-                if (isTail) { a.carryRow[2 * tile + 1] = row; a.carryVal[2 * tile + 1] = 0.0; } /* the whole tile inside one row */
-            } else if (isTail) {
-                a.carryRow[2 * tile + 1] = row;
-                a.carryVal[2 * tile + 1] = sum;
-            } else if (a.accumulate) {
-                a.y[row] += sum;
-            } else {
-                a.y[row] = sum;
+#pragma unroll
+        for (int u = 0; u < TG; ++u) prod[u] *= lds_f64(slot + (static_cast<uint32_t>(u) * 32u + lane) * 8u);
+        __syncwarp(); /* every lane has taken what it needs from the slot: refill it */
+        if (lane == 0) {
+            const int64_t t = tile + static_cast<int64_t>(slots) * Wt;
+            if (t < a.nTiles) {
+                mbar_expect_tx(bar, kTileBytes);
+                tma_bulk_g2s_hint(slot, a.tiles + static_cast<size_t>(t) * kTileBytes, kTileBytes, bar, pol);
             }
+        }
+        const bool headCont = (flags & 1u) != 0u, tailCont = (flags & 2u) != 0u;
+        const int headSeg = __shfl_sync(0xffffffffu, seg[0], 0);
+        const int tailSeg = __shfl_sync(0xffffffffu, seg[TG - 1], 31);
+        auto store = [&](int sg, int r, double sum) {
+            if (r < 0) return; /* the padding entries behind the end of the list */
+            const bool isHead = headCont && sg == headSeg, isTail = tailCont && sg == tailSeg;
+            if (isHead) a.carryVal[2 * tile] = sum;               /* (also the tail: that slot keeps its 0) */
+            else if (isTail) a.carryVal[2 * tile + 1] = sum;
+            else if (a.accumulate) atomicAdd(a.y + r, sum); /* RED.ADD: nobody else adds to this row in this launch, and the warp does not wait for y */
+            else a.y[r] = sum;
         };
-        int carrySeg = -1;
+        int carrySeg = -1, carryRow = -1;
         double carry = 0.0;
 #pragma unroll
         for (int u = 0; u < TG; ++u) {
-            if (u >= liveGroups) break; /* warp-uniform */
-            const bool live = static_cast<int64_t>(g0 + u) * 32 + lane < a.count;
-            const int seg = live ? static_cast<int>(gm[u].x) + __popc(gm[u].y & lanemaskLe & ~1u) : -2 - lane;
-            double prod = v[u] * xv[u];
-            if (lane == 0 && seg == carrySeg) prod += carry;              /* continue the carried segment */
-            if (lane == 0 && carrySeg >= 0 && seg != carrySeg) store(carrySeg, carry); /* it ended with the previous group */
+            double p = prod[u];
+            /* distance to the head of this lane's segment inside the group (lane 0 counts as a head) */
+            const int dist = lane - (31 - __clz(static_cast<int>((m[u] | 1u) & lanemaskLe)));
+            if (lane == 0 && u > 0) {
+                if (seg[u] == carrySeg) p += carry;              /* continue the carried segment */
+                else store(carrySeg, carryRow, carry);           /* it ended with the previous group */
+            }
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, prod, off);
-                const int ss = __shfl_up_sync(0xffffffffu, seg, off);
-                if (lane >= off && ss == seg) prod += t;
+                const double t = __shfl_up_sync(0xffffffffu, p, off);
+                if (dist >= off) p += t;
             }
-            const int snext = __shfl_down_sync(0xffffffffu, seg, 1);
-            const bool tailOfSeg = live && (lane == 31 || snext != seg);
-            const bool carries = lane == 31 && live && u + 1 < liveGroups; /* may continue in the next group of this tile */
-            if (tailOfSeg && !carries) store(seg, prod);
-            carrySeg = __shfl_sync(0xffffffffu, carries ? seg : -1, 31);
-            carry = __shfl_sync(0xffffffffu, prod, 31);
+            const bool tailOfSeg = lane == 31 || ((m[u] >> (lane + 1)) & 1u) != 0u;
+            const bool carries = lane == 31 && u + 1 < TG; /* may continue in the next group of this tile */
+            if (tailOfSeg && !carries) store(seg[u], row[u], p);
+            if (u + 1 < TG) {
+                carrySeg = __shfl_sync(0xffffffffu, seg[u], 31);
+                carryRow = __shfl_sync(0xffffffffu, row[u], 31);
+                carry = __shfl_sync(0xffffffffu, p, 31);
+            }
         }
+        s = s + 1 == slots ? 0 : s + 1;
     }
 }
 
-/* adds the carry slots of every row that spans tiles, in tile order (one thread per run of equal rows) */
-__global__ void __launch_bounds__(256) ehyb_ovfstream_fixup(const int32_t *__restrict__ carryRow, const double *__restrict__ carryVal, int64_t n2,
-                                                          double *__restrict__ y, int accumulate)
+/* Adds the carry slots of every row that spans tiles.  The slots of a row are a run of consecutive
+ * slots known when the stream is built (host/ovfstream.c: runs = {first slot, slots, row}, the short
+ * runs first): one THREAD per short run, one WARP per long one - lane l adds slots l, l + 32, ... in
+ * order and the lanes are combined by a fixed shuffle tree, so the sum of a row that spans thousands
+ * of tiles (a hub row of a power-law graph) is still fixed by the data and no longer one thread's
+ * serial chain of dependent loads (R-MAT 24: ~500 us of a 2 000 us product before). */
+__global__ void __launch_bounds__(256) ehyb_ovfstream_fixup(const int32_t *__restrict__ runs, int64_t nShort, int64_t nRuns,
+                                                          const double *__restrict__ carryVal, double *__restrict__ y, int accumulate)
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n2) return;
-    const int r = carryRow[i];
-    if (r < 0 || (i > 0 && carryRow[i - 1] == r)) return;
+    const int64_t shortBlocks = (nShort + 255) / 256;
+    if (static_cast<int64_t>(blockIdx.x) < shortBlocks) {
+        const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+        if (i >= nShort) return;
+        const int first = runs[3 * i], len = runs[3 * i + 1], r = runs[3 * i + 2];
+        double sum = 0.0;
+        for (int k = 0; k < len; ++k) sum += carryVal[first + k];
+        y[r] = accumulate ? y[r] + sum : sum;
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t i = nShort + (static_cast<int64_t>(blockIdx.x) - shortBlocks) * 8 + (threadIdx.x >> 5);
+    if (i >= nRuns) return;
+    const int first = runs[3 * i], len = runs[3 * i + 1], r = runs[3 * i + 2];
     double sum = 0.0;
-    for (int64_t j = i; j < n2 && carryRow[j] == r; ++j) sum += carryVal[j];
-    y[r] = accumulate ? y[r] + sum : sum;
+    for (int k = lane; k < len; k += 32) sum += carryVal[first + k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) y[r] = accumulate ? y[r] + sum : sum;
 }
 
 } /* namespace ehyb */

@@ -175,6 +175,25 @@ class DistributedBlock:
         check(self.lib, self.lib.ehyb_mg_time_spmv(self.session, warmup, iters, C.byref(ms)), "ehyb_mg_time_spmv")
         return ms.value
 
+    def allreduce_sum(self, vals_d, count):
+        """ehyb_mg_allreduce_sum: count <= 4 doubles at the device address vals_d, summed over the ranks in place
+        (asynchronous, on the session stream; collective)."""
+        check(self.lib, self.lib.ehyb_mg_allreduce_sum(self.session, C.c_void_p(vals_d), int(count)), "ehyb_mg_allreduce_sum")
+
+    def pcg_solve(self, b_local, diag_local=None, max_iters=1000, rtol=1e-10, check_every=8):
+        """ehyb_mg_pcg_solve: distributed (Jacobi-)PCG; this rank's rows of b, diag and x in the block's
+        permuted numbering.  Collective.  Returns (x_local, info)."""
+        b = np.ascontiguousarray(b_local, np.float64)
+        x = np.empty_like(b)
+        d = np.ascontiguousarray(diag_local, np.float64) if diag_local is not None else None
+        o = L.PcgOpts(int(max_iters), float(rtol), int(check_every))
+        r = L.PcgResult()
+        check(self.lib, self.lib.ehyb_mg_pcg_solve(self.session, d.ctypes.data_as(L.c_dbl_p) if d is not None else None,
+                                                   b.ctypes.data_as(L.c_dbl_p), x.ctypes.data_as(L.c_dbl_p), C.byref(o), C.byref(r)),
+              "ehyb_mg_pcg_solve")
+        return x, dict(iters=r.iters, converged=bool(r.converged), rel_residual=r.rel_residual,
+                       true_rel_residual=r.true_rel_residual, ms=r.ms)
+
     def free(self):
         if self.session:
             self.lib.ehyb_mg_session_free(self.session)

@@ -286,7 +286,15 @@ int ehyb_get_y(ehyb_handle *h, double *y_h);
  * session stream, after `warmup` untimed ones.  *ms_total = elapsed milliseconds.
  * If kernel_ms != NULL it receives the summed duration of the main kernel alone, measured
  * with per-launch events in a second pass of the same length. */
+/* y = A x and *dot_d += x . y in ONE launch (p.Ap of a CG iteration; dot_d in device memory, not
+ * zeroed here).  ehyb_spmv_dot_supported: 1 where the product is a single staged / persistent launch. */
+int ehyb_spmv_dot_supported(const ehyb_handle *h);
+int ehyb_spmv_dot(ehyb_handle *h, const double *x_d, double *y_d, double *dot_d);
+int ehyb_spmv_dot_host(ehyb_handle *h, const double *x_h, double *y_h, double *dot_h); /* host vectors, synchronous */
 int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_total, float *kernel_ms);
+/* The same with a COLD L2: `flush_bytes` of scratch memory (>= 2 x the L2 size) are overwritten before
+ * every product, each product is timed by its own event pair; *ms_sum = their sum over `iters`. */
+int ehyb_time_spmv_flushed(ehyb_handle *h, int warmup, int iters, size_t flush_bytes, float *ms_sum);
 /* Number of kernel launches one product issues (1, or 2 when the overflow list is not empty). */
 int ehyb_launches_per_spmv(const ehyb_handle *h);
 int ehyb_sync(ehyb_handle *h);
@@ -330,6 +338,8 @@ void ehyb_pcg_opts_default(ehyb_pcg_opts *o);
  * in the same numbering for Jacobi preconditioning, or NULL for plain CG. */
 int ehyb_pcg_solve(ehyb_handle *h, const double *diag_h, const double *b_h, double *x_h, const ehyb_pcg_opts *opts,
                    ehyb_pcg_result *res);
+/* CUDA device of the session */
+int ehyb_session_device(const ehyb_handle *h);
 /* name of the kernel that computes the session's products */
 const char *ehyb_session_kernel(const ehyb_handle *h);
 /* rows and columns of the session's operator */
@@ -407,6 +417,21 @@ int ehyb_mg_time_spmv(ehyb_mg_session *s, int warmup, int iters, float *ms_total
 int ehyb_mg_spmv_host_batch(ehyb_mg_session *s, const double *const *x_h, double *const *y_h, int count);
 /* Kernel launches one distributed product issues. */
 int ehyb_mg_launches_per_spmv(const ehyb_mg_session *s);
+/* In-stream all-reduce (sum over the ranks) of count <= 4 doubles at vals_d, on the session stream:
+ * what a distributed solver needs for its dot products.  Collective.  Peer-memory sessions exchange
+ * the partial sums through a mailbox every rank maps and add them in rank order (the same bits on
+ * every GPU); NCCL sessions call ncclAllReduce. */
+int ehyb_mg_allreduce_sum(ehyb_mg_session *s, double *vals_d, int count);
+/* ehyb_mg_spmv with the fused dot of ehyb_spmv_dot: *dot_d += x_own . y over THIS rank's rows. */
+int ehyb_mg_spmv_dot_supported(const ehyb_mg_session *s);
+int ehyb_mg_spmv_dot(ehyb_mg_session *s, double *x_d, double *y_d, double *dot_d);
+int ehyb_mg_session_ranks(const ehyb_mg_session *s, int *rank, int *nranks);
+/* Distributed (preconditioned) conjugate gradients: ehyb_pcg_solve over the ranks' blocks.  Collective;
+ * every rank passes ITS rows of b, of the diagonal and of x (the block's permuted numbering, n local
+ * entries).  The dot products are summed over the GPUs by ehyb_mg_allreduce_sum, in rank order: all
+ * ranks see the same residuals and stop in the same iteration. */
+int ehyb_mg_pcg_solve(ehyb_mg_session *s, const double *diag_h, const double *b_h, double *x_h, const ehyb_pcg_opts *opts,
+                      ehyb_pcg_result *res);
 /* Every rank must have finished its products before any rank frees its session (barrier). */
 void ehyb_mg_session_free(ehyb_mg_session *s);
 /* Rows of z-planes [z0, z1) of the 27-point stencil on nx x ny x nz (full rows, global

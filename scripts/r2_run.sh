@@ -1,5 +1,7 @@
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "overflow or power_law or general" ) > gpurun_out/r2_pytest_ovf.log 2>&1; tail -15 gpurun_out/r2_pytest_ovf.log
-timeout 400 python scripts/rmat_variants.py --scale 24 --iters 30 > gpurun_out/r2_rmat24_v2.log 2>&1; tail -14 gpurun_out/r2_rmat24_v2.log
-timeout 400 python bench.py > gpurun_out/r2_bench_n1_b.json 2> gpurun_out/r2_bench_n1_b.err; tail -c 600 gpurun_out/r2_bench_n1_b.err; python -c "
-import json; d=json.loads(open('gpurun_out/r2_bench_n1_b.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value']); print(d['comparisons'].get('config1_l2'))"
+( time timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_driver.py tests/test_gpu_solver.py -m gpu -q -x --durations=8 ) > gpurun_out/r2_pytest_gpu_n2.log 2>&1; tail -30 gpurun_out/r2_pytest_gpu_n2.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/r2_bench_n2_512.json 2> gpurun_out/r2_bench_n2_512.err; tail -c 400 gpurun_out/r2_bench_n2_512.err; python -c "
+import json
+for l in open('gpurun_out/r2_bench_n2_512.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['config']['workload'][:70], d['parity'])"

@@ -14,35 +14,50 @@ ap.add_argument("--scale", type=int, default=22)
 ap.add_argument("--iters", type=int, default=30)
 ap.add_argument("--variants", default="")
 ap.add_argument("--no-cusparse", action="store_true")
+ap.add_argument("--order", default="blocks", choices=["blocks", "degree"],
+                help="level-1 numbering: contiguous blocks of the generator's numbering, or columns by descending reference count (the hubs first)")
 a = ap.parse_args()
 t = time.time()
 n, fi, fj, fv = api.gen_rmat(a.scale, 16, seed=1, add_diagonal=False)
 x = np.random.default_rng(0).uniform(-0.1, 0.1, n)
 m = api.CooMatrix.from_general(n, fi, fj, fv, x)
+if a.order == "degree":
+    # 4 096-vertex partitions in descending order of the column reference counts: the permuted numbering
+    # starts with the hubs, so the x entries most gathers go to share a few hundred cache lines
+    cnt = np.bincount(fj, minlength=n)
+    rank = np.empty(n, np.int64)
+    rank[np.argsort(-cnt, kind="stable")] = np.arange(n)
+    P = max(1, n // 4096)
+    m.set_plan(P, 4096, 1)
+    part = (rank * P // n).astype(np.uint32)
+    del cnt, rank
+else:
+    pl = api.plan(n)
+    m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
+    part = (np.arange(n, dtype=np.int64) * pl.nParts // n).astype(np.uint32)
 del fi, fj, fv
-pl = api.plan(n)
-m.set_plan(pl.nParts, pl.W, pl.ctasPerPart)
-m.reorder_with_partition((np.arange(n, dtype=np.int64) * pl.nParts // n).astype(np.uint32))
+m.reorder_with_partition(part)
 lay = api.Layout(m)
 st = lay.stats()
-print(f"rmat scale {a.scale}: n={n} nnz={st['nnz']} host {time.time()-t:.1f}s; overflow {st['nnzOverflow']} algBytes {st['algBytes']} COO formatBytes {st['formatBytes']}", flush=True)
+print(f"rmat scale {a.scale}, order {a.order}: n={n} nnz={st['nnz']} host {time.time()-t:.1f}s; overflow {st['nnzOverflow']} algBytes {st['algBytes']} COO formatBytes {st['formatBytes']}", flush=True)
 xr = m.vector_reorder(x)
 orc = O.Oracle()
 arr = m.arrays()
 y_ref = orc.csr_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
 absAx = orc.csr_abs_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
-VARIANTS = (("default", "stream: 128-entry tiles x 32 warps, 3 slots, 8192 hubs", {}),
-            ("tg8", "stream: 256-entry tiles x 16 warps, 3 slots", {"EHYB_OVF_TG": "8"}),
-            ("slots2", "stream: 128-entry tiles, 2 slots", {"EHYB_OVF_SLOTS": "2"}),
-            ("slots4", "stream: 128-entry tiles, 4 slots, 2048 hubs", {"EHYB_OVF_SLOTS": "4", "EHYB_OVF_HUBS": "2048"}),
+VARIANTS = (("default", "stream: 128-entry tiles x 32 warps, 2 slots, no hubs, 1 column block", {}),
+            ("k2", "stream: 2 column blocks", {"EHYB_OVF_COLBLOCKS": "2"}),
+            ("k4", "stream: 4 column blocks", {"EHYB_OVF_COLBLOCKS": "4"}),
+            ("k8", "stream: 8 column blocks", {"EHYB_OVF_COLBLOCKS": "8"}),
             ("hubs4k", "stream: 4096 hubs", {"EHYB_OVF_HUBS": "4096"}),
-            ("nohubs", "stream: no hubs", {"EHYB_OVF_HUBS": "0"}),
+            ("hubs8k", "stream: 8192 hubs", {"EHYB_OVF_HUBS": "8192"}),
+            ("slots3", "stream: 3 slots", {"EHYB_OVF_SLOTS": "3"}),
             ("coo", "COO list + atomics (round 1)", {"EHYB_OVF_STREAM": "0"}))
 want = [w for w in a.variants.split(",") if w]
 for key, name, env in VARIANTS:
     if want and key not in want:
         continue
-    for k in ("EHYB_OVF_HUBS", "EHYB_OVF_STREAM", "EHYB_OVF_TG", "EHYB_OVF_SLOTS"):
+    for k in ("EHYB_OVF_HUBS", "EHYB_OVF_STREAM", "EHYB_OVF_TG", "EHYB_OVF_SLOTS", "EHYB_OVF_COLBLOCKS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     s = api.Session(lay)
@@ -53,7 +68,7 @@ for key, name, env in VARIANTS:
     ms = s.time_spmv(5, a.iters)
     ms = ms[0] if isinstance(ms, tuple) else ms
     per = ms / a.iters
-    print(f"{name:52s} {per*1e3:8.1f} us  {2*st['nnz']/(per*1e6):7.1f} GFLOP/s  {st['algBytes']/(per*1e6):7.1f} GB/s alg  gate fails {bad}  bit-reproducible {same}  kernel {s.kernel_name()}", flush=True)
+    print(f"{name:52s} {per*1e3:8.1f} us  {2*st['nnz']/(per*1e6):7.1f} GFLOP/s  {st['algBytes']/(per*1e6):7.1f} GB/s alg  gate fails {bad}  bit-reproducible {same}  kernel {s.kernel_name()} launches {s.launches_per_spmv()}", flush=True)
     s.free()
 cus = os.path.join(ROOT, "ehyb_spmv_gpu_b200", "lib", "libehyb_cusparse.so")
 if os.path.exists(cus) and not a.no_cusparse:

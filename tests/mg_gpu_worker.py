@@ -106,6 +106,40 @@ def run_grid(rank, world, dist, exchange, grid, level1, products):
         y_ref, absAx = orc.stencil27_rows_product(grid, nat, 1.0 + 0.25 * i, 0.003 * i)
         assert np.all(np.abs(yh[i] - y_ref) <= 1e-12 * absAx), "rank %d host batch product %d outside the gate" % (rank, i)
     assert not blk.timed_out()
+    # scalar all-reduce over peer memory (the dots of a distributed solver): 7 of them queued without host
+    # synchronisation, every one with its own values; every rank must hold the SAME bits afterwards
+    vals = torch.zeros((7, 4), dtype=torch.float64, device="cuda")
+    for i in range(7):
+        vals[i] = torch.tensor([(rank + 1) * (i + 1), 0.1 * (rank + 1) + i, 1e-3 * (rank - 0.5) * (i + 2), float(rank == i % world)], dtype=torch.float64)
+    torch.cuda.synchronize()
+    dist.barrier()
+    for i in range(7):
+        blk.allreduce_sum(vals[i].data_ptr(), 1 + i % 4)
+    L.check(lib, lib.ehyb_sync(blk.handle), "ehyb_sync")
+    torch.cuda.synchronize()
+    got = vals.cpu().numpy()
+    for i in range(7):
+        cnt = 1 + i % 4
+        mine = np.array([(rank + 1) * (i + 1), 0.1 * (rank + 1) + i, 1e-3 * (rank - 0.5) * (i + 2), float(rank == i % world)])
+        want = np.zeros(4)
+        for g in range(world):                      # rank order, as the kernel adds
+            want += np.array([(g + 1) * (i + 1), 0.1 * (g + 1) + i, 1e-3 * (g - 0.5) * (i + 2), float(g == i % world)])
+        assert np.array_equal(got[i, :cnt], want[:cnt]), "rank %d all-reduce %d: %s != %s" % (rank, i, got[i, :cnt], want[:cnt])
+        assert np.array_equal(got[i, cnt:], mine[cnt:]), "rank %d all-reduce %d touched values beyond its count" % (rank, i)
+    assert not blk.timed_out()
+    # distributed Jacobi-PCG: A x = b with b = A x_true from the closed form; all ranks stop in the same iteration
+    x_true = orc.x_of_global(nat, 1.0, 0.0)
+    b_loc, _ = orc.stencil27_rows_product(grid, nat, 1.0, 0.0)
+    for jacobi in (True, False):
+        xs_, info = blk.pcg_solve(b_loc, np.full(blk.n, 26.0) if jacobi else None, max_iters=3000, rtol=1e-10, check_every=4)
+        infos = [None] * world
+        dist.all_gather_object(infos, (info["iters"], info["converged"], info["rel_residual"], info["true_rel_residual"]))
+        assert all(i == infos[0] for i in infos), "the ranks disagree about the solve: %s" % (infos,)
+        assert info["converged"] and info["true_rel_residual"] <= 1e-8, info
+        err2 = torch.tensor([float(np.sum((xs_ - x_true) ** 2)), float(np.sum(x_true ** 2))], dtype=torch.float64)
+        dist.all_reduce(err2)
+        assert float(err2[0]) <= (1e-6 ** 2) * float(err2[1]), "rank %d: PCG solution off: %s" % (rank, err2)
+    assert not blk.timed_out()
     ms = blk.time_spmv(3, 50)
     kname = blk.kernel_name()
     dist.barrier()
@@ -113,7 +147,8 @@ def run_grid(rank, world, dist, exchange, grid, level1, products):
     dec.free()
     dist.barrier()
     dist.destroy_process_group()
-    print("rank %d ok (grid path, kernel %s, %d peers, %.1f us/product)" % (rank, kname, int(np.count_nonzero(blk.recvCount)), ms / 50 * 1e3))
+    print("rank %d ok (grid path, kernel %s, %d peers, %.1f us/product; distributed PCG %d iterations, %.1f us each)"
+          % (rank, kname, int(np.count_nonzero(blk.recvCount)), ms / 50 * 1e3, info["iters"], info["ms"] * 1e3 / max(info["iters"], 1)))
 
 
 def main():

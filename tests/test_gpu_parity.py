@@ -191,14 +191,17 @@ def test_persistent_kernel_bit_exact_and_gate(orc, kind, dims, P, W):
     s2.free(); s3.free(); lay.free(); m.free()
 
 
+@pytest.mark.parametrize("blocks", [1, 3])
 @pytest.mark.parametrize("case", ["rmat_all_overflow", "rmat_slices_plus_stream", "stencil_no_cache", "one_long_row"])
-def test_overflow_stream_is_deterministic(orc, case, monkeypatch):
+def test_overflow_stream_is_deterministic(orc, case, blocks, monkeypatch):
     """Large overflow lists run as a CSR-like stream (host/ovfstream.c, ehyb_ovfstream_kernel): hub columns
     in shared memory, row segments summed by warp shuffles, rows that span warp tiles through carry slots
     and a fix-up kernel - no atomics.  EHYB_DETERMINISTIC=1 selects it for lists of any length.  Bars: the
     accuracy gate, and y BIT-IDENTICAL between products and between sessions (the COO kernel's atomics do
-    not give that)."""
+    not give that).  blocks = 3: the list cut into three column blocks, streamed one after the other (what
+    keeps a power-law matrix's gathers in L2; a large x does that by itself, here it is forced)."""
     monkeypatch.setenv("EHYB_DETERMINISTIC", "1")
+    monkeypatch.setenv("EHYB_OVF_COLBLOCKS", str(blocks))
     if case.startswith("rmat"):
         n, fi, fj, fv = api.gen_rmat(14, 16, seed=5, add_diagonal=False)
         m = api.CooMatrix.from_general(n, fi, fj, fv, util.x_random(n, 1))
@@ -223,7 +226,7 @@ def test_overflow_stream_is_deterministic(orc, case, monkeypatch):
     st = lay.stats()
     assert st["nOverflow"] > 0
     s = api.Session(lay)
-    assert s.launches_per_spmv() == (2 if st["nnzEll"] + st["nnzRemInSlice"] == 0 else 3)
+    assert s.launches_per_spmv() == 2 * blocks + (0 if st["nnzEll"] + st["nnzRemInSlice"] == 0 else 1)
     a = m.arrays()
     ys = []
     for seed in (7, 8):

@@ -61,3 +61,46 @@ def test_pcg_matches_numpy_pcg(orc, kind, dims, P, W, jacobi):
     x0, zero = s.pcg_solve(np.zeros(n), None)
     assert zero["converged"] and zero["iters"] == 0 and not x0.any()
     s.free(); lay.free(); m.free()
+
+
+@pytest.mark.parametrize("kernel", ["persistent", "staged"])
+def test_product_with_fused_dot(orc, kernel):
+    """ehyb_spmv_dot: y bit-identical to the plain product, x . y equal to the host's dot product of the same
+    vectors (the p.Ap of a CG iteration is taken from the x window while y is stored)."""
+    kind, dims = "st27", (40, 40, 40)
+    n = util.lower_entries(kind, dims)[0]
+    P, W = (450, 192) if kernel == "persistent" else (20, 3264)
+    m = util.product_pipeline(kind, dims, P, W, 1)
+    lay = api.Layout(m)
+    s = api.Session(lay, kernel=api.KERNEL_PERSISTENT if kernel == "persistent" else api.KERNEL_STAGED)
+    assert s.kernel_name() == ("ehyb_persistent_kernel" if kernel == "persistent" else "ehyb_staged_kernel")
+    assert s.spmv_dot_supported()
+    for seed in (1, 2, 3):
+        x = util.x_random(n, seed)
+        y_plain = s.spmv_host(x)
+        y, d = s.spmv_dot_host(x)
+        assert np.array_equal(y, y_plain), "the fused-dot build of the kernel computes another y"
+        ref = float(np.dot(x, y_plain))
+        assert abs(d - ref) <= 1e-12 * float(np.dot(np.abs(x), np.abs(y_plain))), (d, ref)
+    s.free(); lay.free(); m.free()
+
+
+def test_pcg_on_another_device_than_the_current_one(orc):
+    """the solver allocates and launches on the SESSION's device whatever the caller's
+    current device is, and restores it."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    kind, dims = "lap2d", (64, 64)
+    n = util.lower_entries(kind, dims)[0]
+    m = util.product_pipeline(kind, dims, 4, 1088, 1)
+    a = m.arrays()
+    lay = api.Layout(m)
+    s = api.Session(lay, device=1)
+    torch.cuda.set_device(0)
+    x_true = util.x_random(n, 5)
+    b = orc.csr_spmv(a["rowIdx"], a["J"], a["V"], x_true)
+    x, info = s.pcg_solve(b, None, max_iters=2000, rtol=1e-10)
+    assert info["converged"] and np.linalg.norm(x - x_true) <= 1e-7 * np.linalg.norm(x_true)
+    assert torch.cuda.current_device() == 0
+    s.free(); lay.free(); m.free()
