@@ -1782,7 +1782,14 @@ __global__ void __launch_bounds__(kThreads, 1) ehyb_ovfstream_kernel(const __gri
         }
 #pragma unroll
         for (int u = 0; u < TG; ++u) prod[u] *= lds_f64(slot + (static_cast<uint32_t>(u) * 32u + lane) * 8u);
-        __syncwarp(); /* every lane has taken what it needs from the slot: refill it */
+        /* Refill the slot - but only when every lane's reads of it have been PERFORMED, not merely
+         * issued: this kernel keeps the LSU pipe ~80 % busy with 32-wavefront gathers, a shared-memory
+         * load can wait in its queue for microseconds, and the bulk copy of the next tile (async proxy)
+         * would then land under it.  Measured: without the fence a few rows of R-MAT 24 left the gate,
+         * more with more slots (profiles/r2_notes.md).  fence.proxy.async orders each lane's generic-proxy
+         * reads before later async-proxy writes; the barrier extends that to the lane that issues. */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
         if (lane == 0) {
             const int64_t t = tile + static_cast<int64_t>(slots) * Wt;
             if (t < a.nTiles) {

@@ -52,6 +52,7 @@ VARIANTS = (("default", "stream: 128-entry tiles x 32 warps, 2 slots, no hubs, 1
             ("hubs4k", "stream: 4096 hubs", {"EHYB_OVF_HUBS": "4096"}),
             ("hubs8k", "stream: 8192 hubs", {"EHYB_OVF_HUBS": "8192"}),
             ("slots3", "stream: 3 slots", {"EHYB_OVF_SLOTS": "3"}),
+            ("slots4", "stream: 4 slots", {"EHYB_OVF_SLOTS": "4"}),
             ("coo", "COO list + atomics (round 1)", {"EHYB_OVF_STREAM": "0"}))
 want = [w for w in a.variants.split(",") if w]
 for key, name, env in VARIANTS:
