@@ -410,12 +410,13 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
      * host/ovfstream.c: 12.4 instead of 16 bytes per entry, staged by bulk copies, hub columns in
      * shared memory, no atomics (bit-reproducible y).  Not for peer-memory sessions: there the
      * overflow kernel waits for the neighbours' flags.
-     * Shape: 128-entry tiles x 32 warps (64 registers): 4 096 gathers per SM in flight;
-     * $EHYB_OVF_SLOTS staging slots per warp (default 2) and $EHYB_OVF_HUBS hub columns in shared
-     * memory (default 0).  Both defaults are the SMALLEST shared-memory footprint on purpose: what is
-     * not shared memory is L1, and on a power-law matrix the L1 hits of the hot columns are worth more
-     * than a third slot or an explicit hub cache (R-MAT 24, per product: 2 slots / no hubs 2 011 us,
-     * 2 slots + 8 192 hubs 2 247, 3 slots + 8 192 hubs 3 447; profiles/r2_notes.md). */
+     * Shape: 128-entry tiles x 32 warps (56 registers), four consecutive entries per lane: 4 096
+     * gathers per SM in flight; $EHYB_OVF_SLOTS staging slots per warp (default 2) and $EHYB_OVF_HUBS
+     * hub columns in shared memory (default 2 048).  Small shared-memory footprints on purpose: what is
+     * not shared memory is L1, and on a power-law matrix the L1 hits of the warm columns are worth more
+     * than a third slot or a large explicit hub cache (R-MAT 24, per product: 2 slots with 0 / 1 024 /
+     * 2 048 / 4 096 / 6 144 / 8 192 / 12 288 hubs 1 599 / 1 498 / 1 469 / 1 535 / 1 511 / 1 851 / 2 964 us,
+     * 3 slots without hubs 1 661; profiles/r2_notes.md). */
     h->ovfStream = 0;
     if (h->nOvf > 0 && !peerSession &&
         (env_int("EHYB_DETERMINISTIC", 0) || h->nOvf >= (int64_t)env_int("EHYB_OVF_STREAM_MIN", 1 << 20)) && env_int("EHYB_OVF_STREAM", 1)) {
@@ -425,7 +426,7 @@ static int upload_impl(const ehyb_layout_view *v, const ehyb_session_opts *o, eh
         if (slots > kStreamMaxSlots) slots = kStreamMaxSlots;
         const int warps = tg == 8 ? 16 : 32;
         const size_t staging = (size_t)kStreamHeader + (size_t)warps * slots * EHYB_OVF_TILE_BYTES(tg);
-        int hubCap = env_int("EHYB_OVF_HUBS", 0);
+        int hubCap = env_int("EHYB_OVF_HUBS", 2048);
         const int hubMax = staging < prop.sharedMemPerBlockOptin ? (int)((prop.sharedMemPerBlockOptin - staging) / sizeof(double)) : 0;
         if (hubCap > hubMax) hubCap = hubMax;
         if (hubCap < 0) hubCap = 0;

@@ -1759,34 +1759,50 @@ __global__ void __launch_bounds__(kThreads, 1) ehyb_ovfstream_kernel(const __gri
         const uint32_t slot = slot0 + static_cast<uint32_t>(s) * kTileBytes, bar = bar0 + static_cast<uint32_t>(s) * 8u;
         mbar_wait_bounded(bar, (phases >> s) & 1u);
         phases ^= 1u << s;
-        uint32_t c[TG], m[TG];
-        int seg[TG], row[TG];
-        double prod[TG];
-#pragma unroll
-        for (int u = 0; u < TG; ++u) {
-            c[u] = lds_u32(slot + kColOff + (static_cast<uint32_t>(u) * 32u + lane) * 4u);
-            const int2 gm = lds_s32x2(slot + kGrpOff + static_cast<uint32_t>(u) * 8u);
-            m[u] = static_cast<uint32_t>(gm.y);
-            seg[u] = gm.x + __popc(m[u] & lanemaskLe & ~1u);
-        }
+        /* Lane j owns the FOUR CONSECUTIVE entries 4j..4j+3 of the tile: it adds what belongs to one row
+         * serially, and only one value per lane - the sum behind its last row start - goes through a
+         * cross-lane segmented scan: 12 shuffles per tile.  (One entry per lane and a scan per group of
+         * 32 was 60: ncu showed 38 % of the LSU data pipe - the pipe this kernel is bound by - busy
+         * with shared-memory-class wavefronts of which the loads were 8 %: the shuffles.) */
+        static_assert(TG == 4, "four entries per lane");
+        const uint4 cc = lds_u32x4(slot + kColOff + static_cast<uint32_t>(lane) * 16u);
+        const int2 gmA = lds_s32x2(slot + kGrpOff + static_cast<uint32_t>(lane >> 3) * 8u); /* this lane's group of 32: {seg0, mask} */
+        const int2 gm3 = lds_s32x2(slot + kGrpOff + 24u);
+        const int headSeg = static_cast<int>(lds_u32(slot + kGrpOff));
         const uint32_t flags = lds_u32(slot + kFlagOff);
-        /* the gathers of the whole tile, then the rows of the segments that end in this lane (lane 31
-         * always: its sum may be carried into the next group): all in flight together */
+        const uint32_t gmask = static_cast<uint32_t>(gmA.y);
+        const int sh = 4 * (lane & 7);
+        const uint32_t nib = (gmask >> sh) & 0xfu;                /* bit k: entry 4 lane + k starts a new row */
+        const int nStart = __popc(nib);
+        /* segment of the lane's first entry, and the segment BEFORE the lane's first row start (= the one
+         * the entries in front of it, and the lanes before, contribute to) */
+        const int seg0 = gmA.x + __popc(gmask & ((2u << sh) - 1u) & ~1u);
+        const int sB = seg0 - static_cast<int>(nib & 1u);
+        const int tailSeg = gm3.x + __popc(static_cast<uint32_t>(gm3.y) & ~1u);
+        const bool preStore = nStart > 0 && !(lane == 0 && (nib & 1u)); /* a segment ends at this lane's first row start */
+        /* the gathers, and with them the rows of the segments this lane will store: all in flight together */
+        double p[4];
+        {
+            const uint32_t cs[4] = {cc.x, cc.y, cc.z, cc.w};
 #pragma unroll
-        for (int u = 0; u < TG; ++u)
-            prod[u] = (c[u] & EHYB_OVF_HUB_BIT) ? lds_f64(hubAddr + (c[u] & 0x7fffffffu) * 8u) : __ldg(a.x + c[u]); /* (plain launch: x is constant while this grid lives) */
-#pragma unroll
-        for (int u = 0; u < TG; ++u) {
-            const bool tailOfSeg = lane == 31 || ((m[u] >> (lane + 1)) & 1u) != 0u;
-            row[u] = tailOfSeg ? __ldg(a.rowOfSeg + seg[u]) : -1;
+            for (int k = 0; k < 4; ++k)
+                p[k] = (cs[k] & EHYB_OVF_HUB_BIT) ? lds_f64(hubAddr + (cs[k] & 0x7fffffffu) * 8u) : __ldg(a.x + cs[k]); /* (plain launch: x is constant while this grid lives) */
         }
+        const int rowPre = preStore ? __ldg(a.rowOfSeg + sB) : -1;
+        int rowIn[3];
 #pragma unroll
-        for (int u = 0; u < TG; ++u) prod[u] *= lds_f64(slot + (static_cast<uint32_t>(u) * 32u + lane) * 8u);
+        for (int k = 0; k < 3; ++k) rowIn[k] = nStart > k + 1 ? __ldg(a.rowOfSeg + sB + 1 + k) : -1; /* complete segments inside the lane */
+        const int rowTail = lane == 31 ? __ldg(a.rowOfSeg + tailSeg) : -1;
+        {
+            const double2 v01 = lds_f64x2(slot + static_cast<uint32_t>(lane) * 32u);
+            const double2 v23 = lds_f64x2(slot + static_cast<uint32_t>(lane) * 32u + 16u);
+            p[0] *= v01.x; p[1] *= v01.y; p[2] *= v23.x; p[3] *= v23.y;
+        }
         /* Refill the slot - but only when every lane's reads of it have been PERFORMED, not merely
-         * issued: this kernel keeps the LSU pipe ~80 % busy with 32-wavefront gathers, a shared-memory
-         * load can wait in its queue for microseconds, and the bulk copy of the next tile (async proxy)
-         * would then land under it.  Measured: without the fence a few rows of R-MAT 24 left the gate,
-         * more with more slots (profiles/r2_notes.md).  fence.proxy.async orders each lane's generic-proxy
+         * issued: this kernel keeps the LSU pipe busy with 32-wavefront gathers, a shared-memory load
+         * can wait in its queue for microseconds, and the bulk copy of the next tile (async proxy) would
+         * then land under it.  Measured: without the fence a few rows of R-MAT 24 left the gate, more
+         * with more slots (profiles/r2_notes.md).  fence.proxy.async orders each lane's generic-proxy
          * reads before later async-proxy writes; the barrier extends that to the lane that issues. */
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -1798,8 +1814,6 @@ __global__ void __launch_bounds__(kThreads, 1) ehyb_ovfstream_kernel(const __gri
             }
         }
         const bool headCont = (flags & 1u) != 0u, tailCont = (flags & 2u) != 0u;
-        const int headSeg = __shfl_sync(0xffffffffu, seg[0], 0);
-        const int tailSeg = __shfl_sync(0xffffffffu, seg[TG - 1], 31);
         auto store = [&](int sg, int r, double sum) {
             if (r < 0) return; /* the padding entries behind the end of the list */
             const bool isHead = headCont && sg == headSeg, isTail = tailCont && sg == tailSeg;
@@ -1808,31 +1822,34 @@ __global__ void __launch_bounds__(kThreads, 1) ehyb_ovfstream_kernel(const __gri
             else if (a.accumulate) atomicAdd(a.y + r, sum); /* RED.ADD: nobody else adds to this row in this launch, and the warp does not wait for y */
             else a.y[r] = sum;
         };
-        int carrySeg = -1, carryRow = -1;
-        double carry = 0.0;
+        /* inside the lane: `head` = what precedes the first row start, complete segments between two row
+         * starts are stored on the spot, `run` ends as what follows the last row start */
+        double run = 0.0, head = 0.0;
+        int seen = 0;
 #pragma unroll
-        for (int u = 0; u < TG; ++u) {
-            double p = prod[u];
-            /* distance to the head of this lane's segment inside the group (lane 0 counts as a head) */
-            const int dist = lane - (31 - __clz(static_cast<int>((m[u] | 1u) & lanemaskLe)));
-            if (lane == 0 && u > 0) {
-                if (seg[u] == carrySeg) p += carry;              /* continue the carried segment */
-                else store(carrySeg, carryRow, carry);           /* it ended with the previous group */
+        for (int k = 0; k < 4; ++k) {
+            if ((nib >> k) & 1u) {
+                if (seen == 0) head = run;
+                else store(sB + seen, seen == 1 ? rowIn[0] : seen == 2 ? rowIn[1] : rowIn[2], run); /* (no dynamic index: registers) */
+                run = 0.0;
+                ++seen;
             }
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, p, off);
-                if (dist >= off) p += t;
-            }
-            const bool tailOfSeg = lane == 31 || ((m[u] >> (lane + 1)) & 1u) != 0u;
-            const bool carries = lane == 31 && u + 1 < TG; /* may continue in the next group of this tile */
-            if (tailOfSeg && !carries) store(seg[u], row[u], p);
-            if (u + 1 < TG) {
-                carrySeg = __shfl_sync(0xffffffffu, seg[u], 31);
-                carryRow = __shfl_sync(0xffffffffu, row[u], 31);
-                carry = __shfl_sync(0xffffffffu, p, 31);
-            }
+            run += p[k];
         }
+        /* across the lanes: inclusive scan of `run`, restarted at every lane that has a row start */
+        const uint32_t startLanes = __ballot_sync(0xffffffffu, nStart > 0);
+        const uint32_t upto = startLanes & lanemaskLe;
+        const int dist = upto ? lane - (31 - __clz(static_cast<int>(upto))) : lane; /* lanes back to the last restart (or to lane 0) */
+        double sc = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double t = __shfl_up_sync(0xffffffffu, sc, off);
+            if (dist >= off) sc += t;
+        }
+        double before = __shfl_up_sync(0xffffffffu, sc, 1); /* what the lanes before add to the segment that ends here */
+        if (lane == 0) before = 0.0;
+        if (preStore) store(sB, rowPre, before + head);
+        if (lane == 31) store(tailSeg, rowTail, sc);               /* the tile's last segment */
         s = s + 1 == slots ? 0 : s + 1;
     }
 }

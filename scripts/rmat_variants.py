@@ -45,11 +45,16 @@ orc = O.Oracle()
 arr = m.arrays()
 y_ref = orc.csr_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
 absAx = orc.csr_abs_spmv(arr["rowIdx"], arr["J"], arr["V"], xr)
-VARIANTS = (("default", "stream: 128-entry tiles x 32 warps, 2 slots, no hubs, 1 column block", {}),
+VARIANTS = (("default", "stream: 128-entry tiles x 32 warps, 2 slots, 2048 hubs, 1 column block", {}),
+            ("nohubs", "stream: no hubs", {"EHYB_OVF_HUBS": "0"}),
             ("k2", "stream: 2 column blocks", {"EHYB_OVF_COLBLOCKS": "2"}),
             ("k4", "stream: 4 column blocks", {"EHYB_OVF_COLBLOCKS": "4"}),
             ("k8", "stream: 8 column blocks", {"EHYB_OVF_COLBLOCKS": "8"}),
+            ("hubs1k", "stream: 1024 hubs", {"EHYB_OVF_HUBS": "1024"}),
+            ("hubs2k", "stream: 2048 hubs", {"EHYB_OVF_HUBS": "2048"}),
             ("hubs4k", "stream: 4096 hubs", {"EHYB_OVF_HUBS": "4096"}),
+            ("hubs6k", "stream: 6144 hubs", {"EHYB_OVF_HUBS": "6144"}),
+            ("hubs12k", "stream: 12288 hubs", {"EHYB_OVF_HUBS": "12288"}),
             ("hubs8k", "stream: 8192 hubs", {"EHYB_OVF_HUBS": "8192"}),
             ("slots3", "stream: 3 slots", {"EHYB_OVF_SLOTS": "3"}),
             ("slots4", "stream: 4 slots", {"EHYB_OVF_SLOTS": "4"}),
