@@ -53,6 +53,17 @@ def plan(n: int, dev: DeviceInfo | None = None, kernel: int = 2) -> Plan:
     return p
 
 
+def plan_auto(n: int, nnz: int, dev: DeviceInfo | None = None):
+    """ehyb_plan_auto: (plan, kernel) for a matrix of n rows and nnz entries - one partition per SM when it is
+    L2-resident, the persistent kernel's plan up to ~40 entries per row, the staged plan beyond."""
+    lib = L.load()
+    p = Plan()
+    k = C.c_int()
+    dev = dev or device_info_b200()
+    check(lib, lib.ehyb_plan_auto(n, C.c_int64(nnz), C.byref(dev), C.byref(p), C.byref(k)), "ehyb_plan_auto")
+    return p, k.value
+
+
 def plan_reference(n: int, symmetric: bool = True) -> Plan:
     lib = L.load()
     p = Plan()

@@ -114,6 +114,41 @@ int ehyb_plan_kernel(int n, const ehyb_device_info *dev, int kernel, ehyb_plan_t
     return EHYB_OK;
 }
 
+/*
+ * The plan a driver should use for a matrix of n rows and nnz entries, and the kernel it is for:
+ *   - L2-RESIDENT matrices (matrix data + vectors <= 3/4 of L2, the bound below which the session leaves the L2 hints off; BASELINE config 1: 69 MB): ONE
+ *     partition per SM for the staged kernel - all CTAs are resident at once, a product is one wave
+ *     and launches chain through programmatic dependent launch.  Measured on 5-point 1024^2
+ *     (profiles/r2_sweep_config1_*.log): 13.0 us per product, against 16.7 us with the persistent plan
+ *     (3 partitions per CTA: its start-up is the whole cost when the stream comes out of L2), 16.4 us
+ *     with the direct kernel, 22.5 us with 2 partitions per SM;
+ *   - up to ~40 entries per row: the persistent kernel's plan (3 small partitions per SM);
+ *   - denser rows (3-dof elasticity: remainder-cache lists too long for two buffers): the staged plan.
+ */
+int ehyb_plan_auto(int n, int64_t nnz, const ehyb_device_info *dev, ehyb_plan_t *out, int *kernel)
+{
+    if (n <= 0 || nnz < 0 || !dev || !out || dev->sm_count <= 0) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan_auto: bad argument");
+    const int64_t bytes = 10 * nnz + 16 * (int64_t)n;
+    int k = nnz <= 40 * (int64_t)n ? EHYB_KERNEL_PERSISTENT : EHYB_KERNEL_STAGED;
+    if (dev->l2_bytes > 0 && bytes <= (int64_t)dev->l2_bytes / 4 * 3 && n >= 64 * dev->sm_count && !getenv("EHYB_PARTS_PER_SM")) {
+        /* one partition per SM, if its window fits next to the staging slots */
+        long budget = dev->smem_per_sm_bytes - 1024;
+        if (budget > dev->smem_optin_bytes) budget = dev->smem_optin_bytes;
+        budget -= 128L * 1024 + (long)EHYB_DEFAULT_CACHE_CAP * 8 + EHYB_SMEM_RESERVE;
+        int wMax = (int)(budget / 8 - 2);
+        wMax -= wMax % 64;
+        int W = (int)ceil((double)n / dev->sm_count * 1.025);
+        W = (W + 63) / 64 * 64;
+        if (W <= wMax && W <= 65472) {
+            out->nParts = dev->sm_count; out->W = W; out->ctasPerPart = 1; out->threads = 0; out->ctasPerSM = 1;
+            if (kernel) *kernel = EHYB_KERNEL_STAGED;
+            return EHYB_OK;
+        }
+    }
+    if (kernel) *kernel = k;
+    return ehyb_plan_kernel(n, dev, k, out);
+}
+
 int ehyb_plan_reference(int n, int symmetric, ehyb_plan_t *out)
 {
     if (n <= 0 || !out) return ehyb_fail(EHYB_ERR_ARG, "ehyb_plan_reference: bad argument");

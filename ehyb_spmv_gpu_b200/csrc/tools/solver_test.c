@@ -85,12 +85,7 @@ static int finish(int n, const double *yReorder, const int *reorderList, const d
     return failed;
 }
 
-/* Which kernel the partitions are sized for (single GPU).  The persistent kernel double-buffers
- * window + remainder cache, which pays for matrices with short remainder lists (stencils: config 2
- * 92.2 us vs 94.3 us, 256^3 809 vs 840 us); with ~80 entries per row (3-dof elasticity) the lists
- * are too long for two buffers, the session falls back to the staged kernel, and the finer
- * partitioning then costs (config 3: 428 us vs 403 us): those keep the staged plan. */
-static int plan_kernel_for(int64_t n, int64_t nnz) { return nnz <= 40 * n ? EHYB_KERNEL_PERSISTENT : EHYB_KERNEL_STAGED; }
+/* (the partition parameters and the kernel they are sized for: ehyb_plan_auto, csrc/host/plan.c) */
 
 /* mg_driver.c */
 int ehyb_driver_multi_gpu(int G, const char *gen, const char *brickSpec, int iters);
@@ -170,7 +165,7 @@ int main(int argc, char *argv[])
             ehyb_layout_get(L, &v);
             ehyb_plan_t want;
             if (useRefPlan) ehyb_plan_reference(n, sym, &want);
-            else ehyb_plan_kernel(n, &dev, plan_kernel_for(n, v.nnz), &want);
+            else ehyb_plan_auto(n, v.nnz, &dev, &want, NULL);
             if (oP > 0) want.nParts = oP;
             if (oW > 0) want.W = oW;
             if (oK > 0) want.ctasPerPart = oK;
@@ -248,7 +243,7 @@ int main(int argc, char *argv[])
     /* ------------------------------- partition parameters ------------------------------- */
     ehyb_plan_t plan;
     if (useRefPlan) ehyb_plan_reference(A.dimension, symmetric, &plan);
-    else ehyb_plan_kernel(A.dimension, &dev, plan_kernel_for(A.dimension, A.totalNum), &plan);
+    else ehyb_plan_auto(A.dimension, A.totalNum, &dev, &plan, NULL);
     if (oP > 0) plan.nParts = oP;
     if (oW > 0) plan.W = oW;
     if (oK > 0) plan.ctasPerPart = oK;

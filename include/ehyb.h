@@ -86,6 +86,10 @@ int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out);
  * multi-GPU sessions use): EHYB_KERNEL_PERSISTENT sizes the partitions for the persistent kernel
  * of single-GPU sessions (three or more smaller partitions per SM), see plan.c. */
 int ehyb_plan_kernel(int n, const ehyb_device_info *dev, int kernel, ehyb_plan_t *out);
+/* The plan and the kernel (*kernel, may be NULL) a driver should use for n rows and nnz entries: one
+ * partition per SM (staged kernel) when matrix + vectors fit 3/4 of L2, the persistent kernel's plan up
+ * to ~40 entries per row, the staged plan beyond (plan.c). */
+int ehyb_plan_auto(int n, int64_t nnz, const ehyb_device_info *dev, ehyb_plan_t *out, int *kernel);
 /* The reference's own heuristic for an 82/80-SM, 93 KB device, including its int16_t wrap
  * (SURVEY.md Appendix C).  ctasPerPart = 0 where the reference leaves it uninitialised. */
 int ehyb_plan_reference(int n, int symmetric, ehyb_plan_t *out);

@@ -231,3 +231,22 @@ def test_mtmetis_helper_and_matrix_reorder_entry_point(orc):
         assert np.array_equal(a[k], ro[k]), k
     assert np.array_equal(part, util.metis_partition(kind, dims, P))  # 1 thread: deterministic
     m.free()
+
+
+def test_plan_auto_picks_by_size_and_density():
+    """ehyb_plan_auto (plan.c): one partition per SM for the staged kernel when matrix + vectors fit 3/4 of
+    L2 (BASELINE config 1), the persistent kernel's plan up to ~40 entries per row (config 2), the staged
+    plan for denser rows (config 3)."""
+    dev = api.device_info_b200()
+    p1, k1 = api.plan_auto(1048576, 5238784, dev)               # config 1: 5-point 1024^2, 61 MB
+    assert k1 == api.KERNEL_STAGED and p1.nParts == dev.sm_count and p1.ctasPerPart == 1
+    assert p1.W >= -(-1048576 // dev.sm_count) and p1.W % 64 == 0 and p1.W <= 65472
+    p2, k2 = api.plan_auto(2097152, 55742968, dev)              # config 2: the plan bench.py times
+    assert k2 == api.KERNEL_PERSISTENT and (p2.nParts, p2.W) == (444, 4864)
+    pr = api.plan(2097152, dev, kernel=api.KERNEL_PERSISTENT)
+    assert (p2.nParts, p2.W, p2.ctasPerPart) == (pr.nParts, pr.W, pr.ctasPerPart)
+    p3, k3 = api.plan_auto(3000000, 238172328, dev)             # config 3: ~79 entries per row
+    ps = api.plan(3000000, dev)
+    assert k3 == api.KERNEL_STAGED and (p3.nParts, p3.W) == (ps.nParts, ps.W)
+    p4, k4 = api.plan_auto(4096, 20000, dev)                    # too small for a partition per SM: the generic small-matrix rule
+    assert p4.nParts >= 1 and p4.W >= 64
