@@ -23,8 +23,9 @@ The JSON line carries: value (GFLOP/s = 2 nnz / t, all ranks), roofline (algorit
 the dominant kernel / its CUDA-event duration, against MEASURED_PEAKS.json; traffic = DRAM bytes
 per launch from the committed ncu capture), e2e (the same metric through the host-buffer entry
 point, H2D of x and D2H of y inside the timed region), cpu_baseline (the oracle's CSR product on
-the host cores; rank 0, N=1 only), comparisons (cuSPARSE CSR on the same GPU, after the timed
-region), clocks.  `--impl reference` times the reference's CPU path (CSR over its own arrays, all
+the host cores; rank 0, N=1 only), comparisons (after the timed region, same GPU: cuSPARSE CSR, the
+reference's own kernel.cu recompiled for sm_100a, and BASELINE.json configs[0] - 5-point 1024^2,
+L2-resident - with a warm and with a flushed L2), clocks.  `--impl reference` times the reference's CPU path (CSR over its own arrays, all
 host threads).  The oracle is used only as checker and CPU baseline, never on the product path.
 """
 from __future__ import annotations

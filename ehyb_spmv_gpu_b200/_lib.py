@@ -119,7 +119,7 @@ EXPORTS = [
     "ehyb_plan", "ehyb_plan_kernel", "ehyb_plan_reference", "ehyb_build_graph", "ehyb_set_partitioner", "ehyb_partition_graph",
     "ehyb_reorder_with_partition", "ehyb_reorder", "ehyb_partition_blocks", "ehyb_free_host",
     "ehyb_layout_build", "ehyb_layout_build_csr", "ehyb_layout_get", "ehyb_layout_to_reference",
-    "ehyb_layout_free", "ehyb_layout_save", "ehyb_layout_load", "ehyb_cache_save", "ehyb_cache_load",
+    "ehyb_layout_free", "ehyb_layout_save", "ehyb_layout_load", "ehyb_cache_save", "ehyb_cache_load", "ehyb_cache_set_options_tag",
     "ehyb_session_opts_default", "ehyb_upload", "ehyb_spmv", "ehyb_spmv_host",
     "ehyb_spmv_host_batch", "ehyb_session_vectors", "ehyb_plan_auto", "ehyb_set_x", "ehyb_get_y", "ehyb_time_spmv", "ehyb_time_spmv_flushed",
     "ehyb_launches_per_spmv", "ehyb_pcg_opts_default", "ehyb_pcg_solve", "ehyb_session_size", "ehyb_session_kernel", "ehyb_trace_read", "ehyb_sync", "ehyb_stream", "ehyb_free", "ehyb_describe",

@@ -36,6 +36,13 @@ typedef struct {
     int64_t reserved[4];
 } cache_header;
 
+/* Options the layout was built with that the header's partition parameters do not tell (er_fill,
+ * cache_cap, the partitioner and its pieces, ...): the caller folds them into one 64-bit tag
+ * (ehyb_cache_set_options_tag); a cache written under another tag is rejected like one with other
+ * partition parameters.  0 (the default) on both sides = no options to tell apart. */
+static uint64_t g_optionsTag = 0;
+void ehyb_cache_set_options_tag(uint64_t tag) { g_optionsTag = tag; }
+
 /* layout.c */
 int ehyb_layout_export_arrays(const ehyb_layout *L, const void **arrays, int64_t *bytes, int max);
 int ehyb_layout_import(const ehyb_layout_view *scalars, void *const *arrays, ehyb_layout **out);
@@ -106,6 +113,7 @@ int ehyb_cache_save(const char *path, const char *source_path, const ehyb_layout
     h.nLongRows = v.nLongRows; h.algBytes = v.algBytes; h.formatBytes = v.formatBytes;
     h.hasVectors = reorderList && x && y_golden && absAx;
     h.symmetric = symmetric;
+    h.reserved[0] = (int64_t)g_optionsTag;
     if ((rc = source_identity(source_path, &h))) return rc;
     char tmp[4096];
     snprintf(tmp, sizeof tmp, "%s.tmp%ld", path, (long)getpid());
@@ -153,6 +161,11 @@ int ehyb_cache_load(const char *path, const char *source_path, const ehyb_plan_t
     }
     if (plan && (plan->nParts != h.nParts || plan->W != h.W || (plan->ctasPerPart > 0 ? plan->ctasPerPart : 1) != h.ctasPerPart)) {
         rc = ehyb_fail(EHYB_ERR_IO, "cache: %s holds P=%d W=%d K=%d, wanted P=%d W=%d K=%d", path, h.nParts, h.W, h.ctasPerPart, plan->nParts, plan->W, plan->ctasPerPart);
+        goto done;
+    }
+    if ((uint64_t)h.reserved[0] != g_optionsTag) {
+        rc = ehyb_fail(EHYB_ERR_IO, "cache: %s was built with other layout / partitioner options (tag %llx, this run %llx)", path,
+                       (unsigned long long)h.reserved[0], (unsigned long long)g_optionsTag);
         goto done;
     }
     if (h.n <= 0 || h.n > 0x7fffffff || h.nParts <= 0 || h.nSlices < 0 || h.blobBytes < 0 || h.nOverflow < 0 || h.cacheTotal < 0) { rc = ehyb_fail(EHYB_ERR_IO, "cache: %s has an inconsistent header", path); goto done; }

@@ -153,6 +153,16 @@ int main(int argc, char *argv[])
     /* ------------------------------- binary cache of a previous run ------------------------------- */
     char cachePath[1100] = "";
     if (fileName[0]) snprintf(cachePath, sizeof cachePath, "%s.ehyb", fileName);
+    {   /* what shapes the layout besides P / W / K: a cache built under other settings is rebuilt */
+        const char *fe = getenv("EHYB_ER_FILL");
+        double fill = fe && fe[0] ? atof(fe) : -1.0;
+        uint64_t tag = 0xcbf29ce484222325ULL, bits;
+        memcpy(&bits, &fill, sizeof bits);
+        tag = (tag ^ bits) * 0x100000001b3ULL;
+        tag = (tag ^ (uint64_t)(uint32_t)ehyb_get_partition_pieces()) * 0x100000001b3ULL;
+        tag = (tag ^ (uint64_t)useRefPlan) * 0x100000001b3ULL;
+        ehyb_cache_set_options_tag(tag ? tag : 1);
+    }
     if (useCache && cachePath[0] && access(cachePath, R_OK) == 0) {
         const double t0 = now_s();
         ehyb_layout *L = NULL;

@@ -244,6 +244,10 @@ void ehyb_layout_builder_abort(ehyb_layout_builder *B);
  * other parameters.  Output arrays are malloc'd (ehyb_free_host). */
 int ehyb_layout_save(const ehyb_layout *L, const char *path);
 int ehyb_layout_load(const char *path, ehyb_layout **out);
+/* Options that shaped the layout but are not partition parameters (er_fill, cache_cap, the partition
+ * stage, ...), folded by the caller into one tag: a cache written under another tag is rejected.
+ * Process-wide; 0 = none (the default). */
+void ehyb_cache_set_options_tag(uint64_t tag);
 int ehyb_cache_save(const char *path, const char *source_path, const ehyb_layout *L, int symmetric, const int *reorderList,
                     const double *x, const double *y_golden, const double *absAx);
 int ehyb_cache_load(const char *path, const char *source_path, const ehyb_plan_t *plan, ehyb_layout **L, int *n,

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-( time timeout 1000 python -m pytest tests -m gpu -q --durations=6 ) > gpurun_out/r2_pytest_gpu_final.log 2>&1; tail -14 gpurun_out/r2_pytest_gpu_final.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -2 gpurun_out/r2_smoke.log
-timeout 400 python bench.py > gpurun_out/r2_bench_n1_final.json 2> gpurun_out/r2_bench_n1_final.err; python -c "
-import json; d=json.loads(open('gpurun_out/r2_bench_n1_final.json').read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['cpu_baseline']['value'], d['clocks'])"
-timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2>/dev/null; cut -c1-300 gpurun_out/r2_bench_reference_arm.json
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ovfstream_kernel" --launch-skip 3 --launch-count 1 -o gpurun_out/r2_ovfstream_final_full -f python scripts/rmat_variants.py --scale 24 --iters 2 --variants default --no-cusparse > gpurun_out/ncu_ovf3.log 2>&1; tail -2 gpurun_out/ncu_ovf3.log
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 100 --warmup 10 > gpurun_out/r2_bench_n8_512.json 2> gpurun_out/r2_bench_n8_512.err; tail -c 300 gpurun_out/r2_bench_n8_512.err; python -c "
+import json
+for l in open('gpurun_out/r2_bench_n8_512.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['config']['peers_per_gpu_min'], d['config']['peers_per_gpu_max'], d['config']['halo_x_entries_max_per_gpu'], d['parity'])"
+timeout 200 ./bin/spmv.out -G 8 -g st27:512:512:512 -i 100 > gpurun_out/r2_spmv_out_G8_512.log 2>&1; tail -12 gpurun_out/r2_spmv_out_G8_512.log | cut -c1-250

@@ -3,6 +3,8 @@ is bit-identical to the built one, maps back onto the reference arrays the same 
 that does not belong to the source file / parameters, or is damaged, is rejected."""
 import os
 
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -55,6 +57,18 @@ def test_pipeline_cache_and_rejections(tmp_path):
     # the product evaluated from the cached arrays
     assert np.allclose(util.layout_spmv(back.raw(), m.vector_reorder(x)), m.vector_reorder(m.y_golden), rtol=0, atol=1e-12)
     back.free()
+    # a cache written under other layout / partitioner options (the caller's tag) is rejected, not reused
+    lib = _lib.load()
+    lib.ehyb_cache_set_options_tag(C.c_uint64(0x1234))
+    with pytest.raises(_lib.EhybError, match="other layout / partitioner options"):
+        api.Layout.cache_load(path, src)
+    tagged = tmp_path / "tagged.ehyb"
+    lay.cache_save(tagged, src, True, a["reorderList"], x, m.y_golden, absAx)
+    again, _ = api.Layout.cache_load(tagged, src)
+    again.free()
+    lib.ehyb_cache_set_options_tag(C.c_uint64(0))
+    with pytest.raises(_lib.EhybError, match="other layout / partitioner options"):
+        api.Layout.cache_load(tagged, src)
     # same parameters accepted, other parameters rejected
     st = lay.stats()
     ok = _lib.Plan(st["nParts"], st["W"], st["ctasPerPart"], 0, 1)

@@ -226,7 +226,9 @@ def test_overflow_stream_is_deterministic(orc, case, blocks, monkeypatch):
     st = lay.stats()
     assert st["nOverflow"] > 0
     s = api.Session(lay)
-    assert s.launches_per_spmv() == 2 * blocks + (0 if st["nnzEll"] + st["nnzRemInSlice"] == 0 else 1)
+    main = 0 if st["nnzEll"] + st["nnzRemInSlice"] == 0 else 1
+    # per column block: the stream kernel, and the carry fix-up if a row of the block spans tiles
+    assert blocks + main <= s.launches_per_spmv() <= 2 * blocks + main
     a = m.arrays()
     ys = []
     for seed in (7, 8):
