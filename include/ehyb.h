@@ -86,7 +86,8 @@ int ehyb_plan(int n, const ehyb_device_info *dev, ehyb_plan_t *out);
  * multi-GPU sessions use): EHYB_KERNEL_PERSISTENT sizes the partitions for the persistent kernel
  * of single-GPU sessions (three or more smaller partitions per SM), see plan.c. */
 int ehyb_plan_kernel(int n, const ehyb_device_info *dev, int kernel, ehyb_plan_t *out);
-/* The plan and the kernel (*kernel, may be NULL) a driver should use for n rows and nnz entries: one
+/* What the reference's reader does in solver_test.c:158-182 / :53-77 (pick W, nParts, kernelPerPart),
+ * for a B200: the plan and the kernel (*kernel, may be NULL) a driver should use for n rows and nnz entries: one
  * partition per SM (staged kernel) when matrix + vectors fit 3/4 of L2, the persistent kernel's plan up
  * to ~40 entries per row, the staged plan beyond (plan.c). */
 int ehyb_plan_auto(int n, int64_t nnz, const ehyb_device_info *dev, ehyb_plan_t *out, int *kernel);
@@ -294,13 +295,14 @@ int ehyb_get_y(ehyb_handle *h, double *y_h);
  * session stream, after `warmup` untimed ones.  *ms_total = elapsed milliseconds.
  * If kernel_ms != NULL it receives the summed duration of the main kernel alone, measured
  * with per-launch events in a second pass of the same length. */
-/* y = A x and *dot_d += x . y in ONE launch (p.Ap of a CG iteration; dot_d in device memory, not
- * zeroed here).  ehyb_spmv_dot_supported: 1 where the product is a single staged / persistent launch. */
+/* y = A x and *dot_d += x . y in ONE launch (p.Ap of a CG iteration - the caller the reference's unused
+ * CG helpers imply, kernel.cu:13-42, :288-321; dot_d in device memory, not zeroed here).  ehyb_spmv_dot_supported: 1 where the product is a single staged / persistent launch. */
 int ehyb_spmv_dot_supported(const ehyb_handle *h);
 int ehyb_spmv_dot(ehyb_handle *h, const double *x_d, double *y_d, double *dot_d);
 int ehyb_spmv_dot_host(ehyb_handle *h, const double *x_h, double *y_h, double *dot_h); /* host vectors, synchronous */
 int ehyb_time_spmv(ehyb_handle *h, int warmup, int iters, float *ms_total, float *kernel_ms);
-/* The same with a COLD L2: `flush_bytes` of scratch memory (>= 2 x the L2 size) are overwritten before
+/* The same with a COLD L2 (L2-resident matrices are reported with and without a flush; the
+ * reference times spmv.cu:72-101 warm only): `flush_bytes` of scratch memory (>= 2 x the L2 size) are overwritten before
  * every product, each product is timed by its own event pair; *ms_sum = their sum over `iters`. */
 int ehyb_time_spmv_flushed(ehyb_handle *h, int warmup, int iters, size_t flush_bytes, float *ms_sum);
 /* Number of kernel launches one product issues (1, or 2 when the overflow list is not empty). */
@@ -434,7 +436,8 @@ int ehyb_mg_allreduce_sum(ehyb_mg_session *s, double *vals_d, int count);
 int ehyb_mg_spmv_dot_supported(const ehyb_mg_session *s);
 int ehyb_mg_spmv_dot(ehyb_mg_session *s, double *x_d, double *y_d, double *dot_d);
 int ehyb_mg_session_ranks(const ehyb_mg_session *s, int *rank, int *nranks);
-/* Distributed (preconditioned) conjugate gradients: ehyb_pcg_solve over the ranks' blocks.  Collective;
+/* Distributed (preconditioned) conjugate gradients: ehyb_pcg_solve over the ranks' blocks (no reference
+ * counterpart; its cb_s.PRECOND / realIter hooks, spmv.h:7-15, :75-78, are what it fills in).  Collective;
  * every rank passes ITS rows of b, of the diagonal and of x (the block's permuted numbering, n local
  * entries).  The dot products are summed over the GPUs by ehyb_mg_allreduce_sum, in rank order: all
  * ranks see the same residuals and stop in the same iteration. */
