@@ -197,6 +197,43 @@ def test_tile_stream_decodes_to_the_row_sums(kind, tg, hub_cap):
         L.load().ehyb_ovfstream_free(C.byref(st))
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_tile_stream_random_lists(seed):
+    """Randomized shapes: row lengths from 0 to several tiles, row starts on lane, group and tile borders,
+    list lengths around multiples of the tile size, random hub capacities - decoded by the kernel's
+    bookkeeping, every non-empty row written exactly once with its sum."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(5, 400))
+    kind = seed % 4
+    if kind == 0:
+        deg = rng.integers(0, 9, n)                                   # short rows: many starts per lane
+    elif kind == 1:
+        deg = np.where(rng.random(n) < 0.1, rng.integers(100, 700, n), rng.integers(0, 3, n))   # a few rows over several tiles
+    elif kind == 2:
+        deg = np.full(n, 4 * int(rng.integers(1, 9)))                 # starts aligned with the lanes' four entries
+    else:
+        deg = rng.integers(0, 70, n)
+    deg[rng.integers(0, n)] += 1                                      # at least one entry
+    total = int(deg.sum())
+    if seed % 3 == 0:                                                 # land exactly on a tile border
+        deg[-1] += (-total) % 128
+    row = np.repeat(np.arange(n, dtype=np.int32), deg)
+    col = rng.integers(0, n, len(row)).astype(np.int32)
+    val = rng.uniform(-1, 1, len(row))
+    hub_cap = int(rng.choice([0, 1, 7, 64, 1000]))
+    rc, st = _build(row, col, val, n, hub_cap, 4)
+    assert rc == 0
+    try:
+        x = rng.uniform(-1, 1, n)
+        y, written = _emulate(st, x, n)
+        ref = np.zeros(n)
+        np.add.at(ref, row, val * x[col])
+        assert np.array_equal(written, deg > 0)
+        assert np.allclose(y, ref, rtol=0, atol=1e-12 * max(1.0, float(np.abs(ref).max())))
+    finally:
+        L.load().ehyb_ovfstream_free(C.byref(st))
+
+
 def test_column_blocks_partition_the_list():
     """ehyb_ovfstream_build_blocked: every entry in exactly one block (by column range), the blocks decoded
     one after the other and added up give the row sums; an empty block has no arrays."""
