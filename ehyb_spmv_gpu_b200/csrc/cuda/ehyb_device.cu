@@ -1287,7 +1287,14 @@ extern "C" int ehyb_mg_p2p_supported(int device, int nranks, int *supported)
     *supported = 0;
     int count = 0;
     CU(cudaGetDeviceCount(&count));
-    if (nranks > 32 || nranks > count) return EHYB_OK; /* one rank per GPU of this node, flags masks are 32-bit */
+    if (nranks > 32) return EHYB_OK; /* flags masks are 32-bit */
+    if (nranks > count) {
+        /* more ranks than GPUs: only for tests ($EHYB_MG_SHARE_DEVICE=1) - several ranks (processes) share a
+         * GPU, reach each other's buffers through CUDA IPC on the SAME device, and their kernels take
+         * turns on it (time slicing): the exchange protocol runs on a one-GPU box, at no useful speed */
+        *supported = env_int("EHYB_MG_SHARE_DEVICE", 0) != 0 && count >= 1;
+        return EHYB_OK;
+    }
     for (int g = 0; g < nranks; ++g) {
         if (g == device) continue;
         int can = 0;
@@ -1426,13 +1433,16 @@ static int p2p_connect_impl(ehyb_mg_session *s, const P2PBlob *B, const int64_t 
             if (recvOffsetOnPeer[g] < 0 || recvOffsetOnPeer[g] + sc > B[g].nHalo)
                 return ehyb_fail(EHYB_ERR_ARG, "p2p connect: %lld entries at %lld do not fit rank %d's halo of %lld", (long long)sc,
                                  (long long)recvOffsetOnPeer[g], g, (long long)B[g].nHalo);
-            int can = 0;
-            CU(cudaDeviceCanAccessPeer(&can, s->h->device, B[g].device));
+            const bool sameDevice = B[g].device == s->h->device; /* ranks sharing a GPU ($EHYB_MG_SHARE_DEVICE, tests) */
+            int can = sameDevice ? 1 : 0;
+            if (!sameDevice) CU(cudaDeviceCanAccessPeer(&can, s->h->device, B[g].device));
             if (!can) return ehyb_fail(EHYB_ERR_PEER, "GPU %d cannot access GPU %d (rank %d) directly", s->h->device, B[g].device, g);
             if (localBase) {
-                cudaError_t e = cudaDeviceEnablePeerAccess(B[g].device, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return ehyb_fail(EHYB_ERR_PEER, "cudaDeviceEnablePeerAccess(%d): %s", B[g].device, cudaGetErrorString(e));
-                cudaGetLastError();
+                if (!sameDevice) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(B[g].device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return ehyb_fail(EHYB_ERR_PEER, "cudaDeviceEnablePeerAccess(%d): %s", B[g].device, cudaGetErrorString(e));
+                    cudaGetLastError();
+                }
                 s->peerBase[g] = localBase[g];
             } else {
                 cudaError_t e = cudaIpcOpenMemHandle(&s->peerBase[g], B[g].handle, cudaIpcMemLazyEnablePeerAccess);

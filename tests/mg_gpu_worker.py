@@ -15,6 +15,11 @@ sys.path.insert(0, str(ROOT))
 os.environ.setdefault("EHYB_MTMETIS_BIN", str(ROOT / "bin" / "ehyb_mtmetis"))
 
 
+def _ndev():
+    import torch
+    return max(1, torch.cuda.device_count())
+
+
 def setup_oneway(rank, world, dist, exchange, n_local=6000):
     """A block lower-bidiagonal random matrix: rank r references its own columns and columns of
     rank r-1 only.  The halo dependencies are ONE-WAY (rank 0 sends and never receives, the last
@@ -37,7 +42,7 @@ def setup_oneway(rank, world, dist, exchange, n_local=6000):
     blk.exchange_lists(dist)
     assert (blk.nHalo > 0) == (rank > 0) and (int(blk.sendCount.sum()) > 0) == (rank < world - 1)
     try:
-        dev = api.device_query(rank)
+        dev = api.device_query(rank % max(1, _ndev()))
     except Exception:                        # the CPU (gloo) tier: nominal B200
         dev = api.device_info_b200()
     pl = api.plan(blk.n, dev)
@@ -69,7 +74,7 @@ def run_grid(rank, world, dist, exchange, grid, level1, products):
     else:
         blk, dec = mg.setup_grid(rank, world, grid, brick, dist, "metis", exchange)
     if exchange == "p2p":
-        blk.create_session_p2p(rank, dist)
+        blk.create_session_p2p(rank % _ndev(), dist)
         assert blk.launches_per_spmv() == 1 + (1 if blk.stats["nOverflow"] else 0)
     else:
         ids = [mg.unique_id() if rank == 0 else None]
@@ -174,10 +179,10 @@ def main():
     exchange, partition = sys.argv[1], sys.argv[2]
     grid = tuple(int(v) for v in sys.argv[3].split("x")) if "x" in sys.argv[3] else None
     products = int(sys.argv[4]) if len(sys.argv) > 4 else 7
-    torch.cuda.set_device(rank)
+    torch.cuda.set_device(rank % _ndev())   # (more ranks than GPUs: EHYB_MG_SHARE_DEVICE=1, ranks share a GPU)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     if exchange == "p2p":
-        assert mg.p2p_supported(rank, world), "no peer access between the GPUs of this box"
+        assert mg.p2p_supported(rank % _ndev(), world), "no peer access between the GPUs of this box"
     if partition.startswith("grid"):
         return run_grid(rank, world, dist, exchange, grid, partition.split("-")[1], min(products, 4))
     if partition == "oneway":
@@ -185,7 +190,7 @@ def main():
     else:
         blk, rowStarts = mg.setup_slab(rank, world, grid, dist, partition, exchange)
     if exchange == "p2p":
-        blk.create_session_p2p(rank, dist)
+        blk.create_session_p2p(rank % _ndev(), dist)
         assert blk.launches_per_spmv() == 1 + (1 if blk.stats["nOverflow"] else 0)
     else:
         ids = [mg.unique_id() if rank == 0 else None]
