@@ -1,7 +1,9 @@
-"""Multi-GPU parity on real GPUs (needs >= 2; run with `gpurun --gpus 2 -- python -m pytest tests -m gpu`).
+"""Multi-GPU parity on real GPUs (`gpurun --gpus 2 -- python -m pytest tests -m gpu`; world 4 needs 4).
 
 One process per GPU runs tests/mg_gpu_worker.py: distributed products through the C ABI with
-both exchanges (peer-memory push inside the main kernel, NCCL send/recv) against the oracle."""
+both exchanges (peer-memory push inside the main kernel, NCCL send/recv) against the oracle.
+On a box with ONE GPU, test_two_ranks_sharing_one_gpu runs two ranks on cuda:0 instead (peer memory
+through CUDA IPC on the same device, kernels time-sliced): the protocol is exercised there too."""
 import os
 import socket
 import subprocess
